@@ -1,0 +1,167 @@
+/*
+ * pfbgrid.h — C ABI of the B200-native w-stacked gridder / degridder and
+ * Hessian apply that replaces pfb-imaging's calls into ducc0.wgridder.
+ *
+ * Every entry point returns 0 on success and a non-zero status otherwise; the
+ * message of the last failure on the calling thread is pfbg_last_error().
+ * Nothing aborts or throws across this boundary.  All pointers are plain host
+ * or device pointers (selected by PFBG_DEVICE_PTRS in `flags`); no torch /
+ * numpy types appear in the signatures.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   - ducc0.wgridder.experimental.vis2dirty as called at
+ *       src/pfb_imaging/operators/gridder.py:78-100, 590-613, 633-656,
+ *       672-695, 709-732, 852-875, 888-911, 990-1013, 1087-1111 and
+ *       src/pfb_imaging/operators/hessian.py:68-89         -> pfbg_grid
+ *   - ducc0.wgridder.experimental.dirty2vis as called at
+ *       operators/gridder.py:128-143, 350-365, 485-503, 972-989, 1067-1085
+ *       and operators/hessian.py:50-66                      -> pfbg_degrid
+ *   - hessian_slice (operators/hessian.py:15-100)           -> pfbg_hessian
+ *   - the per-band pinned state of _BandWorkerImpl.load_band
+ *       (operators/band_worker.py:61-106)                   -> pfbg_bind_vis /
+ *                                                              pfbg_bind_weights
+ *   - _compute_counts / counts_to_weights
+ *       (utils/weighting.py:81-140, 143-208)                -> pfbg_counts /
+ *                                                              pfbg_counts_to_weights
+ */
+#ifndef PFBGRID_H
+#define PFBGRID_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFBG_OK 0
+#define PFBG_ERR_ARG 1
+#define PFBG_ERR_CUDA 2
+#define PFBG_ERR_CUFFT 3
+#define PFBG_ERR_STATE 4
+#define PFBG_ERR_NOMEM 5
+
+/* precision of vis / weights / image and of all grid arithmetic */
+#define PFBG_F32 0 /* vis complex64,  wgt float32, image float32 */
+#define PFBG_F64 1 /* vis complex128, wgt float64, image float64 */
+
+/* flags */
+#define PFBG_HOST_PTRS 0u
+#define PFBG_DEVICE_PTRS 1u   /* data pointers are device pointers; call is asynchronous on `stream` */
+#define PFBG_APPLY_WGT 2u     /* degrid: multiply the output by the bound/passed weights */
+#define PFBG_NO_MASK_ZERO 4u  /* degrid: leave masked output samples untouched instead of zeroing */
+
+typedef struct pfbg_plan pfbg_plan;
+
+/* Everything the host-side plan (pfb-imaging_b200/plan.py) decides. */
+typedef struct pfbg_plan_desc {
+  int32_t precision;     /* PFBG_F32 | PFBG_F64 */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t nx, ny;        /* image size (even) */
+  int32_t nu, nv;        /* oversampled grid (multiples of 32) */
+  int32_t W;             /* kernel support, 4..16 */
+  int32_t nplanes;       /* w-planes (1 when do_wgridding == 0) */
+  int32_t do_wgridding;
+  int32_t divide_by_n;
+  double beta;           /* ES kernel shape */
+  double pixsize_x, pixsize_y;
+  double center_x, center_y; /* after the flip rule */
+  double usign, vsign, wsign; /* +-1 */
+  double w0, dw, nshift;
+  const double* corr_u;  /* host (nx): 1/psihat_u */
+  const double* corr_v;  /* host (ny) */
+  const double* gl_x;    /* host (n_gl): Gauss-Legendre nodes on (0,1) */
+  const double* gl_w;    /* host (n_gl) */
+  int32_t n_gl;
+  int32_t reserved;
+} pfbg_plan_desc;
+
+typedef struct pfbg_plan_info {
+  int64_t nrow;
+  int64_t nvis;          /* nrow * nchan */
+  int64_t nactive;       /* samples with mask != 0 */
+  int64_t grid_bytes;    /* plane stack */
+  int64_t total_bytes;   /* all device allocations of the plan */
+  int32_t nchan;
+  int32_t nplanes;
+  int32_t nu, nv, W;
+  int32_t n_work_items;  /* tile work items of the gridding kernel */
+} pfbg_plan_info;
+
+const char* pfbg_last_error(void);
+int pfbg_version(void);
+int pfbg_device_count(int32_t* count);
+
+int pfbg_plan_create(const pfbg_plan_desc* desc, pfbg_plan** out);
+int pfbg_plan_destroy(pfbg_plan* plan);
+int pfbg_plan_get_info(const pfbg_plan* plan, pfbg_plan_info* info);
+
+/*
+ * Kernel 1: upload uvw (nrow,3) f64, fscale (nchan) f64 = freq/c, optional mask
+ * (nrow,nchan) u8, compute the uv-tile / w-plane bucket of every sample and
+ * sort the active samples by bucket.  Cached in the plan until re-bound.
+ */
+int pfbg_bind_vis(pfbg_plan* plan, const double* uvw, const double* fscale, const uint8_t* mask,
+                  int64_t nrow, int32_t nchan, uint32_t flags, void* stream);
+
+/* Optional cached imaging weights (nrow,nchan) of the plan's precision; NULL unbinds. */
+int pfbg_bind_weights(pfbg_plan* plan, const void* wgt, uint32_t flags, void* stream);
+
+/*
+ * Bit-exact check of kernel 1.  Host outputs; any pointer may be NULL.
+ * iu0/iv0/ip0/key have nvis entries (row-major, also for masked samples);
+ * sorted_idx has nactive entries (flat sample index in bucket order).
+ */
+int pfbg_bin_dump(pfbg_plan* plan, int32_t* iu0, int32_t* iv0, int32_t* ip0, uint64_t* key,
+                  uint32_t* sorted_idx);
+
+/*
+ * Kernel 2 (+4, cuFFT): dirty (nx,ny) = R^H (wgt * mask * vis).
+ * vis has element strides (vis_rs, vis_cs) (both 0 = one broadcast value);
+ * wgt may be NULL (then the bound weights, if any, are used).
+ */
+int pfbg_grid(pfbg_plan* plan, const void* vis, int64_t vis_rs, int64_t vis_cs, const void* wgt,
+              void* dirty, uint32_t flags, void* stream);
+
+/* Kernel 3 (+4, cuFFT): vis (nrow,nchan) contiguous = R dirty; masked samples are zeroed. */
+int pfbg_degrid(pfbg_plan* plan, const void* dirty, void* vis, const void* wgt, uint32_t flags,
+                void* stream);
+
+/*
+ * Fused Hessian apply (operators/hessian.py:15-100):
+ *   out = beam * R^H W M R (beam * x) / wsum + eta * x
+ * beam may be NULL, wsum <= 0 means "no division", eta == 0 means "no ridge".
+ * Uses the bound weights (or none).  Model visibilities never leave the device.
+ */
+int pfbg_hessian(pfbg_plan* plan, const void* x, const void* beam, double wsum, double eta,
+                 void* out, uint32_t flags, void* stream);
+
+/* Seconds spent in the phases of the last grid/degrid/hessian call when profiling is on. */
+int pfbg_set_profiling(pfbg_plan* plan, int32_t on);
+int pfbg_get_timings(pfbg_plan* plan, float* ms, int32_t n, int32_t* n_written);
+
+/* Number of kernels this library has launched on the calling process so far. */
+int64_t pfbg_launch_count(void);
+
+/*
+ * Imaging-weight kernels (utils/weighting.py:81-140, 143-208).
+ * counts (ncorr,nx,ny) of `precision`; wgt (ncorr,nrow,nchan); mask (nrow,nchan) u8.
+ */
+int pfbg_counts(int32_t precision, int32_t device, const double* uvw, const double* freq,
+                const uint8_t* mask, const void* wgt, int64_t nrow, int32_t nchan, int32_t ncorr,
+                int32_t nx, int32_t ny, double cell_x, double cell_y, double usign, double vsign,
+                void* counts, uint32_t flags, void* stream);
+/* Bit-exact check of the counts cell index: cells (nrow,nchan,2) int32 host output,
+ * (-1,-1) for masked / off-grid samples.  Host pointers only. */
+int pfbg_counts_cells(int32_t device, const double* uvw, const double* freq, const uint8_t* mask,
+                      int64_t nrow, int32_t nchan, int32_t nx, int32_t ny, double cell_x, double cell_y,
+                      double usign, double vsign, int32_t* cells);
+int pfbg_counts_to_weights(int32_t precision, int32_t device, void* counts, const double* uvw,
+                           const double* freq, void* wgt, const uint8_t* mask, int64_t nrow,
+                           int32_t nchan, int32_t ncorr, int32_t nx, int32_t ny, double cell_x,
+                           double cell_y, double robust, double usign, double vsign, uint32_t flags,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFBGRID_H */

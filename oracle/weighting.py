@@ -1,0 +1,90 @@
+"""TEST INFRASTRUCTURE ONLY — numpy restatement of the imaging-weight functions.
+
+Follows /root/reference/src/pfb_imaging/utils/weighting.py:
+  compute_counts      <- _compute_counts      (:81-140)
+  counts_to_weights   <- counts_to_weights    (:143-208)
+  filter_extreme_counts (:212-226), box_sum_counts (:229-254)
+Pinned by tests/golden/weighting.npz, which was produced by executing those
+reference functions (numba) in the build container (tests/golden/make_golden.py).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may import this.
+"""
+
+import numpy as np
+from scipy.ndimage import uniform_filter
+
+LIGHTSPEED = 299792458.0
+
+
+def uv_cells(uvw, freq, mask, nx, ny, cell_x, cell_y, usign=1.0, vsign=-1.0):
+    """(nrow,nchan) int32 cell indices, -1 where masked or off the grid (weighting.py:103-135)."""
+    u_cell = 1 / (nx * cell_x)
+    umax = np.abs(1 / cell_x / 2)
+    v_cell = 1 / (ny * cell_y)
+    vmax = np.abs(1 / cell_y / 2)
+    cn = np.asarray(freq, dtype=np.float64) / LIGHTSPEED
+    u = np.asarray(uvw)[:, 0:1] * cn[None, :] * usign
+    v = np.asarray(uvw)[:, 1:2] * cn[None, :] * vsign
+    neg = v < 0
+    u = np.where(neg, -u, u)
+    v = np.where(neg, -v, v)
+    ug = np.floor((u + umax) / u_cell)
+    vg = np.floor((v + vmax) / v_cell)
+    ok = (ug >= 0) & (ug < nx) & (vg >= 0) & (vg < ny)
+    if mask is not None:
+        ok &= np.asarray(mask) != 0
+    ui = np.where(ok, ug, -1).astype(np.int32)
+    vi = np.where(ok, vg, -1).astype(np.int32)
+    return ui, vi
+
+
+def compute_counts(uvw, freq, mask, wgt, nx, ny, cell_x, cell_y, dtype, ngrid=1, usign=1.0, vsign=-1.0):
+    ui, vi = uv_cells(uvw, freq, mask, nx, ny, cell_x, cell_y, usign, vsign)
+    ok = ui >= 0
+    ncorr = wgt.shape[0]
+    counts = np.zeros((ncorr, nx, ny), dtype=dtype)
+    for c in range(ncorr):
+        np.add.at(counts[c], (ui[ok], vi[ok]), wgt[c][ok])
+    return counts
+
+
+def counts_to_weights(counts, uvw, freq, weight, mask, nx, ny, cell_x, cell_y, robust, usign=1.0, vsign=-1.0):
+    """In place on `weight` AND `counts`, like the reference."""
+    if not counts.any():
+        return weight
+    ncorr = weight.shape[0]
+    if robust > -2:
+        numsqrt = 5 * 10 ** (-robust)
+        avgwnum = (counts.astype(np.float64) ** 2).sum(axis=(1, 2))
+        avgwden = counts.astype(np.float64).sum(axis=(1, 2))
+        ssq = (numsqrt * numsqrt * avgwden / avgwnum).astype(weight.dtype)
+        counts *= ssq[:, None, None]
+        counts += 1
+    ui, vi = uv_cells(uvw, freq, mask, nx, ny, cell_x, cell_y, usign, vsign)
+    ok = ui >= 0
+    for c in range(ncorr):
+        cv = counts[c][ui[ok], vi[ok]]
+        w = weight[c][ok]
+        pos = cv > 0
+        w[pos] = w[pos] / cv[pos]
+        weight[c][ok] = w
+    return weight
+
+
+def filter_extreme_counts(counts, level=10.0):
+    if not level:
+        return counts
+    ic, ix, iy = np.where(counts > 0)
+    cnts = counts[ic, ix, iy]
+    med = np.median(cnts)
+    counts[ic, ix, iy] = np.maximum(cnts, med / level)
+    return counts
+
+
+def box_sum_counts(counts, npix_super):
+    if npix_super is None or npix_super <= 0:
+        return counts
+    size = 2 * npix_super + 1
+    out = np.empty_like(counts)
+    for c in range(counts.shape[0]):
+        out[c] = uniform_filter(counts[c], size=size, mode="constant", cval=0.0) * (size * size)
+    return out

@@ -1,0 +1,118 @@
+// Shared device helpers of the B200 w-gridder kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PFBG_TILE 16
+#define PFBG_MAXW 16
+
+template <typename T> struct cplx_of;
+template <> struct cplx_of<float> { using type = float2; };
+template <> struct cplx_of<double> { using type = double2; };
+
+// Geometry + kernel parameters, passed by value to every kernel.
+struct GParams {
+  int nx, ny, nu, nv, W, nplanes, nchan;
+  int do_wgridding, divide_by_n;
+  double beta, pixsize_x, pixsize_y, center_x, center_y;
+  double usign, vsign, wsign, w0, dw, nshift;
+  int ntile_u, ntile_v;
+};
+
+// ---------------------------------------------------------------------------
+// Bit-exact coordinate arithmetic (Appendix B of SURVEY.md / oracle.bin_indices):
+// every operation is one correctly rounded IEEE fp64 op, no FMA contraction.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void axis_coord(double t, double pix, int n, int W, double& g, int& i0) {
+  double x = __dmul_rn(t, pix);
+  double f = __dsub_rn(x, floor(x));
+  g = __dadd_rn(__dmul_rn(f, (double)n), 0.5 * (double)n);
+  if (g >= (double)n) g = __dsub_rn(g, (double)n);
+  i0 = (int)floor(__dsub_rn(g, 0.5 * (double)W)) + 1;
+}
+
+struct VisCoord {
+  double ut, vt, wt;  // wavelengths, signs applied
+  double gu, gv, gw;  // grid coordinates
+  int iu0, iv0, ip0;  // first touched cell / plane
+};
+
+__device__ __forceinline__ VisCoord vis_coord(const GParams& p, const double* __restrict__ uvw,
+                                              const double* __restrict__ fscale, int64_t row, int chan) {
+  VisCoord c;
+  double s = fscale[chan];
+  c.ut = __dmul_rn(__dmul_rn(p.usign, uvw[3 * row + 0]), s);
+  c.vt = __dmul_rn(__dmul_rn(p.vsign, uvw[3 * row + 1]), s);
+  c.wt = __dmul_rn(__dmul_rn(p.wsign, uvw[3 * row + 2]), s);
+  axis_coord(c.ut, p.pixsize_x, p.nu, p.W, c.gu, c.iu0);
+  axis_coord(c.vt, p.pixsize_y, p.nv, p.W, c.gv, c.iv0);
+  if (p.do_wgridding) {
+    c.gw = __ddiv_rn(__dsub_rn(c.wt, p.w0), p.dw);
+    int ip = (int)floor(__dsub_rn(c.gw, 0.5 * (double)p.W)) + 1;
+    int hi = p.nplanes - p.W;
+    c.ip0 = ip < 0 ? 0 : (ip > hi ? hi : ip);
+  } else {
+    c.gw = 0.0;
+    c.ip0 = 0;
+  }
+  return c;
+}
+
+__device__ __forceinline__ int wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+__device__ __forceinline__ uint64_t bucket_key(const GParams& p, const VisCoord& c) {
+  int iuw = wrap(c.iu0, p.nu), ivw = wrap(c.iv0, p.nv);
+  uint64_t tile = (uint64_t)(iuw / PFBG_TILE) * (uint64_t)p.ntile_v + (uint64_t)(ivw / PFBG_TILE);
+  uint64_t fine = (uint64_t)((iuw % PFBG_TILE) * PFBG_TILE + (ivw % PFBG_TILE));
+  return (tile * (uint64_t)p.nplanes + (uint64_t)c.ip0) * (uint64_t)(PFBG_TILE * PFBG_TILE) + fine;
+}
+
+// ES kernel phi(x) = exp(beta (sqrt(1-x^2) - 1)), zero outside |x| <= 1.
+__device__ __forceinline__ float es_eval(float x, float beta) {
+  float a = (1.0f - x) * (1.0f + x);
+  return a < 0.0f ? 0.0f : expf(beta * (sqrtf(a) - 1.0f));
+}
+__device__ __forceinline__ double es_eval(double x, double beta) {
+  double a = (1.0 - x) * (1.0 + x);
+  return a < 0.0 ? 0.0 : exp(beta * (sqrt(a) - 1.0));
+}
+
+// weight of cell (i0 + j) for coordinate g
+template <typename T>
+__device__ __forceinline__ T tap(double g, int i0, int j, int W, T beta) {
+  double x = ((double)(i0 + j) - g) * (2.0 / (double)W);
+  return es_eval((T)x, beta);
+}
+
+// e^{2 pi i t} with the fp64 phase reduced to [-1/2, 1/2] turns first
+__device__ __forceinline__ void cis_turns(double t, float& c, float& s) {
+  t -= rint(t);
+  sincospif(2.0f * (float)t, &s, &c);
+}
+__device__ __forceinline__ void cis_turns(double t, double& c, double& s) {
+  t -= rint(t);
+  sincospi(2.0 * t, &s, &c);
+}
+
+// phase (turns) of the centre shift and the n-1 shift for one sample
+__device__ __forceinline__ double vis_phase_turns(const GParams& p, const VisCoord& c) {
+  double t = c.ut * p.center_x + c.vt * p.center_y;
+  if (p.do_wgridding) t += c.wt * p.nshift;
+  return t;
+}
+
+// n - 1 for pixel (i, j), numerically stable
+__device__ __forceinline__ double pixel_nm1(const GParams& p, int i, int j) {
+  double l = p.center_x + (double)(i - p.nx / 2) * p.pixsize_x;
+  double m = p.center_y + (double)(j - p.ny / 2) * p.pixsize_y;
+  double r2 = l * l + m * m;
+  return -r2 / (sqrt(1.0 - r2) + 1.0);
+}
+
+__device__ __forceinline__ void atomic_add_c(float2* a, float re, float im) {
+  atomicAdd(a, make_float2(re, im));  // sm_90+: one vector RED
+}
+__device__ __forceinline__ void atomic_add_c(double2* a, double re, double im) {
+  atomicAdd(&a->x, re);
+  atomicAdd(&a->y, im);
+}

@@ -1,0 +1,747 @@
+// C-ABI implementation (include/pfbgrid.h): plan, binding/sort, cuFFT plumbing
+// and launch sequencing of the sm_100a kernels in kernels.cuh / grid_tile.cuh.
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <atomic>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pfbgrid.h"
+#include "kernels.cuh"
+#include "weighting.cuh"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                           \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(PFBG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+#define CKFFT(call)                                                                        \
+  do {                                                                                     \
+    cufftResult r_ = (call);                                                               \
+    if (r_ != CUFFT_SUCCESS)                                                               \
+      return fail(PFBG_ERR_CUFFT, "%s failed: cufft status %d (%s:%d)", #call, (int)r_,    \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+#define CKRC(call)              \
+  do {                          \
+    int rc_ = (call);           \
+    if (rc_ != PFBG_OK) return rc_; \
+  } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+extern "C" const char* pfbg_last_error(void) { return g_err.c_str(); }
+extern "C" int pfbg_version(void) { return 100; }
+extern "C" int64_t pfbg_launch_count(void) { return g_launches.load(); }
+extern "C" int pfbg_device_count(int32_t* count) {
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  *count = n;
+  return PFBG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct pfbg_plan {
+  int precision = 0, device = 0;
+  GParams gp{};
+  int n_gl = 0;
+  // device state
+  DevBuf corr;                 // (nx,ny) T
+  DevBuf grid;                 // (nplanes,nu,nv) C
+  DevBuf uvw, fscale, mask;    // bound geometry
+  DevBuf wgt;                  // bound weights (nrow,nchan) T
+  DevBuf sorted_idx;           // (nactive) u32
+  DevBuf mvis;                 // (nactive) C, Hessian model vis in bucket order
+  DevBuf img_in, img_out, img_beam;  // staging for host-pointer calls
+  DevBuf vis_stage, wgt_stage;
+  DevBuf flag;
+  cufftHandle fft = 0;
+  bool fft_ok = false;
+  size_t fft_work = 0;
+  int64_t nrow = 0, nvis = 0, nactive = 0;
+  bool bound = false, has_mask = false, has_wgt = false;
+  size_t total_bytes = 0;
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev[8]{};
+  bool ev_ok = false;
+  int n_ev = 0;
+};
+
+static int dev_alloc(pfbg_plan* pl, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return PFBG_OK;
+  if (b.p) {
+    cudaFree(b.p);
+    pl->total_bytes -= b.bytes;
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  if (bytes == 0) return PFBG_OK;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    return fail(PFBG_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  }
+  b.bytes = bytes;
+  pl->total_bytes += bytes;
+  return PFBG_OK;
+}
+static void dev_free(pfbg_plan* pl, DevBuf& b) {
+  if (b.p) {
+    cudaFree(b.p);
+    pl->total_bytes -= b.bytes;
+  }
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+static inline size_t real_bytes(const pfbg_plan* pl) { return pl->precision == PFBG_F32 ? 4 : 8; }
+
+extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
+  if (!pl) return PFBG_OK;
+  cudaSetDevice(pl->device);
+  if (pl->fft_ok) cufftDestroy(pl->fft);
+  DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx,
+                   &pl->mvis, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
+                   &pl->flag};
+  for (DevBuf* b : all) dev_free(pl, *b);
+  if (pl->ev_ok)
+    for (auto& e : pl->ev) cudaEventDestroy(e);
+  delete pl;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
+  if (!d || !out) return fail(PFBG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (d->precision != PFBG_F32 && d->precision != PFBG_F64) return fail(PFBG_ERR_ARG, "bad precision");
+  if (d->nx <= 0 || d->ny <= 0 || (d->nx & 1) || (d->ny & 1)) return fail(PFBG_ERR_ARG, "nx, ny must be positive and even");
+  if (d->W < 4 || d->W > PFBG_MAXW) return fail(PFBG_ERR_ARG, "kernel support W=%d outside [4,%d]", d->W, PFBG_MAXW);
+  if (d->nu % (2 * PFBG_TILE) || d->nv % (2 * PFBG_TILE)) return fail(PFBG_ERR_ARG, "nu, nv must be multiples of %d", 2 * PFBG_TILE);
+  if (d->nu < d->nx + d->W || d->nv < d->ny + d->W) return fail(PFBG_ERR_ARG, "grid smaller than image + support");
+  if (d->nplanes < 1 || (d->do_wgridding && d->nplanes < d->W)) return fail(PFBG_ERR_ARG, "nplanes=%d too small for W=%d", d->nplanes, d->W);
+  if (!d->do_wgridding && d->nplanes != 1) return fail(PFBG_ERR_ARG, "nplanes must be 1 without w-gridding");
+  if (!d->corr_u || !d->corr_v) return fail(PFBG_ERR_ARG, "missing correction vectors");
+  if (d->do_wgridding && (!d->gl_x || !d->gl_w || d->n_gl <= 0 || !(d->dw > 0))) return fail(PFBG_ERR_ARG, "missing quadrature / dw for w-gridding");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (d->device < 0 || d->device >= ndev) return fail(PFBG_ERR_ARG, "device %d out of range (%d visible)", d->device, ndev);
+  CK(cudaSetDevice(d->device));
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10) return fail(PFBG_ERR_STATE, "device %d is sm_%d%d; this library is built for sm_100a only", d->device, prop.major, prop.minor);
+  }
+
+  pfbg_plan* pl = new pfbg_plan();
+  pl->precision = d->precision;
+  pl->device = d->device;
+  GParams& g = pl->gp;
+  g.nx = d->nx; g.ny = d->ny; g.nu = d->nu; g.nv = d->nv; g.W = d->W; g.nplanes = d->nplanes;
+  g.nchan = 0;
+  g.do_wgridding = d->do_wgridding; g.divide_by_n = d->divide_by_n;
+  g.beta = d->beta; g.pixsize_x = d->pixsize_x; g.pixsize_y = d->pixsize_y;
+  g.center_x = d->center_x; g.center_y = d->center_y;
+  g.usign = d->usign; g.vsign = d->vsign; g.wsign = d->wsign;
+  g.w0 = d->w0; g.dw = d->dw; g.nshift = d->nshift;
+  g.ntile_u = d->nu / PFBG_TILE; g.ntile_v = d->nv / PFBG_TILE;
+  pl->n_gl = d->n_gl;
+
+  auto bail = [&](int rc) { pfbg_plan_destroy(pl); return rc; };
+  const size_t rb = real_bytes(pl);
+  int rc;
+  if ((rc = dev_alloc(pl, pl->corr, (size_t)g.nx * g.ny * rb))) return bail(rc);
+  if ((rc = dev_alloc(pl, pl->grid, (size_t)g.nplanes * g.nu * g.nv * 2 * rb))) return bail(rc);
+  if ((rc = dev_alloc(pl, pl->flag, 64))) return bail(rc);
+
+  // correction image
+  {
+    DevBuf cu, cv, gx, gw;
+    std::vector<double> glw;
+    auto cleanup = [&]() { dev_free(pl, cu); dev_free(pl, cv); dev_free(pl, gx); dev_free(pl, gw); };
+    if ((rc = dev_alloc(pl, cu, g.nx * sizeof(double))) || (rc = dev_alloc(pl, cv, g.ny * sizeof(double)))) { cleanup(); return bail(rc); }
+    cudaMemcpy(cu.p, d->corr_u, g.nx * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(cv.p, d->corr_v, g.ny * sizeof(double), cudaMemcpyHostToDevice);
+    int ngl = 0;
+    if (g.do_wgridding) {
+      ngl = d->n_gl;
+      glw.resize(ngl);
+      // psihat(xi) = (W/2) int_{-1}^{1} phi cos = W * sum_k w_k phi(x_k) cos(pi W xi x_k) over the half interval
+      for (int k = 0; k < ngl; ++k) {
+        double x = d->gl_x[k];
+        glw[k] = (double)g.W * d->gl_w[k] * exp(g.beta * (sqrt((1.0 - x) * (1.0 + x)) - 1.0));
+      }
+      if ((rc = dev_alloc(pl, gx, ngl * sizeof(double))) || (rc = dev_alloc(pl, gw, ngl * sizeof(double)))) { cleanup(); return bail(rc); }
+      cudaMemcpy(gx.p, d->gl_x, ngl * sizeof(double), cudaMemcpyHostToDevice);
+      cudaMemcpy(gw.p, glw.data(), ngl * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    dim3 blk(128), grd((g.ny + 127) / 128, g.nx);
+    if (pl->precision == PFBG_F32)
+      k_corr_init<float><<<grd, blk>>>(g, (const double*)cu.p, (const double*)cv.p, (const double*)gx.p, (const double*)gw.p, ngl, (float*)pl->corr.p);
+    else
+      k_corr_init<double><<<grd, blk>>>(g, (const double*)cu.p, (const double*)cv.p, (const double*)gx.p, (const double*)gw.p, ngl, (double*)pl->corr.p);
+    LAUNCHED();
+    cudaError_t e = cudaDeviceSynchronize();
+    cleanup();
+    if (e != cudaSuccess) { fail(PFBG_ERR_CUDA, "correction kernel failed: %s", cudaGetErrorString(e)); return bail(PFBG_ERR_CUDA); }
+  }
+
+  // batched 2-D FFT over the plane stack
+  {
+    cufftResult r = cufftCreate(&pl->fft);
+    if (r != CUFFT_SUCCESS) { fail(PFBG_ERR_CUFFT, "cufftCreate failed (%d)", (int)r); return bail(PFBG_ERR_CUFFT); }
+    pl->fft_ok = true;
+    long long n[2] = {g.nu, g.nv};
+    size_t ws = 0;
+    r = cufftMakePlanMany64(pl->fft, 2, n, nullptr, 1, 0, nullptr, 1, 0,
+                            pl->precision == PFBG_F32 ? CUFFT_C2C : CUFFT_Z2Z, g.nplanes, &ws);
+    if (r != CUFFT_SUCCESS) { fail(PFBG_ERR_CUFFT, "cufftMakePlanMany64(%d x %d, batch %d) failed (%d)", g.nu, g.nv, g.nplanes, (int)r); return bail(PFBG_ERR_CUFFT); }
+    pl->fft_work = ws;
+    pl->total_bytes += ws;
+  }
+  *out = pl;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_plan_get_info(const pfbg_plan* pl, pfbg_plan_info* info) {
+  if (!pl || !info) return fail(PFBG_ERR_ARG, "null argument");
+  memset(info, 0, sizeof *info);
+  info->nrow = pl->nrow; info->nvis = pl->nvis; info->nactive = pl->nactive;
+  info->grid_bytes = (int64_t)pl->grid.bytes; info->total_bytes = (int64_t)pl->total_bytes;
+  info->nchan = pl->gp.nchan; info->nplanes = pl->gp.nplanes;
+  info->nu = pl->gp.nu; info->nv = pl->gp.nv; info->W = pl->gp.W;
+  info->n_work_items = 0;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_set_profiling(pfbg_plan* pl, int32_t on) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  CK(cudaSetDevice(pl->device));
+  if (on && !pl->ev_ok) {
+    for (auto& e : pl->ev) CK(cudaEventCreate(&e));
+    pl->ev_ok = true;
+  }
+  pl->profiling = on != 0;
+  pl->n_ev = 0;
+  return PFBG_OK;
+}
+static inline void mark(pfbg_plan* pl, cudaStream_t s) {
+  if (pl->profiling && pl->n_ev < 8) cudaEventRecord(pl->ev[pl->n_ev++], s);
+}
+extern "C" int pfbg_get_timings(pfbg_plan* pl, float* ms, int32_t n, int32_t* n_written) {
+  if (!pl || !ms || !n_written) return fail(PFBG_ERR_ARG, "null argument");
+  *n_written = 0;
+  if (!pl->profiling || pl->n_ev < 2) return PFBG_OK;
+  CK(cudaSetDevice(pl->device));
+  CK(cudaEventSynchronize(pl->ev[pl->n_ev - 1]));
+  for (int i = 0; i + 1 < pl->n_ev && i < n; ++i) {
+    CK(cudaEventElapsedTime(&ms[i], pl->ev[i], pl->ev[i + 1]));
+    *n_written = i + 1;
+  }
+  return PFBG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static int fetch(pfbg_plan* pl, DevBuf& stage, const void* src, size_t bytes, bool dev, cudaStream_t s,
+                 const void** out) {
+  // device pointers are used in place; host pointers are staged on the stream
+  if (dev) { *out = src; return PFBG_OK; }
+  CKRC(dev_alloc(pl, stage, bytes));
+  CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, s));
+  *out = stage.p;
+  return PFBG_OK;
+}
+
+static int fft_exec(pfbg_plan* pl, cudaStream_t s, int dir) {
+  CKFFT(cufftSetStream(pl->fft, s));
+  if (pl->precision == PFBG_F32)
+    CKFFT(cufftExecC2C(pl->fft, (cufftComplex*)pl->grid.p, (cufftComplex*)pl->grid.p, dir));
+  else
+    CKFFT(cufftExecZ2Z(pl->fft, (cufftDoubleComplex*)pl->grid.p, (cufftDoubleComplex*)pl->grid.p, dir));
+  LAUNCHED();
+  return PFBG_OK;
+}
+
+static int grid_blocks(const pfbg_plan* pl, int64_t nact) {
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
+  int64_t want = (nact + 7) / 8;
+  int64_t cap = (int64_t)sm * 8;  // 8 resident CTAs of 256 threads per SM
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------
+// kernel 1: bind + bin + sort
+// ---------------------------------------------------------------------------
+extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fscale, const uint8_t* mask,
+                             int64_t nrow, int32_t nchan, uint32_t flags, void* stream) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  if (nrow < 0 || nchan <= 0) return fail(PFBG_ERR_ARG, "bad nrow/nchan");
+  if ((!uvw && nrow > 0) || !fscale) return fail(PFBG_ERR_ARG, "null uvw/fscale");
+  int64_t nvis = nrow * (int64_t)nchan;
+  if (nvis >= (int64_t)UINT32_MAX) return fail(PFBG_ERR_ARG, "more than 2^32-1 samples in one binding");
+  CK(cudaSetDevice(pl->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  pl->bound = false;
+  pl->gp.nchan = nchan;
+  pl->nrow = nrow; pl->nvis = nvis; pl->nactive = 0;
+  pl->has_wgt = false;
+  CKRC(dev_alloc(pl, pl->uvw, (size_t)(nrow > 0 ? nrow : 1) * 3 * sizeof(double)));
+  CKRC(dev_alloc(pl, pl->fscale, (size_t)nchan * sizeof(double)));
+  if (nrow > 0) CK(cudaMemcpyAsync(pl->uvw.p, uvw, (size_t)nrow * 3 * sizeof(double), kind, s));
+  CK(cudaMemcpyAsync(pl->fscale.p, fscale, (size_t)nchan * sizeof(double), kind, s));
+  pl->has_mask = mask != nullptr;
+  if (mask && nvis > 0) {
+    CKRC(dev_alloc(pl, pl->mask, (size_t)nvis));
+    CK(cudaMemcpyAsync(pl->mask.p, mask, (size_t)nvis, kind, s));
+  }
+  if (nvis == 0) {
+    pl->bound = true;
+    CK(cudaStreamSynchronize(s));
+    return PFBG_OK;
+  }
+  const GParams& g = pl->gp;
+  // key width
+  uint64_t maxkey = (uint64_t)g.ntile_u * g.ntile_v * (uint64_t)g.nplanes * (PFBG_TILE * PFBG_TILE);
+  int bits = 1;
+  while ((1ull << bits) <= maxkey) ++bits;  // inactive key = maxkey needs `bits` bits
+  DevBuf keys_a, keys_b, vals_a, vals_b, tmp;
+  auto cleanup = [&]() { dev_free(pl, keys_a); dev_free(pl, keys_b); dev_free(pl, vals_a); dev_free(pl, vals_b); dev_free(pl, tmp); };
+  int rc;
+  if ((rc = dev_alloc(pl, keys_a, nvis * 8)) || (rc = dev_alloc(pl, keys_b, nvis * 8)) ||
+      (rc = dev_alloc(pl, vals_a, nvis * 4)) || (rc = dev_alloc(pl, vals_b, nvis * 4))) { cleanup(); return rc; }
+  CK(cudaMemsetAsync(pl->flag.p, 0, 64, s));
+  {
+    int blk = 256;
+    int64_t grd = (nvis + blk - 1) / blk;
+    k_bin<<<(unsigned)grd, blk, 0, s>>>(g, (const double*)pl->uvw.p, (const double*)pl->fscale.p,
+                                        pl->has_mask ? (const uint8_t*)pl->mask.p : nullptr, nvis, maxkey,
+                                        (uint64_t*)keys_a.p, (uint32_t*)vals_a.p, (unsigned long long*)pl->flag.p);
+    LAUNCHED();
+  }
+  size_t tmp_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint64_t*)keys_a.p, (uint64_t*)keys_b.p,
+                                                  (const uint32_t*)vals_a.p, (uint32_t*)vals_b.p, nvis, 0, bits, s);
+  if (e != cudaSuccess) { cleanup(); return fail(PFBG_ERR_CUDA, "cub sort sizing failed: %s", cudaGetErrorString(e)); }
+  if ((rc = dev_alloc(pl, tmp, tmp_bytes ? tmp_bytes : 16))) { cleanup(); return rc; }
+  e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, (const uint64_t*)keys_a.p, (uint64_t*)keys_b.p,
+                                      (const uint32_t*)vals_a.p, (uint32_t*)vals_b.p, nvis, 0, bits, s);
+  LAUNCHED();
+  if (e != cudaSuccess) { cleanup(); return fail(PFBG_ERR_CUDA, "cub sort failed: %s", cudaGetErrorString(e)); }
+  unsigned long long nact = 0;
+  e = cudaMemcpyAsync(&nact, pl->flag.p, sizeof nact, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { cleanup(); return fail(PFBG_ERR_CUDA, "binning failed: %s", cudaGetErrorString(e)); }
+  pl->nactive = (int64_t)nact;
+  if ((rc = dev_alloc(pl, pl->sorted_idx, (size_t)(nact ? nact : 1) * 4))) { cleanup(); return rc; }
+  if (nact) {
+    e = cudaMemcpyAsync(pl->sorted_idx.p, vals_b.p, (size_t)nact * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cleanup(); return fail(PFBG_ERR_CUDA, "copy of sorted order failed: %s", cudaGetErrorString(e)); }
+  }
+  cleanup();
+  pl->bound = true;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_bind_weights(pfbg_plan* pl, const void* wgt, uint32_t flags, void* stream) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  if (!pl->bound) return fail(PFBG_ERR_STATE, "bind_vis must be called before bind_weights");
+  CK(cudaSetDevice(pl->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!wgt || pl->nvis == 0) { pl->has_wgt = false; return PFBG_OK; }
+  size_t bytes = (size_t)pl->nvis * real_bytes(pl);
+  CKRC(dev_alloc(pl, pl->wgt, bytes));
+  CK(cudaMemcpyAsync(pl->wgt.p, wgt, bytes, (flags & PFBG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  pl->has_wgt = true;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_bin_dump(pfbg_plan* pl, int32_t* iu0, int32_t* iv0, int32_t* ip0, uint64_t* key,
+                             uint32_t* sorted_idx) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  CK(cudaSetDevice(pl->device));
+  int64_t n = pl->nvis;
+  if (n > 0 && (iu0 || iv0 || ip0 || key)) {
+    DevBuf a, b, c, k;
+    auto cleanup = [&]() { dev_free(pl, a); dev_free(pl, b); dev_free(pl, c); dev_free(pl, k); };
+    int rc;
+    if ((rc = dev_alloc(pl, a, n * 4)) || (rc = dev_alloc(pl, b, n * 4)) || (rc = dev_alloc(pl, c, n * 4)) ||
+        (rc = dev_alloc(pl, k, n * 8))) { cleanup(); return rc; }
+    k_bin_dump<<<(unsigned)((n + 255) / 256), 256>>>(pl->gp, (const double*)pl->uvw.p, (const double*)pl->fscale.p, n,
+                                                     (int32_t*)a.p, (int32_t*)b.p, (int32_t*)c.p, (uint64_t*)k.p);
+    LAUNCHED();
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && iu0) e = cudaMemcpy(iu0, a.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && iv0) e = cudaMemcpy(iv0, b.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ip0) e = cudaMemcpy(ip0, c.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && key) e = cudaMemcpy(key, k.p, n * 8, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "bin dump failed: %s", cudaGetErrorString(e));
+  }
+  if (sorted_idx && pl->nactive > 0)
+    CK(cudaMemcpy(sorted_idx, pl->sorted_idx.p, (size_t)pl->nactive * 4, cudaMemcpyDeviceToHost));
+  return PFBG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// direction drivers (templated on precision)
+// ---------------------------------------------------------------------------
+template <typename T>
+static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs, int64_t cs, const void* wgt,
+                      int vis_sorted, int apply_phase) {
+  using C = typename cplx_of<T>::type;
+  CK(cudaMemsetAsync(pl->grid.p, 0, pl->grid.bytes, s));
+  if (pl->nactive > 0) {
+    k_grid_direct<T><<<grid_blocks(pl, pl->nactive), 256, 0, s>>>(
+        pl->gp, (const double*)pl->uvw.p, (const double*)pl->fscale.p, (const uint32_t*)pl->sorted_idx.p, pl->nactive,
+        (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p, vis_sorted, apply_phase);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
+  return PFBG_OK;
+}
+
+template <typename T>
+static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_out, void* out_sorted, int apply_phase) {
+  using C = typename cplx_of<T>::type;
+  if (pl->nactive > 0) {
+    k_degrid_direct<T><<<grid_blocks(pl, pl->nactive), 256, 0, s>>>(
+        pl->gp, (const double*)pl->uvw.p, (const double*)pl->fscale.p, (const uint32_t*)pl->sorted_idx.p, pl->nactive,
+        (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out, (C*)out_sorted, apply_phase);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
+  return PFBG_OK;
+}
+
+template <typename T>
+static int run_img2grid(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam) {
+  using C = typename cplx_of<T>::type;
+  const GParams& g = pl->gp;
+  dim3 blk(256), grd((g.nv + 255) / 256, g.nu);
+  k_img2grid<T><<<grd, blk, 0, s>>>(g, (const T*)x, (const T*)beam, (const T*)pl->corr.p, (C*)pl->grid.p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+
+template <typename T>
+static int run_grid2img(pfbg_plan* pl, cudaStream_t s, const void* beam, const void* xin, double inv_wsum, double eta,
+                        void* out) {
+  using C = typename cplx_of<T>::type;
+  const GParams& g = pl->gp;
+  dim3 blk(256), grd((g.ny + 255) / 256, g.nx);
+  k_grid2img<T><<<grd, blk, 0, s>>>(g, (const C*)pl->grid.p, (const T*)pl->corr.p, (const T*)beam, (const T*)xin,
+                                    inv_wsum, eta, (T*)out);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+
+#define DISPATCH(fn, ...) (pl->precision == PFBG_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t vis_cs, const void* wgt,
+                         void* dirty, uint32_t flags, void* stream) {
+  if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
+  if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (!vis && pl->nvis > 0) return fail(PFBG_ERR_ARG, "null vis");
+  CK(cudaSetDevice(pl->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = real_bytes(pl);
+  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  pl->n_ev = 0;
+  mark(pl, s);
+  const void* dvis = vis;
+  const void* dwgt = wgt;
+  if (!dev && pl->nvis > 0) {
+    bool bcast = (vis_rs == 0 && vis_cs == 0);
+    if (!bcast && !(vis_cs == 1 && vis_rs == pl->gp.nchan)) return fail(PFBG_ERR_ARG, "host vis must be C-contiguous or a broadcast scalar");
+    CKRC(fetch(pl, pl->vis_stage, vis, bcast ? 2 * rb : (size_t)pl->nvis * 2 * rb, false, s, &dvis));
+    if (wgt) CKRC(fetch(pl, pl->wgt_stage, wgt, (size_t)pl->nvis * rb, false, s, &dwgt));
+  }
+  if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
+  mark(pl, s);
+  CKRC(DISPATCH(run_spread, pl, s, dvis, vis_rs, vis_cs, dwgt, 0, 1));
+  mark(pl, s);
+  CKRC(fft_exec(pl, s, CUFFT_INVERSE));
+  mark(pl, s);
+  void* dout = dirty;
+  if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
+  CKRC(DISPATCH(run_grid2img, pl, s, nullptr, nullptr, 1.0, 0.0, dout));
+  mark(pl, s);
+  if (!dev) {
+    CK(cudaMemcpyAsync(dirty, dout, img_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  mark(pl, s);
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const void* wgt, uint32_t flags,
+                           void* stream) {
+  if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
+  if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (!vis && pl->nvis > 0) return fail(PFBG_ERR_ARG, "null vis");
+  CK(cudaSetDevice(pl->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = real_bytes(pl);
+  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  const size_t vis_bytes = (size_t)pl->nvis * 2 * rb;
+  pl->n_ev = 0;
+  mark(pl, s);
+  const void* dimg = dirty;
+  CKRC(fetch(pl, pl->img_in, dirty, img_bytes, dev, s, &dimg));
+  const void* dwgt = nullptr;
+  if (flags & PFBG_APPLY_WGT) {
+    dwgt = wgt;
+    if (wgt && !dev) CKRC(fetch(pl, pl->wgt_stage, wgt, (size_t)pl->nvis * rb, false, s, &dwgt));
+    if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
+  }
+  mark(pl, s);
+  CKRC(DISPATCH(run_img2grid, pl, s, dimg, nullptr));
+  mark(pl, s);
+  CKRC(fft_exec(pl, s, CUFFT_FORWARD));
+  mark(pl, s);
+  void* dvis = vis;
+  if (!dev && pl->nvis > 0) { CKRC(dev_alloc(pl, pl->vis_stage, vis_bytes)); dvis = pl->vis_stage.p; }
+  if (pl->nvis > 0) {
+    if (pl->has_mask && !(flags & PFBG_NO_MASK_ZERO)) CK(cudaMemsetAsync(dvis, 0, vis_bytes, s));
+    CKRC(DISPATCH(run_gather, pl, s, dwgt, dvis, nullptr, 1));
+  }
+  mark(pl, s);
+  if (!dev && pl->nvis > 0) {
+    CK(cudaMemcpyAsync(vis, dvis, vis_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  mark(pl, s);
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, double wsum, double eta, void* out,
+                            uint32_t flags, void* stream) {
+  if (!pl || !x || !out) return fail(PFBG_ERR_ARG, "null argument");
+  if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  CK(cudaSetDevice(pl->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = real_bytes(pl);
+  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  pl->n_ev = 0;
+  mark(pl, s);
+  const void *dx = x, *dbeam = beam;
+  CKRC(fetch(pl, pl->img_in, x, img_bytes, dev, s, &dx));
+  if (beam) CKRC(fetch(pl, pl->img_beam, beam, img_bytes, dev, s, &dbeam));
+  CKRC(dev_alloc(pl, pl->mvis, (size_t)(pl->nactive ? pl->nactive : 1) * 2 * rb));
+  const void* dwgt = pl->has_wgt ? pl->wgt.p : nullptr;
+  mark(pl, s);
+  // R (beam * x): pad + screen, FFT, gather (phase factors cancel against the adjoint)
+  CKRC(DISPATCH(run_img2grid, pl, s, dx, dbeam));
+  CKRC(fft_exec(pl, s, CUFFT_FORWARD));
+  mark(pl, s);
+  CKRC(DISPATCH(run_gather, pl, s, nullptr, nullptr, pl->mvis.p, 0));
+  mark(pl, s);
+  // R^H W: spread (weights applied on load), FFT, screen + crop + epilogue
+  CKRC(DISPATCH(run_spread, pl, s, pl->mvis.p, 0, 0, dwgt, 1, 0));
+  mark(pl, s);
+  CKRC(fft_exec(pl, s, CUFFT_INVERSE));
+  void* dout = out;
+  if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
+  CKRC(DISPATCH(run_grid2img, pl, s, dbeam, eta != 0.0 ? dx : nullptr, wsum > 0.0 ? 1.0 / wsum : 1.0, eta, dout));
+  mark(pl, s);
+  if (!dev) {
+    CK(cudaMemcpyAsync(out, dout, img_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  mark(pl, s);
+  return PFBG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// imaging weights (utils/weighting.py:81-140, 143-208)
+// ---------------------------------------------------------------------------
+static WParams make_wparams(int64_t nrow, int nchan, int ncorr, int nx, int ny, double cell_x, double cell_y,
+                            double usign, double vsign) {
+  WParams w;
+  w.nrow = nrow; w.nchan = nchan; w.ncorr = ncorr; w.nx = nx; w.ny = ny;
+  w.u_cell = 1.0 / ((double)nx * cell_x);
+  w.umax = fabs(1.0 / cell_x / 2.0);
+  w.v_cell = 1.0 / ((double)ny * cell_y);
+  w.vmax = fabs(1.0 / cell_y / 2.0);
+  w.usign = usign; w.vsign = vsign; w.lightspeed = 299792458.0;
+  return w;
+}
+
+struct TmpBufs {
+  std::vector<void*> ptrs;
+  ~TmpBufs() { for (void* p : ptrs) cudaFree(p); }
+  int get(void** out, const void* src, size_t bytes, bool dev, bool copy, cudaStream_t s) {
+    if (dev) { *out = (void*)src; return PFBG_OK; }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(PFBG_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    ptrs.push_back(p);
+    if (copy && bytes) {
+      e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return PFBG_OK;
+  }
+};
+
+extern "C" int pfbg_counts(int32_t precision, int32_t device, const double* uvw, const double* freq,
+                           const uint8_t* mask, const void* wgt, int64_t nrow, int32_t nchan, int32_t ncorr,
+                           int32_t nx, int32_t ny, double cell_x, double cell_y, double usign, double vsign,
+                           void* counts, uint32_t flags, void* stream) {
+  if (!uvw || !freq || !wgt || !counts) return fail(PFBG_ERR_ARG, "null argument");
+  if (nrow < 0 || nchan <= 0 || ncorr <= 0 || nx <= 0 || ny <= 0) return fail(PFBG_ERR_ARG, "bad sizes");
+  if (precision != PFBG_F32 && precision != PFBG_F64) return fail(PFBG_ERR_ARG, "bad precision");
+  CK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = precision == PFBG_F32 ? 4 : 8;
+  const int64_t nvis = nrow * nchan;
+  const size_t cbytes = (size_t)ncorr * nx * ny * rb;
+  TmpBufs t;
+  void *duvw, *dfreq, *dmask = nullptr, *dwgt, *dcounts;
+  CKRC(t.get(&duvw, uvw, (size_t)nrow * 24, dev, true, s));
+  CKRC(t.get(&dfreq, freq, (size_t)nchan * 8, dev, true, s));
+  if (mask) CKRC(t.get(&dmask, mask, (size_t)nvis, dev, true, s));
+  CKRC(t.get(&dwgt, wgt, (size_t)ncorr * nvis * rb, dev, true, s));
+  CKRC(t.get(&dcounts, counts, cbytes, dev, false, s));
+  CK(cudaMemsetAsync(dcounts, 0, cbytes, s));
+  WParams w = make_wparams(nrow, nchan, ncorr, nx, ny, cell_x, cell_y, usign, vsign);
+  if (nvis > 0) {
+    unsigned grd = (unsigned)((nvis + 255) / 256);
+    if (precision == PFBG_F32)
+      k_counts<float><<<grd, 256, 0, s>>>(w, (const double*)duvw, (const double*)dfreq, (const uint8_t*)dmask, (const float*)dwgt, (float*)dcounts, nullptr);
+    else
+      k_counts<double><<<grd, 256, 0, s>>>(w, (const double*)duvw, (const double*)dfreq, (const uint8_t*)dmask, (const double*)dwgt, (double*)dcounts, nullptr);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
+  if (!dev) {
+    CK(cudaMemcpyAsync(counts, dcounts, cbytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return PFBG_OK;
+}
+
+// cell index dump for the bit-exact check: cells (nrow,nchan,2) int32, -1 = skipped
+extern "C" int pfbg_counts_cells(int32_t device, const double* uvw, const double* freq, const uint8_t* mask,
+                                 int64_t nrow, int32_t nchan, int32_t nx, int32_t ny, double cell_x, double cell_y,
+                                 double usign, double vsign, int32_t* cells) {
+  if (!uvw || !freq || !cells) return fail(PFBG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(device));
+  const int64_t nvis = nrow * nchan;
+  TmpBufs t;
+  void *duvw, *dfreq, *dmask = nullptr, *dcells;
+  CKRC(t.get(&duvw, uvw, (size_t)nrow * 24, false, true, 0));
+  CKRC(t.get(&dfreq, freq, (size_t)nchan * 8, false, true, 0));
+  if (mask) CKRC(t.get(&dmask, mask, (size_t)nvis, false, true, 0));
+  CKRC(t.get(&dcells, cells, (size_t)nvis * 8, false, false, 0));
+  WParams w = make_wparams(nrow, nchan, 1, nx, ny, cell_x, cell_y, usign, vsign);
+  if (nvis > 0) {
+    k_counts<float><<<(unsigned)((nvis + 255) / 256), 256>>>(w, (const double*)duvw, (const double*)dfreq, (const uint8_t*)dmask, nullptr, nullptr, (int32_t*)dcells);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(cells, dcells, (size_t)nvis * 8, cudaMemcpyDeviceToHost));
+  }
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_counts_to_weights(int32_t precision, int32_t device, void* counts, const double* uvw,
+                                      const double* freq, void* wgt, const uint8_t* mask, int64_t nrow,
+                                      int32_t nchan, int32_t ncorr, int32_t nx, int32_t ny, double cell_x,
+                                      double cell_y, double robust, double usign, double vsign, uint32_t flags,
+                                      void* stream) {
+  if (!uvw || !freq || !wgt || !counts) return fail(PFBG_ERR_ARG, "null argument");
+  if (nrow < 0 || nchan <= 0 || ncorr <= 0 || ncorr > 16 || nx <= 0 || ny <= 0) return fail(PFBG_ERR_ARG, "bad sizes");
+  if (precision != PFBG_F32 && precision != PFBG_F64) return fail(PFBG_ERR_ARG, "bad precision");
+  CK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = precision == PFBG_F32 ? 4 : 8;
+  const int64_t nvis = nrow * nchan, ncell = (int64_t)nx * ny;
+  const size_t cbytes = (size_t)ncorr * ncell * rb, wbytes = (size_t)ncorr * nvis * rb;
+  TmpBufs t;
+  void *duvw, *dfreq, *dmask = nullptr, *dwgt, *dcounts, *dsums;
+  CKRC(t.get(&duvw, uvw, (size_t)nrow * 24, dev, true, s));
+  CKRC(t.get(&dfreq, freq, (size_t)nchan * 8, dev, true, s));
+  if (mask) CKRC(t.get(&dmask, mask, (size_t)nvis, dev, true, s));
+  CKRC(t.get(&dwgt, wgt, wbytes, dev, true, s));
+  CKRC(t.get(&dcounts, counts, cbytes, dev, true, s));
+  CKRC(t.get(&dsums, nullptr, (2 * 16 + 1) * 8, false, false, s));
+  CK(cudaMemsetAsync(dsums, 0, (2 * 16 + 1) * 8, s));
+  dim3 rgrid(592, ncorr);
+  if (precision == PFBG_F32) k_counts_sums<float><<<rgrid, 256, 0, s>>>((const float*)dcounts, ncell, ncorr, (double*)dsums);
+  else k_counts_sums<double><<<rgrid, 256, 0, s>>>((const double*)dcounts, ncell, ncorr, (double*)dsums);
+  LAUNCHED();
+  double sums[33];
+  CK(cudaMemcpyAsync(sums, dsums, sizeof sums, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (sums[2 * ncorr] == 0.0) return PFBG_OK;  // `if not counts.any(): return weight`
+  if (robust > -2.0) {
+    double numsqrt = 5.0 * pow(10.0, -robust);
+    double ssq[16];
+    for (int c = 0; c < ncorr; ++c) ssq[c] = numsqrt * numsqrt * sums[2 * c + 1] / sums[2 * c];
+    CK(cudaMemcpyAsync(dsums, ssq, ncorr * 8, cudaMemcpyHostToDevice, s));
+    if (precision == PFBG_F32) k_counts_scale<float><<<rgrid, 256, 0, s>>>((float*)dcounts, ncell, (const double*)dsums);
+    else k_counts_scale<double><<<rgrid, 256, 0, s>>>((double*)dcounts, ncell, (const double*)dsums);
+    LAUNCHED();
+  }
+  WParams w = make_wparams(nrow, nchan, ncorr, nx, ny, cell_x, cell_y, usign, vsign);
+  if (nvis > 0) {
+    unsigned grd = (unsigned)((nvis + 255) / 256);
+    if (precision == PFBG_F32) k_apply_counts<float><<<grd, 256, 0, s>>>(w, (const double*)duvw, (const double*)dfreq, (const uint8_t*)dmask, (const float*)dcounts, (float*)dwgt);
+    else k_apply_counts<double><<<grd, 256, 0, s>>>(w, (const double*)duvw, (const double*)dfreq, (const uint8_t*)dmask, (const double*)dcounts, (double*)dwgt);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
+  if (!dev) {
+    CK(cudaMemcpyAsync(wgt, dwgt, wbytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(counts, dcounts, cbytes, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return PFBG_OK;
+}

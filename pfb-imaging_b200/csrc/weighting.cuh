@@ -1,0 +1,101 @@
+// Imaging-weight kernels: nearest-cell weight histogram on the padded uv grid and
+// the Briggs / uniform re-weighting that divides by it.  The integer cell index
+// follows /root/reference/src/pfb_imaging/utils/weighting.py:115-135 operation
+// for operation in fp64 without FMA contraction (bit-exact contract).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct WParams {
+  int64_t nrow;
+  int nchan, ncorr, nx, ny;
+  double u_cell, v_cell, umax, vmax, usign, vsign, lightspeed;
+};
+
+// returns false when the sample falls off the grid
+__device__ __forceinline__ bool uv_cell(const WParams& w, const double* __restrict__ uvw,
+                                        const double* __restrict__ freq, int64_t r, int f, int& ui, int& vi) {
+  double cn = __ddiv_rn(freq[f], w.lightspeed);
+  double u = __dmul_rn(__dmul_rn(uvw[3 * r + 0], cn), w.usign);
+  double v = __dmul_rn(__dmul_rn(uvw[3 * r + 1], cn), w.vsign);
+  if (v < 0) { u = -u; v = -v; }
+  double ug = __ddiv_rn(__dadd_rn(u, w.umax), w.u_cell);
+  double vg = __ddiv_rn(__dadd_rn(v, w.vmax), w.v_cell);
+  double fu = floor(ug), fv = floor(vg);
+  if (!(fu >= 0.0) || !(fu < (double)w.nx) || !(fv >= 0.0) || !(fv < (double)w.ny)) return false;
+  ui = (int)fu;
+  vi = (int)fv;
+  return true;
+}
+
+template <typename T>
+__global__ void k_counts(WParams w, const double* __restrict__ uvw, const double* __restrict__ freq,
+                         const uint8_t* __restrict__ mask, const T* __restrict__ wgt, T* __restrict__ counts,
+                         int32_t* __restrict__ cell_dump) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t nvis = w.nrow * w.nchan;
+  if (k >= nvis) return;
+  int64_t r = k / w.nchan;
+  int f = (int)(k - r * w.nchan);
+  if (cell_dump) { cell_dump[2 * k] = -1; cell_dump[2 * k + 1] = -1; }
+  if (mask && !mask[k]) return;
+  int ui, vi;
+  if (!uv_cell(w, uvw, freq, r, f, ui, vi)) return;
+  if (cell_dump) { cell_dump[2 * k] = ui; cell_dump[2 * k + 1] = vi; }
+  if (!counts) return;
+  for (int c = 0; c < w.ncorr; ++c) {
+    T v = wgt[(int64_t)c * nvis + k];
+    atomicAdd(&counts[((int64_t)c * w.nx + ui) * w.ny + vi], v);
+  }
+}
+
+// per-correlation sum(c^2) and sum(c) -> sums[2*corr], sums[2*corr+1]; any-nonzero flag in sums[2*ncorr]
+template <typename T>
+__global__ void k_counts_sums(const T* __restrict__ counts, int64_t ncell, int ncorr, double* __restrict__ sums) {
+  int c = blockIdx.y;
+  const T* p = counts + (int64_t)c * ncell;
+  double s2 = 0, s1 = 0;
+  bool nz = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = (double)p[i];
+    s2 += v * v;
+    s1 += v;
+    nz |= (v != 0.0);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  nz = __any_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[2 * c], s2);
+    atomicAdd(&sums[2 * c + 1], s1);
+    if (nz) sums[2 * ncorr] = 1.0;
+  }
+}
+
+template <typename T>
+__global__ void k_counts_scale(T* __restrict__ counts, int64_t ncell, const double* __restrict__ ssq) {
+  int c = blockIdx.y;
+  T s = (T)ssq[c];
+  T* p = counts + (int64_t)c * ncell;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = p[i] * s + (T)1;
+}
+
+template <typename T>
+__global__ void k_apply_counts(WParams w, const double* __restrict__ uvw, const double* __restrict__ freq,
+                               const uint8_t* __restrict__ mask, const T* __restrict__ counts, T* __restrict__ wgt) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t nvis = w.nrow * w.nchan;
+  if (k >= nvis) return;
+  int64_t r = k / w.nchan;
+  int f = (int)(k - r * w.nchan);
+  if (mask && !mask[k]) return;
+  int ui, vi;
+  if (!uv_cell(w, uvw, freq, r, f, ui, vi)) return;
+  for (int c = 0; c < w.ncorr; ++c) {
+    T cv = counts[((int64_t)c * w.nx + ui) * w.ny + vi];
+    if (cv > (T)0) wgt[(int64_t)c * nvis + k] /= cv;
+  }
+}

@@ -1,0 +1,268 @@
+"""Host-side plan for the B200 w-stacked gridder.
+
+A :class:`Plan` fixes everything the CUDA kernels need and nothing they can
+decide themselves: oversampled grid ``nu x nv``, ES-kernel support ``W`` and
+shape ``beta``, the w-plane stack ``(w0, dw, nplanes)``, the ``n-1`` shift, and
+the fp64 separable grid-correction vectors.  It replaces the parameter search
+ducc0.wgridder 0.41.0 (``pyproject.toml:42``, ``uv.lock:1119-1120``; source not
+in the reference tree) performs internally for every ``vis2dirty`` /
+``dirty2vis`` call made from ``src/pfb_imaging/operators/gridder.py:78-100``
+and ``operators/hessian.py:50-89``.
+
+Conventions (pinned by ``tests/test_hessian_approx.py:23-67`` and
+``operators/gridder.py:23-34``):
+
+    l_i = center_x + (i - nx/2) * pixsize_x       m_j likewise
+    nm1 = n - 1 = -(l^2+m^2) / (sqrt(1-l^2-m^2) + 1)
+    vis = sum_ij dirty_ij * exp(-2 pi i f/c (u l + v m - w nm1))   [/ n]
+
+``flip_u`` negates ``u`` *and* ``center_x`` (same for v); ``flip_w`` negates w.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+from numpy.polynomial.legendre import leggauss
+
+from . import kernel_table as kt
+
+LIGHTSPEED = 299792458.0  # scipy.constants.c, as used at operators/gridder.py:12
+
+TILE = 16  # uv tile edge of the binning kernel (cells)
+N_GL = 64  # Gauss-Legendre nodes for the w-correction evaluated on device
+
+
+def good_size(n: int, primes=(2, 3, 5, 7)) -> int:
+    """Smallest integer >= n whose prime factors are all in `primes`.
+
+    Stands in for ``ducc0.fft.good_size`` (``utils/misc.py:921-951``) with the
+    factor set restricted to what cuFFT handles without Bluestein.
+    """
+    n = int(n)
+    if n <= 1:
+        return 1
+    best = 1 << (n - 1).bit_length()
+    p7 = 1
+    while p7 < best:
+        p57 = p7
+        while p57 < best:
+            p357 = p57
+            while p357 < best:
+                x = p357
+                while x < n:
+                    x *= 2
+                if x < best:
+                    best = x
+                if 3 not in primes:
+                    break
+                p357 *= 3
+            if 5 not in primes:
+                break
+            p57 *= 5
+        if 7 not in primes:
+            break
+        p7 *= 7
+    return best
+
+
+def padded_size(n: int, sigma: float, W: int, mult: int = 2 * TILE) -> int:
+    """Oversampled grid length: a 7-smooth multiple of `mult`, >= sigma*n and >= n+W."""
+    need = max(int(math.ceil(sigma * n - 1e-9)), n + W + 1)
+    return good_size((need + mult - 1) // mult) * mult
+
+
+def nm1_of_r2(r2):
+    r2 = np.asarray(r2, dtype=np.float64)
+    return -r2 / (np.sqrt(1.0 - r2) + 1.0)
+
+
+def _axis_range2(c, n, d):
+    """min and max of l^2 over the pixel centres l = c + (i - n/2) d, i in [0, n)."""
+    lo = c - (n // 2) * d
+    hi = c + (n - 1 - n // 2) * d
+    a, b = min(lo, hi), max(lo, hi)
+    mx = max(a * a, b * b)
+    mn = 0.0 if a <= 0.0 <= b else min(a * a, b * b)
+    return mn, mx
+
+
+@dataclass
+class Plan:
+    precision: str  # "single" | "double"
+    nx: int
+    ny: int
+    nu: int
+    nv: int
+    W: int
+    beta: float
+    sigma: float
+    nplanes: int
+    w0: float
+    dw: float
+    nshift: float
+    pixsize_x: float
+    pixsize_y: float
+    center_x: float  # after the flip rule
+    center_y: float
+    usign: float
+    vsign: float
+    wsign: float
+    do_wgridding: bool
+    divide_by_n: bool
+    epsilon: float
+    kernel_err: float
+    corr_u: np.ndarray = field(repr=False)  # (nx,) fp64: 1/psihat(i'/nu)
+    corr_v: np.ndarray = field(repr=False)
+    gl_x: np.ndarray = field(repr=False)  # nodes on [0,1] for psihat_w on device
+    gl_w: np.ndarray = field(repr=False)
+    est_cost: float = 0.0
+
+    @property
+    def real_bytes(self) -> int:
+        return 4 if self.precision == "single" else 8
+
+    def info(self) -> dict:
+        return dict(
+            precision=self.precision, nx=self.nx, ny=self.ny, nu=self.nu, nv=self.nv,
+            W=self.W, beta=self.beta, sigma=self.sigma, nplanes=self.nplanes,
+            w0=self.w0, dw=self.dw, nshift=self.nshift, kernel_err=self.kernel_err,
+        )
+
+
+def w_range(uvw, freq, wsign=1.0):
+    """min/max of w*f/c over all rows and channels (wavelengths)."""
+    w = np.asarray(uvw)[:, 2].astype(np.float64) * wsign
+    f = np.asarray(freq, dtype=np.float64)
+    if w.size == 0 or f.size == 0:
+        return 0.0, 0.0
+    s_lo, s_hi = f.min() / LIGHTSPEED, f.max() / LIGHTSPEED
+    wmin, wmax = float(w.min()), float(w.max())
+    cands = (wmin * s_lo, wmin * s_hi, wmax * s_lo, wmax * s_hi)
+    return min(cands), max(cands)
+
+
+def _correction(n, nbig, W, beta):
+    ip = np.arange(n) - n // 2
+    return 1.0 / kt.kernel_ft(ip / float(nbig), W, beta)
+
+
+# cost-model coefficients (seconds): per cell update of the spreading/gathering
+# kernels and per complex grid cell of one plane (memset/flush + FFT + screen).
+# Calibrated on B200 ("plan cost model").
+COST_CELL_UPDATE = {"single": 2.0e-12, "double": 5.0e-12}
+COST_GRID_CELL = {"single": 1.2e-11, "double": 2.9e-11}
+
+# Largest kernel support per precision.  In single precision the grid
+# correction 1/psihat amplifies the fp32 round-off of the FFT by
+# psihat(0)/psihat(1/(2 sigma)) ~ exp(beta - sqrt(beta^2 - (pi W / (2 sigma))^2)),
+# which explodes for wide kernels at low oversampling; ducc0 applies the same
+# cap (W <= 8 for float).
+W_LIMIT = {"single": 8, "double": kt.W_MAX}
+
+
+def make_plan(
+    *, nx, ny, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
+    flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
+    sigma_min=1.1, sigma_max=2.6, precision="double", wmin=0.0, wmax=0.0, nvis=0,
+    force_sigma=None, force_W=None,
+) -> Plan:
+    """Choose (sigma, W, beta, nu, nv, planes) for one gridder geometry."""
+    nx, ny = int(nx), int(ny)
+    if nx <= 0 or ny <= 0 or nx % 2 or ny % 2:
+        raise ValueError("image dimensions must be positive and even (utils/misc.py:930-932)")
+    if not (pixsize_x > 0 and pixsize_y > 0):
+        raise ValueError("pixel sizes must be positive")
+    if not (epsilon > 0):
+        raise ValueError("epsilon must be positive")
+    if precision not in ("single", "double"):
+        raise ValueError("precision must be 'single' or 'double'")
+    if precision == "single" and epsilon < 1e-7 * 3:
+        raise ValueError("epsilon too small for single precision (needs >= 3e-7)")
+    if epsilon < 1e-13:
+        raise ValueError("epsilon too small for double precision")
+
+    cx = -center_x if flip_u else center_x
+    cy = -center_y if flip_v else center_y
+    usign = -1.0 if flip_u else 1.0
+    vsign = -1.0 if flip_v else 1.0
+    wsign = -1.0 if flip_w else 1.0
+
+    l2min, l2max = _axis_range2(cx, nx, pixsize_x)
+    m2min, m2max = _axis_range2(cy, ny, pixsize_y)
+    if l2max + m2max >= 1.0:
+        raise ValueError("image extends beyond the unit sphere (l^2+m^2 >= 1)")
+    nm1_lo = float(nm1_of_r2(l2max + m2max))  # most negative
+    nm1_hi = float(nm1_of_r2(l2min + m2min))
+    if do_wgridding:
+        nshift = -0.5 * (nm1_lo + nm1_hi)
+        numax = max(0.5 * (nm1_hi - nm1_lo), 1e-300)
+    else:
+        nshift, numax = 0.0, 0.0
+
+    ndim = 3 if do_wgridding else 2
+    target = epsilon / math.sqrt(ndim)
+
+    sig_lo = max(float(sigma_min), kt.SIGMAS[0])
+    sig_hi = max(min(float(sigma_max), kt.SIGMAS[-1]), sig_lo)
+    if force_sigma is not None:
+        cand_sig = [float(force_sigma)]
+    else:
+        cand_sig = [s for s in kt.SIGMAS if sig_lo - 1e-9 <= s <= sig_hi + 1e-9] or [sig_lo]
+
+    best = None
+    for s in cand_sig:
+        W = None
+        for Wc in range(kt.W_MIN, W_LIMIT[precision] + 1):
+            if force_W is not None and Wc != force_W:
+                continue
+            beta, err = kt.lookup(s, Wc)
+            if err <= target or force_W is not None:
+                W = Wc
+                break
+        if W is None:
+            continue
+        nu = padded_size(nx, s, W)
+        nv = padded_size(ny, s, W)
+        sig_eff = min(nu / nx, nv / ny)
+        if do_wgridding and wmax > wmin:
+            dw = 1.0 / (2.0 * s * numax)
+            npl = int(math.ceil((wmax - wmin) / dw)) + W
+        elif do_wgridding:
+            dw = 1.0 / (2.0 * s * numax)
+            npl = W
+        else:
+            dw, npl = 1.0, 1
+        cost = (
+            2.0 * nvis * (W ** ndim) * COST_CELL_UPDATE[precision]
+            + 2.0 * npl * nu * nv * COST_GRID_CELL[precision]
+        )
+        if best is None or cost < best[0]:
+            best = (cost, s, W, beta, err, nu, nv, dw, npl, sig_eff)
+    if best is None:
+        raise ValueError(
+            f"no (sigma, W) in [{sig_lo}, {sig_hi}] x [{kt.W_MIN}, {W_LIMIT[precision]}] reaches "
+            f"epsilon={epsilon} in {precision} precision"
+        )
+    cost, s, W, beta, err, nu, nv, dw, npl, sig_eff = best
+
+    if do_wgridding:
+        # plane p sits at w0 + p*dw; the lowest sample's support starts at plane 0
+        w0 = 0.5 * (wmin + wmax) - 0.5 * (npl - 1) * dw
+    else:
+        w0 = 0.0
+
+    gx, gw = leggauss(2 * N_GL)
+    gl_x, gl_w = gx[N_GL:].copy(), gw[N_GL:].copy()  # positive half; integrand is even
+
+    return Plan(
+        precision=precision, nx=nx, ny=ny, nu=nu, nv=nv, W=W, beta=float(beta), sigma=float(s),
+        nplanes=int(npl), w0=float(w0), dw=float(dw), nshift=float(nshift),
+        pixsize_x=float(pixsize_x), pixsize_y=float(pixsize_y), center_x=float(cx), center_y=float(cy),
+        usign=usign, vsign=vsign, wsign=wsign, do_wgridding=bool(do_wgridding),
+        divide_by_n=bool(divide_by_n), epsilon=float(epsilon), kernel_err=float(err),
+        corr_u=_correction(nx, nu, W, beta), corr_v=_correction(ny, nv, W, beta),
+        gl_x=gl_x, gl_w=gl_w, est_cost=float(cost),
+    )

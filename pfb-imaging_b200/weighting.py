@@ -1,0 +1,120 @@
+"""Imaging weights on the B200: drop-ins for the numba functions of
+``/root/reference/src/pfb_imaging/utils/weighting.py`` —
+``_compute_counts`` (:81-140), ``counts_to_weights`` (:143-208),
+``filter_extreme_counts`` (:212-226), ``box_sum_counts`` (:229-254) — with the
+same positional signatures and in-place behaviour (``counts_to_weights`` mutates
+both ``weight`` and ``counts``).  The histogram / gather run in
+``libpfbgrid.so`` (``csrc/weighting.cuh``); the median filter and the box sum are
+small image-sized host operations and stay in numpy/scipy.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .wgridder import current_device
+
+
+def _prec(dt):
+    dt = np.dtype(dt)
+    if dt == np.float32:
+        return _lib.PFBG_F32
+    if dt == np.float64:
+        return _lib.PFBG_F64
+    raise TypeError(f"weights must be float32 or float64, got {dt}")
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _geom(uvw, freq, mask, nrow, nchan):
+    uvw = np.ascontiguousarray(uvw, dtype=np.float64)
+    freq = np.ascontiguousarray(freq, dtype=np.float64)
+    if uvw.shape != (nrow, 3) or freq.shape != (nchan,):
+        raise ValueError("uvw/freq shapes do not match the weights")
+    if mask is not None:
+        mask = np.asarray(mask)
+        if mask.shape != (nrow, nchan):
+            raise ValueError("mask shape does not match the weights")
+        mask = np.ascontiguousarray(mask if mask.dtype == np.uint8 else mask != 0, dtype=np.uint8)
+    return uvw, freq, mask
+
+
+def _compute_counts(uvw, freq, mask, wgt, nx, ny, cell_size_x, cell_size_y, dtype, ngrid=1, usign=1.0, vsign=-1.0):
+    """(ncorr, nx, ny) sum of weights per uv cell.  `ngrid` is accepted and ignored."""
+    wgt = np.asarray(wgt)
+    if wgt.ndim != 3:
+        raise ValueError("wgt must have shape (ncorr, nrow, nchan)")
+    ncorr, nrow, nchan = wgt.shape
+    dt = np.dtype(dtype)
+    w = np.ascontiguousarray(wgt, dtype=dt)
+    uvw, freq, mask = _geom(uvw, freq, mask, nrow, nchan)
+    counts = np.empty((ncorr, int(nx), int(ny)), dtype=dt)
+    lib = _lib.load()
+    _lib.check(lib.pfbg_counts(_prec(dt), current_device(), _p(uvw), _p(freq), _p(mask), _p(w), nrow, nchan, ncorr,
+                               int(nx), int(ny), float(cell_size_x), float(cell_size_y), float(usign), float(vsign),
+                               _p(counts), _lib.HOST_PTRS, None))
+    return counts
+
+
+def counts_cells(uvw, freq, mask, nx, ny, cell_size_x, cell_size_y, usign=1.0, vsign=-1.0):
+    """Bit-exact check hook: (nrow, nchan, 2) int32 cell index per sample (-1 = skipped)."""
+    uvw = np.ascontiguousarray(uvw, dtype=np.float64)
+    freq = np.ascontiguousarray(freq, dtype=np.float64)
+    nrow, nchan = uvw.shape[0], freq.size
+    uvw, freq, mask = _geom(uvw, freq, mask, nrow, nchan)
+    cells = np.empty((nrow, nchan, 2), dtype=np.int32)
+    lib = _lib.load()
+    _lib.check(lib.pfbg_counts_cells(current_device(), _p(uvw), _p(freq), _p(mask), nrow, nchan, int(nx), int(ny),
+                                     float(cell_size_x), float(cell_size_y), float(usign), float(vsign), _p(cells)))
+    return cells
+
+
+def counts_to_weights(counts, uvw, freq, weight, mask, nx, ny, cell_size_x, cell_size_y, robust, usign=1.0, vsign=-1.0):
+    """Briggs/uniform re-weighting, in place on `weight` and `counts` (weighting.py:173-174,206)."""
+    if not isinstance(weight, np.ndarray) or weight.ndim != 3:
+        raise ValueError("weight must be an ndarray of shape (ncorr, nrow, nchan)")
+    ncorr, nrow, nchan = weight.shape
+    dt = weight.dtype
+    if counts.dtype != dt or counts.shape != (ncorr, int(nx), int(ny)):
+        raise ValueError("counts must be (ncorr, nx, ny) of the weights' dtype")
+    uvw, freq, mask = _geom(uvw, freq, mask, nrow, nchan)
+    w = weight if weight.flags.c_contiguous else np.ascontiguousarray(weight)
+    c = counts if counts.flags.c_contiguous else np.ascontiguousarray(counts)
+    lib = _lib.load()
+    _lib.check(lib.pfbg_counts_to_weights(_prec(dt), current_device(), _p(c), _p(uvw), _p(freq), _p(w), _p(mask),
+                                          nrow, nchan, ncorr, int(nx), int(ny), float(cell_size_x),
+                                          float(cell_size_y), float(robust), float(usign), float(vsign),
+                                          _lib.HOST_PTRS, None))
+    if w is not weight:
+        weight[...] = w
+    if c is not counts:
+        counts[...] = c
+    return weight
+
+
+def filter_extreme_counts(counts, level=10.0):
+    if not level:
+        return counts
+    ic, ix, iy = np.where(counts > 0)
+    cnts = counts[ic, ix, iy]
+    counts[ic, ix, iy] = np.maximum(cnts, np.median(cnts) / level)
+    return counts
+
+
+def box_sum_counts(counts, npix_super):
+    if npix_super is None or npix_super <= 0:
+        return counts
+    if not np.issubdtype(counts.dtype, np.floating):
+        raise AssertionError(f"box_sum_counts requires a floating-point counts array; got dtype={counts.dtype}")
+    from scipy.ndimage import uniform_filter
+
+    size = 2 * npix_super + 1
+    out = np.empty_like(counts)
+    for c in range(counts.shape[0]):
+        out[c] = uniform_filter(counts[c], size=size, mode="constant", cval=0.0) * (size * size)
+    return out

@@ -1,0 +1,283 @@
+"""Drop-in ``vis2dirty`` / ``dirty2vis`` with the keyword signatures pfb-imaging
+uses for ``ducc0.wgridder[.experimental]`` (``/root/reference/src/pfb_imaging/
+operators/gridder.py:78-100, 485-503``; ``operators/hessian.py:50-89``).
+
+numpy in, numpy out; the work happens in ``libpfbgrid.so`` on a B200.
+:class:`GridderPlan` is the stateful form (geometry bound and binned once,
+reused across calls); the free functions build a plan per call like ducc0 does.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .plan import LIGHTSPEED, Plan, make_plan, w_range
+
+_PREC = {"single": _lib.PFBG_F32, "double": _lib.PFBG_F64}
+_RDT = {"single": np.float32, "double": np.float64}
+_CDT = {"single": np.complex64, "double": np.complex128}
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def current_device() -> int:
+    import os
+
+    return int(os.environ.get("PFBG_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+class GridderPlan:
+    """A plan bound to one set of (uvw, freq, mask): the analogue of the state a
+    band worker pins (``operators/band_worker.py:61-106``)."""
+
+    def __init__(self, plan: Plan, device: int | None = None):
+        self.plan = plan
+        self.device = current_device() if device is None else int(device)
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        self._keep = (np.ascontiguousarray(plan.corr_u, dtype=np.float64),
+                      np.ascontiguousarray(plan.corr_v, dtype=np.float64),
+                      np.ascontiguousarray(plan.gl_x, dtype=np.float64),
+                      np.ascontiguousarray(plan.gl_w, dtype=np.float64))
+        d = _lib.PlanDesc(
+            precision=_PREC[plan.precision], device=self.device, nx=plan.nx, ny=plan.ny, nu=plan.nu, nv=plan.nv,
+            W=plan.W, nplanes=plan.nplanes, do_wgridding=int(plan.do_wgridding), divide_by_n=int(plan.divide_by_n),
+            beta=plan.beta, pixsize_x=plan.pixsize_x, pixsize_y=plan.pixsize_y,
+            center_x=plan.center_x, center_y=plan.center_y, usign=plan.usign, vsign=plan.vsign, wsign=plan.wsign,
+            w0=plan.w0, dw=plan.dw, nshift=plan.nshift,
+            corr_u=self._keep[0].ctypes.data, corr_v=self._keep[1].ctypes.data,
+            gl_x=self._keep[2].ctypes.data, gl_w=self._keep[3].ctypes.data, n_gl=len(self._keep[2]),
+        )
+        _lib.check(self._lib.pfbg_plan_create(C.byref(d), C.byref(self._h)))
+        self.nrow = self.nchan = 0
+        self.rdt = _RDT[plan.precision]
+        self.cdt = _CDT[plan.precision]
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pfbg_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- binding ------------------------------------------------------------
+    def bind(self, uvw, freq, mask=None, stream=None):
+        uvw = np.ascontiguousarray(uvw, dtype=np.float64)
+        freq = np.ascontiguousarray(freq, dtype=np.float64)
+        if uvw.ndim != 2 or uvw.shape[1] != 3:
+            raise ValueError("uvw must have shape (nrow, 3)")
+        if freq.ndim != 1 or freq.size == 0:
+            raise ValueError("freq must be a non-empty 1-D array")
+        nrow, nchan = uvw.shape[0], freq.size
+        fscale = np.ascontiguousarray(freq / LIGHTSPEED)
+        if mask is not None:
+            mask = np.asarray(mask)
+            if mask.shape != (nrow, nchan):
+                raise ValueError(f"mask shape {mask.shape} != ({nrow}, {nchan})")
+            mask = np.ascontiguousarray(mask != 0 if mask.dtype != np.uint8 else mask, dtype=np.uint8)
+        _lib.check(self._lib.pfbg_bind_vis(self._h, _ptr(uvw), _ptr(fscale), _ptr(mask), nrow, nchan,
+                                           _lib.HOST_PTRS, stream))
+        self.nrow, self.nchan = nrow, nchan
+        return self
+
+    def bind_weights(self, wgt, stream=None):
+        if wgt is not None:
+            wgt = self._check_wgt(wgt)
+        _lib.check(self._lib.pfbg_bind_weights(self._h, _ptr(wgt), _lib.HOST_PTRS, stream))
+        return self
+
+    def info(self) -> dict:
+        i = _lib.PlanInfo()
+        _lib.check(self._lib.pfbg_plan_get_info(self._h, C.byref(i)))
+        out = {k: getattr(i, k) for k, _ in _lib.PlanInfo._fields_}
+        out.update(self.plan.info())
+        return out
+
+    def bin_dump(self):
+        """Kernel-1 outputs for the bit-exact check (host arrays)."""
+        i = self.info()
+        n, na = i["nvis"], i["nactive"]
+        iu0, iv0, ip0 = (np.empty(n, np.int32) for _ in range(3))
+        key = np.empty(n, np.uint64)
+        sidx = np.empty(na, np.uint32)
+        _lib.check(self._lib.pfbg_bin_dump(self._h, _ptr(iu0), _ptr(iv0), _ptr(ip0), _ptr(key), _ptr(sidx)))
+        return dict(iu0=iu0, iv0=iv0, ip0=ip0, key=key, sorted_idx=sidx)
+
+    # -- argument checks ----------------------------------------------------
+    def _check_wgt(self, wgt):
+        wgt = np.asarray(wgt)
+        if wgt.shape != (self.nrow, self.nchan):
+            raise ValueError(f"wgt shape {wgt.shape} != ({self.nrow}, {self.nchan})")
+        if wgt.dtype != self.rdt:
+            raise TypeError(f"wgt dtype {wgt.dtype} does not match precision '{self.plan.precision}' ({self.rdt.__name__})")
+        return np.ascontiguousarray(wgt)
+
+    def _check_img(self, x, name):
+        x = np.asarray(x)
+        if x.shape != (self.plan.nx, self.plan.ny):
+            raise ValueError(f"{name} shape {x.shape} != ({self.plan.nx}, {self.plan.ny})")
+        if x.dtype != self.rdt:
+            raise TypeError(f"{name} dtype {x.dtype} does not match precision '{self.plan.precision}'")
+        return np.ascontiguousarray(x)
+
+    # -- operators (host arrays) ---------------------------------------------
+    def grid(self, vis, wgt=None, dirty=None, stream=None):
+        vis = np.asarray(vis)
+        if vis.shape != (self.nrow, self.nchan):
+            raise ValueError(f"vis shape {vis.shape} != ({self.nrow}, {self.nchan})")
+        if vis.dtype != self.cdt:
+            raise TypeError(f"vis dtype {vis.dtype} does not match precision '{self.plan.precision}' ({self.cdt.__name__})")
+        if vis.size and all(s == 0 for s in vis.strides):
+            rs = cs = 0  # np.broadcast_to(scalar): operators/gridder.py:627-629
+        else:
+            vis = np.ascontiguousarray(vis)
+            rs, cs = self.nchan, 1
+        if wgt is not None:
+            wgt = self._check_wgt(wgt)
+        out = self._out_img(dirty, "dirty")
+        tmp = out if out.flags.c_contiguous else np.empty(out.shape, out.dtype)
+        _lib.check(self._lib.pfbg_grid(self._h, _ptr(vis), rs, cs, _ptr(wgt), _ptr(tmp), _lib.HOST_PTRS, stream))
+        if tmp is not out:
+            out[...] = tmp
+        return out
+
+    def _out_img(self, arr, name):
+        if arr is None:
+            return np.empty((self.plan.nx, self.plan.ny), dtype=self.rdt)
+        if not isinstance(arr, np.ndarray) or arr.shape != (self.plan.nx, self.plan.ny) or arr.dtype != self.rdt:
+            raise ValueError(f"`{name}` must be a ({self.plan.nx}, {self.plan.ny}) {self.rdt.__name__} array")
+        if not arr.flags.writeable:
+            raise ValueError(f"`{name}` is read-only")
+        return arr
+
+    def degrid(self, dirty, wgt=None, vis=None, stream=None):
+        x = self._check_img(dirty, "dirty")
+        flags = _lib.HOST_PTRS
+        if wgt is not None:
+            wgt = self._check_wgt(wgt)
+            flags |= _lib.APPLY_WGT
+        if vis is None:
+            out = np.empty((self.nrow, self.nchan), dtype=self.cdt)
+        else:
+            if not isinstance(vis, np.ndarray) or vis.shape != (self.nrow, self.nchan) or vis.dtype != self.cdt:
+                raise ValueError(f"`vis` must be a ({self.nrow}, {self.nchan}) {self.cdt.__name__} array")
+            if not vis.flags.writeable:
+                raise ValueError("`vis` is read-only")
+            out = vis
+        tmp = out if out.flags.c_contiguous else np.empty(out.shape, out.dtype)
+        _lib.check(self._lib.pfbg_degrid(self._h, _ptr(x), _ptr(tmp), _ptr(wgt), flags, stream))
+        if tmp is not out:
+            out[...] = tmp
+        return out
+
+    def hessian(self, x, beam=None, wsum=None, eta=None, out=None, stream=None):
+        x = self._check_img(x, "x")
+        if beam is not None:
+            beam = self._check_img(beam, "beam")
+        res = self._out_img(out, "out")
+        tmp = res if res.flags.c_contiguous else np.empty(res.shape, res.dtype)
+        _lib.check(self._lib.pfbg_hessian(self._h, _ptr(x), _ptr(beam), float(wsum) if wsum else 0.0,
+                                          float(eta) if eta else 0.0, _ptr(tmp), _lib.HOST_PTRS, stream))
+        if tmp is not res:
+            res[...] = tmp
+        return res
+
+    # -- operators (device pointers; asynchronous on `stream`) ----------------
+    def hessian_dev(self, x_ptr, beam_ptr, wsum, eta, out_ptr, stream=None):
+        _lib.check(self._lib.pfbg_hessian(self._h, x_ptr, beam_ptr, float(wsum) if wsum else 0.0,
+                                          float(eta) if eta else 0.0, out_ptr, _lib.DEVICE_PTRS, stream))
+
+    def grid_dev(self, vis_ptr, wgt_ptr, dirty_ptr, stream=None, rs=None, cs=1):
+        rs = self.nchan if rs is None else rs
+        _lib.check(self._lib.pfbg_grid(self._h, vis_ptr, rs, cs, wgt_ptr, dirty_ptr, _lib.DEVICE_PTRS, stream))
+
+    def degrid_dev(self, dirty_ptr, vis_ptr, stream=None):
+        _lib.check(self._lib.pfbg_degrid(self._h, dirty_ptr, vis_ptr, None, _lib.DEVICE_PTRS, stream))
+
+    def set_profiling(self, on=True):
+        _lib.check(self._lib.pfbg_set_profiling(self._h, int(on)))
+
+    def timings(self):
+        ms = (C.c_float * 8)()
+        n = C.c_int32(0)
+        _lib.check(self._lib.pfbg_get_timings(self._h, ms, 8, C.byref(n)))
+        return [ms[i] for i in range(n.value)]
+
+
+def _precision_of(dtype, what):
+    dt = np.dtype(dtype)
+    if dt in (np.dtype(np.complex64), np.dtype(np.float32)):
+        return "single"
+    if dt in (np.dtype(np.complex128), np.dtype(np.float64)):
+        return "double"
+    raise TypeError(f"unsupported {what} dtype {dt}")
+
+
+def plan_for(uvw, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
+             flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
+             sigma_min=1.1, sigma_max=2.6, precision="double", mask=None, device=None, **force) -> GridderPlan:
+    """Build a plan for the geometry and bind (uvw, freq, mask) to it."""
+    uvw = np.asarray(uvw)
+    freq = np.asarray(freq)
+    wmin, wmax = w_range(uvw, freq, -1.0 if flip_w else 1.0) if do_wgridding else (0.0, 0.0)
+    p = make_plan(nx=npix_x, ny=npix_y, pixsize_x=pixsize_x, pixsize_y=pixsize_y, center_x=center_x,
+                  center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w,
+                  do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min, sigma_max=sigma_max,
+                  precision=precision, wmin=wmin, wmax=wmax, nvis=uvw.shape[0] * freq.size, **force)
+    gp = GridderPlan(p, device=device)
+    try:
+        gp.bind(uvw, freq, mask)
+    except Exception:
+        gp.close()
+        raise
+    return gp
+
+
+def vis2dirty(*, uvw, freq, vis, wgt=None, mask=None, npix_x, npix_y, pixsize_x, pixsize_y,
+              center_x=0.0, center_y=0.0, epsilon, flip_u=False, flip_v=False, flip_w=False,
+              do_wgridding=True, divide_by_n=True, nthreads=1, sigma_min=1.1, sigma_max=2.6,
+              double_precision_accumulation=False, verbosity=0, dirty=None, allow_nshift=True, gpu=False):
+    """``ducc0.wgridder.experimental.vis2dirty`` replacement (B200).
+
+    ``nthreads``, ``verbosity``, ``double_precision_accumulation`` (the plane sum
+    is always accumulated in fp64), ``allow_nshift`` and ``gpu`` are accepted
+    for signature compatibility and otherwise ignored.
+    """
+    vis = np.asarray(vis)
+    prec = _precision_of(vis.dtype, "vis")
+    with plan_for(uvw, freq, npix_x=npix_x, npix_y=npix_y, pixsize_x=pixsize_x, pixsize_y=pixsize_y,
+                  center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v,
+                  flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min,
+                  sigma_max=sigma_max, precision=prec, mask=mask) as gp:
+        return gp.grid(vis, wgt=wgt, dirty=dirty)
+
+
+def dirty2vis(*, uvw, freq, dirty, wgt=None, mask=None, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0,
+              epsilon, flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
+              nthreads=1, sigma_min=1.1, sigma_max=2.6, verbosity=0, vis=None, allow_nshift=True, gpu=False):
+    """``ducc0.wgridder.experimental.dirty2vis`` replacement (B200)."""
+    dirty = np.asarray(dirty)
+    if dirty.ndim != 2:
+        raise ValueError("dirty must be 2-D")
+    prec = _precision_of(dirty.dtype, "dirty")
+    with plan_for(uvw, freq, npix_x=dirty.shape[0], npix_y=dirty.shape[1], pixsize_x=pixsize_x,
+                  pixsize_y=pixsize_y, center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u,
+                  flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=divide_by_n,
+                  sigma_min=sigma_min, sigma_max=sigma_max, precision=prec, mask=mask) as gp:
+        return gp.degrid(dirty, wgt=wgt, vis=vis)

@@ -1,0 +1,68 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/pfbgrid.h declares;
+compute entry points fail loudly (no CPU fallback) when no B200 is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pfb_imaging_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pfbgrid.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pfbg_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_symbols():
+    syms = header_symbols()
+    assert "pfbg_grid" in syms and "pfbg_degrid" in syms and "pfbg_hessian" in syms and "pfbg_bind_vis" in syms
+    assert len(syms) >= 15
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.build())
+    for s in header_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/pfbgrid.h but not exported"
+
+
+def test_binding_covers_header():
+    assert set(header_symbols()) == set(_lib.SIGNATURES), "ctypes SIGNATURES and the header drifted"
+    lib = _lib.load()
+    assert lib.pfbg_version() >= 100
+
+
+def test_struct_layout_matches_header():
+    # 8 int32 + 2 int32 + 11 doubles + 4 pointers + 2 int32
+    assert ctypes.sizeof(_lib.PlanDesc) == 10 * 4 + 11 * 8 + 4 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.PlanInfo) == 5 * 8 + 6 * 4
+
+
+def _no_gpu():
+    try:
+        return _lib.device_count() == 0
+    except RuntimeError:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on the GPU-less build container")
+def test_no_silent_cpu_fallback():
+    from pfb_imaging_b200 import wgridder
+
+    uvw = np.zeros((4, 3))
+    freq = np.array([1e9])
+    with pytest.raises(RuntimeError, match="pfbgrid error"):
+        wgridder.dirty2vis(uvw=uvw, freq=freq, dirty=np.ones((16, 16)), pixsize_x=1e-5, pixsize_y=1e-5, epsilon=1e-5)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pfb-imaging_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"

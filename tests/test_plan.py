@@ -1,0 +1,69 @@
+"""CPU: host-side plan logic (parameter choice, sizes, argument errors)."""
+import numpy as np
+import pytest
+
+from pfb_imaging_b200 import kernel_table as kt
+from pfb_imaging_b200.plan import good_size, make_plan, padded_size, w_range
+
+
+def test_good_size():
+    for n in (1, 2, 7, 11, 13, 97, 1000, 4097, 5734):
+        g = good_size(n)
+        assert g >= n
+        m = g
+        for p in (2, 3, 5, 7):
+            while m % p == 0:
+                m //= p
+        assert m == 1
+    assert good_size(5734) == 5760  # good_size(1.4*4096), BASELINE.md C2
+
+
+def test_padded_size_is_tileable():
+    for n, s, W in ((4096, 1.5, 8), (2048, 1.25, 10), (512, 2.0, 7), (100, 1.1, 16)):
+        nu = padded_size(n, s, W)
+        assert nu % 32 == 0 and nu >= s * n - 1e-9 and nu >= n + W
+
+
+def test_kernel_table_monotone():
+    for s in (1.2, 1.5, 2.0):
+        errs = [kt.lookup(s, W)[1] for W in range(4, 15)]
+        assert all(a > b for a, b in zip(errs, errs[1:]))
+
+
+@pytest.mark.parametrize("prec,eps", [("single", 1e-5), ("single", 1e-4), ("double", 1e-7), ("double", 1e-10)])
+def test_plan_meets_epsilon(prec, eps):
+    p = make_plan(nx=4096, ny=4096, pixsize_x=5.5e-6, pixsize_y=5.5e-6, epsilon=eps, precision=prec,
+                  wmin=-2e4, wmax=2e4, nvis=25_000_000, flip_v=True, divide_by_n=False, sigma_max=3.0)
+    assert p.kernel_err <= eps / np.sqrt(3)
+    assert p.nu >= p.sigma * p.nx - 1e-9 and p.nu % 32 == 0
+    assert p.nplanes >= p.W
+    if prec == "single":
+        assert p.W <= 8
+    # every sample's support fits in the plane stack
+    for w in (-2e4, 2e4):
+        ip0 = np.floor((w - p.w0) / p.dw - 0.5 * p.W) + 1
+        assert 0 <= ip0 <= p.nplanes - p.W
+    assert p.vsign == -1.0 and p.usign == 1.0
+
+
+def test_plan_flip_rule_and_no_wgridding():
+    p = make_plan(nx=64, ny=64, pixsize_x=1e-4, pixsize_y=1e-4, center_x=0.1, center_y=-0.2, epsilon=1e-6,
+                  flip_u=True, flip_v=True, do_wgridding=False)
+    assert p.center_x == -0.1 and p.center_y == 0.2 and p.nplanes == 1 and p.nshift == 0.0
+
+
+def test_plan_errors():
+    base = dict(nx=64, ny=64, pixsize_x=1e-4, pixsize_y=1e-4, epsilon=1e-6)
+    for bad in (dict(nx=63), dict(ny=0), dict(pixsize_x=-1.0), dict(epsilon=0.0), dict(epsilon=1e-20),
+                dict(precision="half"), dict(precision="single", epsilon=1e-9), dict(center_x=0.9, center_y=0.9)):
+        with pytest.raises(ValueError):
+            make_plan(**{**base, **bad})
+
+
+def test_w_range():
+    uvw = np.array([[0, 0, -3.0], [0, 0, 5.0]])
+    f = np.array([1e9, 2e9])
+    lo, hi = w_range(uvw, f)
+    assert np.isclose(lo, -3.0 * 2e9 / 299792458.0) and np.isclose(hi, 5.0 * 2e9 / 299792458.0)
+    lo2, hi2 = w_range(uvw, f, -1.0)
+    assert np.isclose(lo2, -hi) and np.isclose(hi2, -lo)
