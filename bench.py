@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — Mvis/s per Hessian apply (degrid + grid) on synthetic MeerKAT-like bands.
+
+Contract (see README / DESIGN.md §measurement):
+  python bench.py --gpus N --steps K --warmup W            our arm (B200 kernels)
+  python bench.py --impl reference --gpus N ...           CPU arm (oracle port; ducc0 unavailable)
+One JSON line on stdout from rank 0.  N>1 is launched with torch.distributed.run (one rank per
+GPU, one imaging band per rank, no data-path collective: weak scaling across bands).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]/[2] geometry, one band per GPU
+    "c2": dict(nx=4096, ntime=775, nchan=16, precision="single", epsilon=1e-5,
+               name="pfb grid/sara C2: 4096^2, 8-band MeerKAT-like, 25.0M vis/band, fp32, eps=1e-5, one band per GPU"),
+    # configs[0]: the reference's own CPU-runnable case
+    "c1": dict(nx=2048, ntime=62, nchan=8, precision="double", epsilon=1e-5,
+               name="C1: 2048^2, 1.0M vis, fp64, eps=1e-5, single band"),
+}
+
+
+def algorithmic_bytes(info, nvis, nchan, p):
+    """B = nvis(5p+2+48/nchan) + 2 P (6 nu nv 2p + 3 nx ny p)."""
+    P, nu, nv, nx, ny = info["nplanes"], info["nu"], info["nv"], info["nx"], info["ny"]
+    return nvis * (5 * p + 2 + 48.0 / nchan) + 2.0 * P * (6.0 * nu * nv * 2 * p + 3.0 * nx * ny * p)
+
+
+def spread_kernel_bytes(info, nvis, nchan, p):
+    """Algorithmic bytes of one launch of the gridding (spreading) kernel: compulsory visibility
+    traffic (uvw 24/nchan + sorted index 4 + wgt p + vis 2p per sample) plus the plane stack
+    written once (RED to a zeroed grid = one read-modify-write pass: 2 * P nu nv 2p)."""
+    P, nu, nv = info["nplanes"], info["nu"], info["nv"]
+    return nvis * (3 * p + 4 + 24.0 / nchan) + 2.0 * P * nu * nv * 2 * p
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.samples, self.reasons, self.stop_flag = dev, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_inputs(cfg, band, with_vis=False):
+    from pfb_imaging_b200 import synth
+
+    d = synth.make_band(cfg["ntime"], cfg["nchan"], band=band, nband=8, precision=cfg["precision"], with_vis=with_vis)
+    cell = synth.default_cell(d["uvw"], 1712e6)  # one cell size for all bands (top of L-band)
+    rdt = np.float32 if cfg["precision"] == "single" else np.float64
+    x = synth.point_source_image(cfg["nx"], cfg["nx"], dtype=rdt)
+    return d, cell, x
+
+
+def cpu_hessian_sample(cfg, band, row_step, nthreads_note=True):
+    """Time the CPU restatement (oracle/cwgridder) on a bounded sample: the plane work (FFTs, screens)
+    in full, the per-visibility loops on every `row_step`-th row; extrapolate the latter."""
+    from oracle import cwgridder as cw
+    from pfb_imaging_b200.plan import make_plan, w_range
+
+    d, cell, x = make_inputs(cfg, band)
+    uvw, freq = d["uvw"], d["freq"]
+    wmin, wmax = w_range(uvw, freq)
+    nvis_full = uvw.shape[0] * freq.size
+    plan = make_plan(nx=cfg["nx"], ny=cfg["nx"], pixsize_x=cell, pixsize_y=cell, epsilon=cfg["epsilon"], flip_v=True,
+                     divide_by_n=False, sigma_min=1.1, sigma_max=3.0, precision=cfg["precision"], wmin=wmin, wmax=wmax,
+                     nvis=nvis_full)
+    sub = uvw[::row_step]
+    wgt = d["wgt"][::row_step].astype(np.float64)
+    mask = d["mask"][::row_step]
+    nvis_s = sub.shape[0] * freq.size
+    from oracle import wgridder_np as wg
+
+    wg._image_factors(plan)  # plan-level constants: set-up, not part of an apply (same on the GPU side)
+    t0 = time.perf_counter()
+    b = cw._bin(plan, sub, freq, mask)
+    t_bin = time.perf_counter() - t0
+    td, tg = {}, {}
+    mv = cw.dirty2vis_c(plan, sub, freq, x.astype(np.float64), mask, b=b, timings=td)
+    cw.vis2dirty_c(plan, sub, freq, mv, wgt, mask, b=b, timings=tg)
+    scale = nvis_full / nvis_s
+    t_planes = td["planes"] + tg["planes"]
+    t_vis = (td["vis"] + tg["vis"] + td["prep"] + tg["prep"]) * scale
+    t_full = t_planes + t_vis
+    return dict(value=nvis_full / t_full / 1e6, t_full=t_full, t_planes=t_planes, t_vis_sample=t_vis / scale,
+                t_bin_sample=t_bin, nvis_sample=nvis_s, nvis_full=nvis_full, cores=cw.nthreads(),
+                plan=dict(W=plan.W, sigma=plan.sigma, nu=plan.nu, nplanes=plan.nplanes))
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    vals, last = [], None
+    for _ in range(min(steps, 2)):  # each step = one bounded sample (tens of seconds of CPU work)
+        last = cpu_hessian_sample(cfg, 0, args.cpu_row_step)
+        vals.append(last["value"])
+    v = float(np.mean(vals))
+    sample = (f"every {args.cpu_row_step}th row of band 0 for the per-visibility loops ({last['nvis_sample']} vis, extrapolated "
+              f"to {last['nvis_full']}); plane FFTs/screens at full size; fp64 CPU restatement (ducc0 unavailable)")
+    line = {
+        "impl": "reference", "metric": "Mvis/s per Hessian apply (degrid+grid)", "value": v, "unit": "Mvis/s",
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * last["t_full"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["name"], "plan": last["plan"]},
+        "cpu_baseline": {"value": v, "unit": "Mvis/s", "cores": last["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mvis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from pfb_imaging_b200 import _lib, operators as ops, wgridder as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    band = rank % 8
+    d, cell, x = make_inputs(cfg, band)
+    uvw, freq = d["uvw"], d["freq"]
+    nvis = uvw.shape[0] * freq.size
+    p = 4 if cfg["precision"] == "single" else 8
+    gp = W.plan_for(uvw, freq, npix_x=cfg["nx"], npix_y=cfg["nx"], pixsize_x=cell, pixsize_y=cell,
+                    epsilon=cfg["epsilon"], flip_v=True, divide_by_n=False, precision=cfg["precision"],
+                    mask=d["mask"], sigma_min=1.1, sigma_max=3.0, device=local)
+    gp.bind_weights(d["wgt"])
+    info = gp.info()
+    wsum = float(d["wgt"].sum(dtype=np.float64))
+
+    tdt = torch.float32 if p == 4 else torch.float64
+    x_d = torch.from_numpy(x).to(dev)
+    out_d = torch.empty_like(x_d)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        gp.hessian_dev(x_d.data_ptr(), None, wsum, 0.0, out_d.data_ptr(), stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.load().pfbg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.load().pfbg_launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    nvis_all = torch.tensor([float(nvis)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(nvis_all, op=dist.ReduceOp.SUM)
+    value = float(nvis_all.item()) / (ms_step * 1e-3) / 1e6
+
+    # ---- per-phase timing of the dominant kernel (events inside the library, same stream) ---
+    gp.set_profiling(True)
+    phase = []
+    for _ in range(3):
+        step_dev()
+        torch.cuda.synchronize()
+        phase.append(gp.timings())
+    gp.set_profiling(False)
+    ph = np.median(np.array(phase), axis=0).tolist()
+    names = ["stage_in", "pad_screen_fft", "degrid", "zero_grid", "spread", "fft_crop_screen", "stage_out"]
+    phases = dict(zip(names, ph))
+
+    # ---- end to end through the operator call a pfb solver makes (host numpy in/out) ------
+    kw = dict(uvw=uvw, weight=d["wgt"], vis_mask=d["mask"], freq=freq, cell=cell, epsilon=cfg["epsilon"],
+              wsum=wsum, flip_v=True)
+    ops.clear_plan_cache()
+    xo = np.empty_like(x)
+    for _ in range(2):
+        ops.hessian_slice(x, xout=xo, **kw)  # first call binds the band (like load_band); later calls hit the cache
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ops.hessian_slice(x, xout=xo, **kw)
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = float(nvis_all.item()) / float(te.item()) / 1e6
+    ops.clear_plan_cache()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        B = algorithmic_bytes(info, nvis, freq.size, p)
+        dom = max(("degrid", "spread", "pad_screen_fft", "fft_crop_screen"), key=lambda k: phases.get(k, 0.0))
+        kb = spread_kernel_bytes(info, nvis, freq.size, p)
+        k_ms = phases.get("spread", float("nan"))
+        roof = {
+            "bound": "hbm", "kernel": "k_grid (spreading kernel, one launch per Hessian apply)",
+            "achieved": kb / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": kb / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "kernel_ms": k_ms, "algorithmic_bytes_per_launch": kb,
+            "step_algorithmic_bytes": B, "step_achieved": B / (ms_step * 1e-3) / 1e9,
+            "step_frac": B / (ms_step * 1e-3) / 1e9 / peak, "step_frac_of_nominal_8TBs": B / (ms_step * 1e-3) / 1e9 / 8000.0,
+            "dominant_phase": dom, "phases_ms": phases,
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            c = cpu_hessian_sample(cfg, band, args.cpu_row_step)
+            cpu = {"value": c["value"], "unit": "Mvis/s", "cores": c["cores"], "kind": "port",
+                   "sample": (f"every {args.cpu_row_step}th row for the per-visibility loops ({c['nvis_sample']} of {c['nvis_full']} vis, "
+                              f"extrapolated), plane FFTs at full size; fp64 C/OpenMP restatement + scipy.fft (ducc0 unavailable); "
+                              f"planes {c['t_planes']:.1f}s, vis(sample) {c['t_vis_sample']:.1f}s")}
+        img_bytes = int(x.nbytes)
+        line = {
+            "metric": "Mvis/s per Hessian apply (degrid+grid)", "value": value, "unit": "Mvis/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if p == 4 else "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "bands": world, "nvis_per_band": nvis, "l2": "inputs larger than L2 (plane stack %.1f GB per band)" % (info["grid_bytes"] / 1e9),
+                       "plan": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "beta")},
+                       "parallelism": f"band-sharded x{world}, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "Mvis/s", "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
+                    "call": "operators.hessian_slice(x, uvw=, weight=, vis_mask=, freq=, ...) with host numpy in/out; band geometry pinned on first call"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    gp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-row-step", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+/* TEST INFRASTRUCTURE ONLY — C/OpenMP restatement of the per-visibility loops of the
+ * w-stacked gridder (the CPU baseline timed by bench.py and a fast checker for tests).
+ *
+ * The algorithm is the published one of ducc0.wgridder 0.41.0 (Arras et al. 2021, A&A 646
+ * A58), a third-party dependency of the reference (/root/reference/pyproject.toml:42,
+ * uv.lock:1119-1120) whose source is not in the reference tree; call sites:
+ * /root/reference/src/pfb_imaging/operators/gridder.py:78-100,128-143 and
+ * operators/hessian.py:50-89.  Like ducc0, each thread accumulates a uv tile (+halo) of the
+ * W planes a bucket touches in a private buffer and flushes it to the shared grid.
+ * Coordinates / bucket order come from oracle/wgridder_np.py:bin_indices (bit-exact spec);
+ * the FFTs and image-space factors stay in numpy/scipy (oracle/cwgridder.py).
+ *
+ * Parity: pinned against the explicit DFT and the golden vectors through
+ * tests/test_oracle.py; parity with ducc0's own binary output is unpinned (ducc0 cannot be
+ * installed here).  Nothing under pfb-imaging_b200/ links or calls this file.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define TILE 16
+#define MAXW 16
+
+static inline double es(double x, double beta) {
+  double a = (1.0 - x) * (1.0 + x);
+  return a < 0.0 ? 0.0 : exp(beta * (sqrt(a) - 1.0));
+}
+
+static inline int wrapi(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+int cw_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* Spread n samples (already in bucket order) onto grid[P][nu][nv] (interleaved re,im). */
+void cw_grid(int64_t n, const int64_t* order, const double* gu, const double* gv, const double* gw,
+             const int32_t* iu0, const int32_t* iv0, const int32_t* ip0, const uint64_t* key,
+             const double* a /* 2n: re,im of weight*phase*vis */, int W, double beta, int nu, int nv,
+             int P, int do_w, double* grid) {
+  const int npl = do_w ? W : 1;
+  const int side = TILE + MAXW;
+  const int64_t plane = (int64_t)nu * nv;
+#pragma omp parallel
+  {
+    double* buf = (double*)calloc((size_t)npl * side * side * 2, sizeof(double));
+    int64_t cur = -1;
+    int bu = 0, bv = 0, bp = 0;
+    double ku[MAXW], kv[MAXW], kw[MAXW];
+#pragma omp for schedule(dynamic, 4096)
+    for (int64_t s = 0; s < n; ++s) {
+      int64_t k = order[s];
+      int64_t bucket = (int64_t)(key[k] / (TILE * TILE));
+      if (bucket != cur) {
+        if (cur >= 0) { /* flush */
+          for (int q = 0; q < npl; ++q)
+            for (int i = 0; i < TILE + W - 1; ++i) {
+              int iu = wrapi(bu + i, nu);
+              for (int j = 0; j < TILE + W - 1; ++j) {
+                double re = buf[((q * side + i) * side + j) * 2], im = buf[((q * side + i) * side + j) * 2 + 1];
+                if (re != 0.0 || im != 0.0) {
+                  int iv = wrapi(bv + j, nv);
+                  double* g = grid + ((int64_t)(bp + q) * plane + (int64_t)iu * nv + iv) * 2;
+#pragma omp atomic
+                  g[0] += re;
+#pragma omp atomic
+                  g[1] += im;
+                }
+              }
+            }
+          memset(buf, 0, (size_t)npl * side * side * 2 * sizeof(double));
+        }
+        cur = bucket;
+        bu = (wrapi(iu0[k], nu) / TILE) * TILE;
+        bv = (wrapi(iv0[k], nv) / TILE) * TILE;
+        bp = ip0[k];
+      }
+      for (int j = 0; j < W; ++j) {
+        ku[j] = es(((double)(iu0[k] + j) - gu[k]) * (2.0 / W), beta);
+        kv[j] = es(((double)(iv0[k] + j) - gv[k]) * (2.0 / W), beta);
+        kw[j] = do_w ? es(((double)(ip0[k] + j) - gw[k]) * (2.0 / W), beta) : 1.0;
+      }
+      int ou = wrapi(iu0[k], nu) - bu, ov = wrapi(iv0[k], nv) - bv;
+      double are = a[2 * k], aim = a[2 * k + 1];
+      for (int q = 0; q < npl; ++q) {
+        double qre = are * kw[q], qim = aim * kw[q];
+        for (int i = 0; i < W; ++i) {
+          double ire = qre * ku[i], iim = qim * ku[i];
+          double* row = buf + ((q * side + ou + i) * side + ov) * 2;
+          for (int j = 0; j < W; ++j) {
+            row[2 * j] += ire * kv[j];
+            row[2 * j + 1] += iim * kv[j];
+          }
+        }
+      }
+    }
+    if (cur >= 0) {
+      for (int q = 0; q < npl; ++q)
+        for (int i = 0; i < TILE + W - 1; ++i) {
+          int iu = wrapi(bu + i, nu);
+          for (int j = 0; j < TILE + W - 1; ++j) {
+            double re = buf[((q * side + i) * side + j) * 2], im = buf[((q * side + i) * side + j) * 2 + 1];
+            if (re != 0.0 || im != 0.0) {
+              int iv = wrapi(bv + j, nv);
+              double* g = grid + ((int64_t)(bp + q) * plane + (int64_t)iu * nv + iv) * 2;
+#pragma omp atomic
+              g[0] += re;
+#pragma omp atomic
+              g[1] += im;
+            }
+          }
+        }
+    }
+    free(buf);
+  }
+}
+
+/* Gather: out[2k..] = sum over the W^3 support of grid * weights, for every sample. */
+void cw_degrid(int64_t n, const int64_t* order, const double* gu, const double* gv, const double* gw,
+               const int32_t* iu0, const int32_t* iv0, const int32_t* ip0, int W, double beta, int nu,
+               int nv, int P, int do_w, const double* grid, double* out) {
+  const int npl = do_w ? W : 1;
+  const int64_t plane = (int64_t)nu * nv;
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t s = 0; s < n; ++s) {
+    int64_t k = order[s];
+    double ku[MAXW], kv[MAXW], kw[MAXW];
+    int ivs[MAXW];
+    for (int j = 0; j < W; ++j) {
+      ku[j] = es(((double)(iu0[k] + j) - gu[k]) * (2.0 / W), beta);
+      kv[j] = es(((double)(iv0[k] + j) - gv[k]) * (2.0 / W), beta);
+      kw[j] = do_w ? es(((double)(ip0[k] + j) - gw[k]) * (2.0 / W), beta) : 1.0;
+      ivs[j] = wrapi(wrapi(iv0[k], nv) + j, nv);
+    }
+    double re = 0.0, im = 0.0;
+    for (int q = 0; q < npl; ++q) {
+      double pre = 0.0, pim = 0.0;
+      for (int i = 0; i < W; ++i) {
+        int iu = wrapi(wrapi(iu0[k], nu) + i, nu);
+        const double* row = grid + ((int64_t)(ip0[k] + q) * plane + (int64_t)iu * nv) * 2;
+        double rre = 0.0, rim = 0.0;
+        for (int j = 0; j < W; ++j) {
+          rre += row[2 * ivs[j]] * kv[j];
+          rim += row[2 * ivs[j] + 1] * kv[j];
+        }
+        pre += rre * ku[i];
+        pim += rim * ku[i];
+      }
+      re += pre * kw[q];
+      im += pim * kw[q];
+    }
+    out[2 * k] = re;
+    out[2 * k + 1] = im;
+  }
+}

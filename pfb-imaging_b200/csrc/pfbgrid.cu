@@ -428,7 +428,6 @@ template <typename T>
 static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs, int64_t cs, const void* wgt,
                       int vis_sorted, int apply_phase) {
   using C = typename cplx_of<T>::type;
-  CK(cudaMemsetAsync(pl->grid.p, 0, pl->grid.bytes, s));
   if (pl->nactive > 0) {
     k_grid_direct<T><<<grid_blocks(pl, pl->nactive), 256, 0, s>>>(
         pl->gp, (const double*)pl->uvw.p, (const double*)pl->fscale.p, (const uint32_t*)pl->sorted_idx.p, pl->nactive,
@@ -500,6 +499,7 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
   }
   if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
   mark(pl, s);
+  CK(cudaMemsetAsync(pl->grid.p, 0, pl->grid.bytes, s));
   CKRC(DISPATCH(run_spread, pl, s, dvis, vis_rs, vis_cs, dwgt, 0, 1));
   mark(pl, s);
   CKRC(fft_exec(pl, s, CUFFT_INVERSE));
@@ -581,6 +581,8 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   CKRC(DISPATCH(run_gather, pl, s, nullptr, nullptr, pl->mvis.p, 0));
   mark(pl, s);
   // R^H W: spread (weights applied on load), FFT, screen + crop + epilogue
+  CK(cudaMemsetAsync(pl->grid.p, 0, pl->grid.bytes, s));
+  mark(pl, s);
   CKRC(DISPATCH(run_spread, pl, s, pl->mvis.p, 0, 0, dwgt, 1, 0));
   mark(pl, s);
   CKRC(fft_exec(pl, s, CUFFT_INVERSE));

@@ -167,7 +167,7 @@ def make_plan(
     *, nx, ny, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
     flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
     sigma_min=1.1, sigma_max=2.6, precision="double", wmin=0.0, wmax=0.0, nvis=0,
-    force_sigma=None, force_W=None,
+    force_sigma=None, force_W=None, safety=None,
 ) -> Plan:
     """Choose (sigma, W, beta, nu, nv, planes) for one gridder geometry."""
     nx, ny = int(nx), int(ny)
@@ -202,8 +202,15 @@ def make_plan(
     else:
         nshift, numax = 0.0, 0.0
 
+    # Error budget: the 1-D kernel error must stay below epsilon / safety.  Double precision
+    # splits epsilon linearly over the interpolated axes (worst-case sum; this is what keeps the
+    # max-abs bound of /root/reference/tests/test_hessian_approx.py:188-231 at epsilon=1e-10),
+    # single precision splits it in quadrature (the contract there is the relative L2 norm and
+    # fp32 round-off, not the kernel, sets the max-abs floor).
     ndim = 3 if do_wgridding else 2
-    target = epsilon / math.sqrt(ndim)
+    if safety is None:
+        safety = float(ndim) if precision == "double" else math.sqrt(ndim)
+    target = epsilon / safety
 
     sig_lo = max(float(sigma_min), kt.SIGMAS[0])
     sig_hi = max(min(float(sigma_max), kt.SIGMAS[-1]), sig_lo)
