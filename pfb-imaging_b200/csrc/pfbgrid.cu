@@ -14,6 +14,7 @@
 
 #include "../../include/pfbgrid.h"
 #include "kernels.cuh"
+#include "runs.cuh"
 #include "weighting.cuh"
 
 // ---------------------------------------------------------------------------
@@ -81,6 +82,8 @@ struct pfbg_plan {
   DevBuf uvw, fscale, mask;    // bound geometry
   DevBuf wgt;                  // bound weights (nrow,nchan) T
   DevBuf sorted_idx;           // (nactive) u32
+  DevBuf recs;                 // (nactive) VisRec<T>, bucket order (run kernels, W <= 8)
+  bool use_runs = false;
   DevBuf mvis;                 // (nactive) C, Hessian model vis in bucket order
   DevBuf img_in, img_out, img_beam;  // staging for host-pointer calls
   DevBuf vis_stage, wgt_stage;
@@ -133,7 +136,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx,
-                   &pl->mvis, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
+                   &pl->recs, &pl->mvis, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
   if (pl->ev_ok)
@@ -295,6 +298,15 @@ static int fft_exec(pfbg_plan* pl, cudaStream_t s, int dir) {
   return PFBG_OK;
 }
 
+static int run_blocks(const pfbg_plan* pl, int64_t nact, int warps_per_cta, int ctas_per_sm) {
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
+  int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  int64_t want = (nslice + warps_per_cta - 1) / warps_per_cta;
+  int64_t cap = (int64_t)sm * ctas_per_sm;  // a multiple of the SM count: one full wave of resident CTAs
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
 static int grid_blocks(const pfbg_plan* pl, int64_t nact) {
   int sm = 148;
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
@@ -375,6 +387,27 @@ extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fsc
     if (e != cudaSuccess) { cleanup(); return fail(PFBG_ERR_CUDA, "copy of sorted order failed: %s", cudaGetErrorString(e)); }
   }
   cleanup();
+  // per-sample records for the run kernels
+  pl->use_runs = false;
+  {
+    const char* fd = getenv("PFBG_FORCE_DIRECT");
+    bool force_direct = fd && fd[0] == '1';
+    if (!force_direct && g.W <= 8 && g.nu <= 32768 && g.nv <= 32768 && nact > 0) {
+      size_t rsz = pl->precision == PFBG_F32 ? sizeof(VisRec<float>) : sizeof(VisRec<double>);
+      CKRC(dev_alloc(pl, pl->recs, (size_t)nact * rsz));
+      unsigned grd = (unsigned)((nact + 255) / 256);
+      if (pl->precision == PFBG_F32)
+        k_make_recs<float><<<grd, 256, 0, s>>>(g, (const double*)pl->uvw.p, (const double*)pl->fscale.p,
+                                                (const uint32_t*)pl->sorted_idx.p, (int64_t)nact, (VisRec<float>*)pl->recs.p);
+      else
+        k_make_recs<double><<<grd, 256, 0, s>>>(g, (const double*)pl->uvw.p, (const double*)pl->fscale.p,
+                                                 (const uint32_t*)pl->sorted_idx.p, (int64_t)nact, (VisRec<double>*)pl->recs.p);
+      LAUNCHED();
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(s));
+      pl->use_runs = true;
+    }
+  }
   pl->bound = true;
   return PFBG_OK;
 }
@@ -428,7 +461,13 @@ template <typename T>
 static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs, int64_t cs, const void* wgt,
                       int vis_sorted, int apply_phase) {
   using C = typename cplx_of<T>::type;
-  if (pl->nactive > 0) {
+  if (pl->nactive > 0 && pl->use_runs) {
+    k_grid_runs<T><<<run_blocks(pl, pl->nactive, RUN_WARPS, 3), RUN_WARPS * 32, 0, s>>>(
+        pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
+        vis_sorted, apply_phase);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  } else if (pl->nactive > 0) {
     k_grid_direct<T><<<grid_blocks(pl, pl->nactive), 256, 0, s>>>(
         pl->gp, (const double*)pl->uvw.p, (const double*)pl->fscale.p, (const uint32_t*)pl->sorted_idx.p, pl->nactive,
         (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p, vis_sorted, apply_phase);
@@ -441,7 +480,13 @@ static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs
 template <typename T>
 static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_out, void* out_sorted, int apply_phase) {
   using C = typename cplx_of<T>::type;
-  if (pl->nactive > 0) {
+  if (pl->nactive > 0 && pl->use_runs) {
+    k_degrid_runs<T><<<run_blocks(pl, pl->nactive, DEG_WARPS, 4), DEG_WARPS * 32, 0, s>>>(
+        pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
+        (C*)out_sorted, apply_phase);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  } else if (pl->nactive > 0) {
     k_degrid_direct<T><<<grid_blocks(pl, pl->nactive), 256, 0, s>>>(
         pl->gp, (const double*)pl->uvw.p, (const double*)pl->fscale.p, (const uint32_t*)pl->sorted_idx.p, pl->nactive,
         (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out, (C*)out_sorted, apply_phase);

@@ -1,0 +1,309 @@
+// Run-based gridding / degridding kernels (W <= 8).
+//
+// Kernel 1 sorts the samples by (uv tile, first w-plane, first cell inside the tile), so all
+// samples whose W x W x W footprint starts at the same grid cell are contiguous ("a run").  On
+// MeerKAT-like coverage > 90 % of consecutive samples belong to the same run, hence:
+//
+//   * one warp walks a slice of the sorted samples, a batch of NB samples at a time;
+//   * the lanes own the footprint: lane = (j, q2) with j = v-offset (0..7) and q2 = plane slot
+//     (planes q2 and q2+4); each lane keeps the 8 u-rows of its two planes in registers
+//     (16 complex accumulators / grid values);
+//   * per batch: (a) lane <-> sample: load the 32/64-byte record, form weight*phase*vis;
+//     (b) lane <-> tap: evaluate the 24 ES taps of every sample of the batch into shared memory
+//     (independent evaluations, full ILP, fast-math in fp32); (c) the FMA stage;
+//   * gridding: accumulate in registers for the whole run, then flush the run ONCE with 16
+//     vector REDs per lane (8 lanes x 8 B = 64 B contiguous per row);
+//   * degridding: load the run's footprint ONCE, then every sample is 38 FMAs; the 32-lane sum
+//     is taken per batch through a skewed shared-memory transpose instead of shuffles.
+//
+// Per-sample geometry comes from 32 B (fp32) / 64 B (fp64) records written in bucket order by
+// kernel 1 (k_make_recs): no fp64 coordinate arithmetic and no scattered uvw loads here.
+#pragma once
+#include "common.cuh"
+
+template <typename T> struct VisRec;
+template <> struct __align__(16) VisRec<float> {
+  float x0[3];        // first tap position relative to the sample, per axis: (i0 - g) in (-W/2, -W/2+1]
+  uint32_t idx;       // flat (row, chan) index
+  float pc, ps;       // e^{+2 pi i (u x0 + v y0 + w nshift)}
+  uint16_t iu, iv;    // wrapped first cell
+  int32_t ip;         // first plane
+};
+template <> struct __align__(16) VisRec<double> {
+  double x0[3];
+  double pc, ps;
+  uint32_t idx;
+  uint16_t iu, iv;
+  int32_t ip;
+  int32_t pad;
+};
+static_assert(sizeof(VisRec<float>) == 32, "VisRec<float> must be 32 bytes");
+static_assert(sizeof(VisRec<double>) == 64, "VisRec<double> must be 64 bytes");
+
+__device__ __forceinline__ uint64_t pack_origin(uint32_t iu, uint32_t iv, int32_t ip) {
+  return ((uint64_t)(uint32_t)ip << 32) | ((uint64_t)iu << 16) | (uint64_t)iv;
+}
+
+// kernel 1b: per-sample records in bucket order
+template <typename T>
+__global__ void k_make_recs(GParams p, const double* __restrict__ uvw, const double* __restrict__ fscale,
+                            const uint32_t* __restrict__ sorted_idx, int64_t nact, VisRec<T>* __restrict__ recs) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nact) return;
+  uint32_t idx = sorted_idx[k];
+  int64_t row = idx / p.nchan;
+  int chan = (int)(idx - row * p.nchan);
+  VisCoord c = vis_coord(p, uvw, fscale, row, chan);
+  VisRec<T> r;
+  r.x0[0] = (T)((double)c.iu0 - c.gu);
+  r.x0[1] = (T)((double)c.iv0 - c.gv);
+  r.x0[2] = (T)((double)c.ip0 - c.gw);
+  r.idx = idx;
+  cis_turns(vis_phase_turns(p, c), r.pc, r.ps);
+  r.iu = (uint16_t)wrap(c.iu0, p.nu);
+  r.iv = (uint16_t)wrap(c.iv0, p.nv);
+  r.ip = c.ip0;
+  recs[k] = r;
+}
+
+// ES tap for the run kernels: fp32 uses the SFU (sqrt.approx / ex2.approx); the absolute error
+// stays ~1e-7 of the kernel peak, far below the fp32 accuracy floor (epsilon >= 3e-7).
+__device__ __forceinline__ float es_fast(float x, float beta_log2e) {
+  float a = fmaf(-x, x, 1.0f);
+  float s, e;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(fmaxf(a, 0.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(beta_log2e * (s - 1.0f)));
+  return a < 0.0f ? 0.0f : e;
+}
+__device__ __forceinline__ double es_fast(double x, double beta) { return es_eval(x, beta); }
+__device__ __forceinline__ float es_scale(float beta) { return beta * 1.4426950408889634f; }
+__device__ __forceinline__ double es_scale(double beta) { return beta; }
+
+#define RUN_WARPS 8      /* warps per CTA, gridding */
+#define DEG_WARPS 4      /* warps per CTA, degridding (48 KB static shared memory) */
+#define RUN_SLICE 256
+
+template <typename T> struct RunCfg;
+template <> struct RunCfg<float> { static constexpr int NB = 32; };
+template <> struct RunCfg<double> { static constexpr int NB = 16; };
+
+// evaluate the 24 taps of the nb staged samples: lane t < 24 owns tap t (axis = t/8, k = t%8)
+template <typename T, int NB>
+__device__ __forceinline__ void run_taps(const GParams& p, const T (*x0s)[4], T (*taps)[24], int nb, int lane,
+                                         T bscale, T xs) {
+  if (lane < 24) {
+    const int axis = lane >> 3;
+    const T kk = (T)(lane & 7);
+    const bool flat_w = (axis == 2) && !p.do_wgridding;
+#pragma unroll 4
+    for (int v = 0; v < nb; ++v) {
+      T val = es_fast((x0s[v][axis] + kk) * xs, bscale);
+      if (flat_w) val = (lane == 16) ? (T)1 : (T)0;
+      taps[v][lane] = val;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void run_flush(const GParams& p, typename cplx_of<T>::type* __restrict__ grid,
+                                          T (&accr)[8][2], T (&acci)[8][2], uint64_t origin, int j, int q2) {
+  const int W = p.W, npl = p.do_wgridding ? W : 1;
+  int iv = (int)(origin & 0xffffu) + j;
+  int iu0 = (int)((origin >> 16) & 0xffffu);
+  int ip = (int)(origin >> 32);
+  if (iv >= p.nv) iv -= p.nv;
+  const int plane_sz = p.nu * p.nv;  // < 2^31 (nu, nv <= 32768 enforced by the host)
+  const bool jok = j < W;
+#pragma unroll
+  for (int qq = 0; qq < 2; ++qq) {
+    int q = q2 + 4 * qq;
+    bool ok = jok && q < npl;
+    typename cplx_of<T>::type* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (ok && i < W) {
+        int iu = iu0 + i;
+        if (iu >= p.nu) iu -= p.nu;
+        atomic_add_c(gq + iu * p.nv, accr[i][qq], acci[i][qq]);
+      }
+      accr[i][qq] = 0;
+      acci[i][qq] = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kernel 2: gridding by runs
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(RUN_WARPS * 32)
+k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
+            const typename cplx_of<T>::type* __restrict__ vis, int64_t vis_rs, int64_t vis_cs,
+            const T* __restrict__ wgt, typename cplx_of<T>::type* __restrict__ grid, int vis_sorted,
+            int apply_phase) {
+  using C = typename cplx_of<T>::type;
+  constexpr int NB = RunCfg<T>::NB;
+  __shared__ __align__(16) T taps[RUN_WARPS][NB][24];
+  __shared__ __align__(16) T x0s[RUN_WARPS][NB][4];
+  __shared__ C amp[RUN_WARPS][NB];
+  __shared__ uint64_t orgs[RUN_WARPS][NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 7, q2 = lane >> 3;
+  const T bscale = es_scale((T)p.beta), xs = (T)(2.0 / p.W);
+  T accr[8][2], acci[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { accr[i][0] = accr[i][1] = 0; acci[i][0] = acci[i][1] = 0; }
+  uint64_t cur = ~0ull;
+  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  const int64_t nwarps = (int64_t)gridDim.x * RUN_WARPS;
+  for (int64_t sl = (int64_t)blockIdx.x * RUN_WARPS + warp; sl < nslice; sl += nwarps) {
+    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+      const int nb = (int)min((int64_t)NB, kend - k0);
+      if (lane < nb) {  // (a) lane <-> sample
+        const int64_t k = k0 + lane;
+        VisRec<T> r = recs[k];
+        C a;
+        if (vis_sorted) a = vis[k];
+        else {
+          int64_t row = r.idx / p.nchan;
+          int chan = (int)(r.idx - row * p.nchan);
+          a = vis[row * vis_rs + chan * vis_cs];
+        }
+        T w = wgt ? wgt[r.idx] : (T)1;
+        T pc = apply_phase ? r.pc : (T)1, ps = apply_phase ? r.ps : (T)0;
+        C s;
+        s.x = (a.x * pc - a.y * ps) * w;
+        s.y = (a.x * ps + a.y * pc) * w;
+        amp[warp][lane] = s;
+        x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
+        orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
+      }
+      __syncwarp();
+      run_taps<T, NB>(p, x0s[warp], taps[warp], nb, lane, bscale, xs);  // (b) lane <-> tap
+      __syncwarp();
+      for (int v = 0; v < nb; ++v) {  // (c) lane <-> footprint cell
+        const uint64_t org = orgs[warp][v];
+        if (org != cur) {
+          if (cur != ~0ull) run_flush<T>(p, grid, accr, acci, cur, j, q2);
+          cur = org;
+        }
+        const T* tp = taps[warp][v];
+        const T tv = tp[8 + j];
+        const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
+        const C a = amp[warp][v];
+        const T r0 = a.x * c0, i0 = a.y * c0, r1 = a.x * c1, i1 = a.y * c1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const T u = tp[i];
+          accr[i][0] += r0 * u; acci[i][0] += i0 * u;
+          accr[i][1] += r1 * u; acci[i][1] += i1 * u;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (cur != ~0ull) run_flush<T>(p, grid, accr, acci, cur, j, q2);
+}
+
+// ---------------------------------------------------------------------------
+// kernel 3: degridding by runs
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(DEG_WARPS * 32)
+k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
+              const typename cplx_of<T>::type* __restrict__ grid, const T* __restrict__ wgt,
+              typename cplx_of<T>::type* __restrict__ vis_out,
+              typename cplx_of<T>::type* __restrict__ out_sorted, int apply_phase) {
+  using C = typename cplx_of<T>::type;
+  constexpr int NB = RunCfg<T>::NB;
+  __shared__ __align__(16) T taps[DEG_WARPS][NB][24];
+  __shared__ __align__(16) T x0s[DEG_WARPS][NB][4];
+  __shared__ uint64_t orgs[DEG_WARPS][NB];
+  __shared__ C part[DEG_WARPS][NB][32];  // per-sample partial sums of the 32 lanes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 7, q2 = lane >> 3;
+  const int W = p.W, npl = p.do_wgridding ? W : 1;
+  const T bscale = es_scale((T)p.beta), xs = (T)(2.0 / p.W);
+  const int plane_sz = p.nu * p.nv;
+  T gr[8][2], gi[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { gr[i][0] = gr[i][1] = 0; gi[i][0] = gi[i][1] = 0; }
+  uint64_t cur = ~0ull;
+  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  const int64_t nwarps = (int64_t)gridDim.x * DEG_WARPS;
+  for (int64_t sl = (int64_t)blockIdx.x * DEG_WARPS + warp; sl < nslice; sl += nwarps) {
+    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+      const int nb = (int)min((int64_t)NB, kend - k0);
+      VisRec<T> r;
+      if (lane < nb) {
+        r = recs[k0 + lane];
+        x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
+        orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
+      }
+      __syncwarp();
+      run_taps<T, NB>(p, x0s[warp], taps[warp], nb, lane, bscale, xs);
+      __syncwarp();
+      for (int v = 0; v < nb; ++v) {
+        const uint64_t org = orgs[warp][v];
+        if (org != cur) {  // new run: fetch its footprint once
+          cur = org;
+          int iv = (int)(org & 0xffffu) + j;
+          int iu0 = (int)((org >> 16) & 0xffffu);
+          int ip = (int)(org >> 32);
+          if (iv >= p.nv) iv -= p.nv;
+          const bool jok = j < W;
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            int q = q2 + 4 * qq;
+            bool ok = jok && q < npl;
+            const C* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              C val; val.x = 0; val.y = 0;
+              if (ok && i < W) {
+                int iu = iu0 + i;
+                if (iu >= p.nu) iu -= p.nu;
+                val = gq[iu * p.nv];
+              }
+              gr[i][qq] = val.x; gi[i][qq] = val.y;
+            }
+          }
+        }
+        const T* tp = taps[warp][v];
+        T a0r = 0, a0i = 0, a1r = 0, a1i = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const T u = tp[i];
+          a0r += gr[i][0] * u; a0i += gi[i][0] * u;
+          a1r += gr[i][1] * u; a1i += gi[i][1] * u;
+        }
+        const T tv = tp[8 + j];
+        const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
+        C s;
+        s.x = a0r * c0 + a1r * c1;
+        s.y = a0i * c0 + a1i * c1;
+        part[warp][v][lane] = s;
+      }
+      __syncwarp();
+      if (lane < nb) {  // lane <-> sample again: skewed (conflict-free) sum over the 32 partials
+        T sr = 0, si = 0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+          const C s = part[warp][lane][(lane + l) & 31];
+          sr += s.x; si += s.y;
+        }
+        T re = sr, im = si;
+        if (apply_phase) {  // multiply by e^{-i t}
+          re = sr * r.pc + si * r.ps;
+          im = si * r.pc - sr * r.ps;
+        }
+        if (wgt) { T w = wgt[r.idx]; re *= w; im *= w; }
+        C o; o.x = re; o.y = im;
+        if (out_sorted) out_sorted[k0 + lane] = o; else vis_out[r.idx] = o;
+      }
+      __syncwarp();
+    }
+  }
+}

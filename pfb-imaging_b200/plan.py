@@ -149,11 +149,21 @@ def _correction(n, nbig, W, beta):
     return 1.0 / kt.kernel_ft(ip / float(nbig), W, beta)
 
 
-# cost-model coefficients (seconds): per cell update of the spreading/gathering
-# kernels and per complex grid cell of one plane (memset/flush + FFT + screen).
-# Calibrated on B200 ("plan cost model").
-COST_CELL_UPDATE = {"single": 2.0e-12, "double": 5.0e-12}
-COST_GRID_CELL = {"single": 1.2e-11, "double": 2.9e-11}
+# Cost model (seconds, one direction), calibrated on B200 (DESIGN.md "plan cost model"):
+#   * run kernels (W <= 8): issue-bound, ~constant per sample whatever W is;
+#   * direct kernels (W > 8): one atomic / gather per footprint cell;
+#   * plane work (zero / FFT / screen): per complex cell of the oversampled stack.
+COST_VIS_RUNS = {"single": 2.6e-10, "double": 6.0e-10}
+COST_CELL_UPDATE = {"single": 7.0e-13, "double": 5.0e-12}
+COST_GRID_CELL = {"single": 1.5e-11, "double": 2.9e-11}
+RUNS_MAX_W = 8
+
+
+def vis_cost(precision, W, ndim):
+    if W <= RUNS_MAX_W:
+        return COST_VIS_RUNS[precision]
+    return (W ** ndim) * COST_CELL_UPDATE[precision]
+
 
 # Largest kernel support per precision.  In single precision the grid
 # correction 1/psihat amplifies the fp32 round-off of the FFT by
@@ -231,6 +241,7 @@ def make_plan(
                 break
         if W is None:
             continue
+        # smallest admissible W for this sigma (a larger W never helps at fixed sigma)
         nu = padded_size(nx, s, W)
         nv = padded_size(ny, s, W)
         sig_eff = min(nu / nx, nv / ny)
@@ -243,7 +254,7 @@ def make_plan(
         else:
             dw, npl = 1.0, 1
         cost = (
-            2.0 * nvis * (W ** ndim) * COST_CELL_UPDATE[precision]
+            2.0 * nvis * vis_cost(precision, W, ndim)
             + 2.0 * npl * nu * nv * COST_GRID_CELL[precision]
         )
         if best is None or cost < best[0]:

@@ -57,6 +57,9 @@ def test_kat_wgridder_conventions(gpu, k):
 def test_psfvis_delta_1e10(gpu, center):
     """tests/test_hessian_approx.py:188-231: analytic off-centre point source == dirty2vis(delta), 1e-10."""
     npix, pix, uvw, freq = seed42_array(nsub=7)
+    # The reference runs this on a ~km-scale MS; the seed-42 array has 10x longer baselines, whose
+    # ~1e4-turn phases put the fp64 rounding floor of the *analytic* expression itself at ~1e-10.
+    uvw = 0.1 * uvw
     fu, fv, fw, x0, y0 = ops.wgridder_conventions(*center)
     eps = 1e-10
     n = np.sqrt(1 - x0**2 - y0**2)
@@ -194,7 +197,8 @@ def test_hessian_slice_matches_composition(gpu, prec):
     # zero input short-circuit, xout reuse, cache hit and invalidation on in-place edits
     assert not ops.hessian_slice(np.zeros_like(x), **kw).any()
     xo = np.empty_like(x)
-    assert ops.hessian_slice(x, xout=xo, **kw) is xo and rel_l2(xo, h) <= 1e-12
+    assert ops.hessian_slice(x, xout=xo, **kw) is xo
+    assert rel_l2(xo, h) <= (1e-13 if prec == "double" else 1e-6)  # atomics: summation order varies
     wgt *= 2.0
     kw["wsum"] = 2 * wsum
     h2 = ops.hessian_slice(x, **kw)
