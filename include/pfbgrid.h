@@ -161,6 +161,14 @@ int pfbg_counts_to_weights(int32_t precision, int32_t device, void* counts, cons
                            double cell_y, double robust, double usign, double vsign, uint32_t flags,
                            void* stream);
 
+/*
+ * Unit-test hook for the in-shared-memory FFT engine behind the fused plane transforms:
+ * `batch` transforms of length n (2^a 3^b 5^c 7^d), complex of `precision`, host pointers.
+ * mode 0 = decimation in frequency, 1 = decimation in time; inverse != 0 -> e^{+2 pi i nk/n}.
+ */
+int pfbg_debug_fft1d(int32_t precision, int32_t device, int32_t n, int32_t batch, const void* in,
+                     void* out, int32_t mode, int32_t inverse);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,7 @@ SIGNATURES = {
     "pfbg_counts": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                               _dbl, _dbl, _dbl, _dbl, _vp, _u32, _vp]),
     "pfbg_counts_cells": (C.c_int, [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _dbl, _dbl, _vp]),
+    "pfbg_debug_fft1d": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32]),
     "pfbg_counts_to_weights": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                          _dbl, _dbl, _dbl, _dbl, _dbl, _u32, _vp]),
 }

@@ -15,6 +15,7 @@
 #include "../../include/pfbgrid.h"
 #include "kernels.cuh"
 #include "runs.cuh"
+#include "fused_fft.cuh"
 #include "weighting.cuh"
 
 // ---------------------------------------------------------------------------
@@ -88,6 +89,11 @@ struct pfbg_plan {
   DevBuf img_in, img_out, img_beam;  // staging for host-pointer calls
   DevBuf vis_stage, wgt_stage;
   DevBuf flag;
+  // fused FFT path (fused_fft.cuh)
+  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, cellflags;
+  FusedTabs ftabs{};
+  bool fused = false;          // tables built and sizes fit shared memory
+  int col_c = 4;               // columns per CTA in the column passes
   cufftHandle fft = 0;
   bool fft_ok = false;
   size_t fft_work = 0;
@@ -136,7 +142,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx,
-                   &pl->recs, &pl->mvis, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
+                   &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->cellflags, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
   if (pl->ev_ok)
@@ -144,6 +150,9 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   delete pl;
   return PFBG_OK;
 }
+
+template <typename T> static int fused_setup_t(pfbg_plan* pl);
+static int cufft_setup(pfbg_plan* pl);
 
 extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
   if (!d || !out) return fail(PFBG_ERR_ARG, "null argument");
@@ -220,21 +229,152 @@ extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
     if (e != cudaSuccess) { fail(PFBG_ERR_CUDA, "correction kernel failed: %s", cudaGetErrorString(e)); return bail(PFBG_ERR_CUDA); }
   }
 
-  // batched 2-D FFT over the plane stack
+  // plane transforms: fused in-shared-memory FFT when the sizes fit, cuFFT otherwise
   {
-    cufftResult r = cufftCreate(&pl->fft);
-    if (r != CUFFT_SUCCESS) { fail(PFBG_ERR_CUFFT, "cufftCreate failed (%d)", (int)r); return bail(PFBG_ERR_CUFFT); }
-    pl->fft_ok = true;
-    long long n[2] = {g.nu, g.nv};
-    size_t ws = 0;
-    r = cufftMakePlanMany64(pl->fft, 2, n, nullptr, 1, 0, nullptr, 1, 0,
-                            pl->precision == PFBG_F32 ? CUFFT_C2C : CUFFT_Z2Z, g.nplanes, &ws);
-    if (r != CUFFT_SUCCESS) { fail(PFBG_ERR_CUFFT, "cufftMakePlanMany64(%d x %d, batch %d) failed (%d)", g.nu, g.nv, g.nplanes, (int)r); return bail(PFBG_ERR_CUFFT); }
-    pl->fft_work = ws;
-    pl->total_bytes += ws;
+    int rc2 = pl->precision == PFBG_F32 ? fused_setup_t<float>(pl) : fused_setup_t<double>(pl);
+    if (rc2) return bail(rc2);
+    if (!pl->fused && (rc2 = cufft_setup(pl))) return bail(rc2);
   }
   *out = pl;
   return PFBG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// fused FFT tables
+// ---------------------------------------------------------------------------
+static bool factorize(int n, FftDesc& d) {
+  d.n = n;
+  d.nstage = 0;
+  int m = n;
+  const int odd[3] = {7, 5, 3};
+  for (int r : odd)
+    while (m % r == 0) {
+      if (d.nstage >= FFT_MAX_STAGES) return false;
+      d.radix[d.nstage++] = r;
+      m /= r;
+    }
+  int a = 0;
+  while (m % 2 == 0) { m /= 2; ++a; }
+  if (m != 1) return false;
+  while (a >= 4) {
+    if (d.nstage >= FFT_MAX_STAGES) return false;
+    d.radix[d.nstage++] = 16;
+    a -= 4;
+  }
+  if (a > 0) {
+    if (d.nstage >= FFT_MAX_STAGES) return false;
+    d.radix[d.nstage++] = 1 << a;
+  }
+  return true;
+}
+
+static void digit_tables(const FftDesc& d, std::vector<int>& rev, std::vector<int>& pos) {
+  rev.assign(d.n, 0);
+  pos.assign(d.n, 0);
+  for (int k = 0; k < d.n; ++k) {
+    int kk = k, M = d.n, p = 0;
+    for (int s = 0; s < d.nstage; ++s) {
+      M /= d.radix[s];
+      p += (kk % d.radix[s]) * M;
+      kk /= d.radix[s];
+    }
+    pos[k] = p;
+    rev[p] = k;
+  }
+}
+
+template <typename T>
+static int upload_twiddles(pfbg_plan* pl, DevBuf& buf, int n) {
+  std::vector<cx2<T>> tw(n);
+  for (int t = 0; t < n; ++t) {
+    double ang = -2.0 * M_PI * (double)t / (double)n;
+    tw[t].x = (T)cos(ang);
+    tw[t].y = (T)sin(ang);
+  }
+  CKRC(dev_alloc(pl, buf, (size_t)n * sizeof(cx2<T>)));
+  CK(cudaMemcpy(buf.p, tw.data(), (size_t)n * sizeof(cx2<T>), cudaMemcpyHostToDevice));
+  return PFBG_OK;
+}
+
+static const size_t kMaxSmem = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+template <typename T>
+static int fused_setup_t(pfbg_plan* pl) {
+  using C = typename cplx_of<T>::type;
+  const GParams& g = pl->gp;
+  pl->fused = false;
+  const char* env = getenv("PFBG_FFT");
+  if (env && strcmp(env, "cufft") == 0) return PFBG_OK;
+  pl->col_c = (int)(32 / sizeof(C));
+  if ((size_t)g.nv * sizeof(C) > kMaxSmem || g.nv > RINV_THREADS * RINV_MAXPER) return PFBG_OK;
+  if ((size_t)g.nu * pl->col_c * sizeof(C) > kMaxSmem) return PFBG_OK;
+  FftDesc du, dv;
+  if (!factorize(g.nu, du) || !factorize(g.nv, dv)) return PFBG_OK;
+  std::vector<int> rev, pos;
+  CKRC(upload_twiddles<T>(pl, pl->tw_u, g.nu));
+  CKRC(upload_twiddles<T>(pl, pl->tw_v, g.nv));
+  digit_tables(du, rev, pos);
+  CKRC(dev_alloc(pl, pl->rev_u, (size_t)g.nu * 4));
+  CK(cudaMemcpy(pl->rev_u.p, rev.data(), (size_t)g.nu * 4, cudaMemcpyHostToDevice));
+  digit_tables(dv, rev, pos);
+  CKRC(dev_alloc(pl, pl->rev_v, (size_t)g.nv * 4));
+  CKRC(dev_alloc(pl, pl->pos_v, (size_t)g.nv * 4));
+  CK(cudaMemcpy(pl->rev_v.p, rev.data(), (size_t)g.nv * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->pos_v.p, pos.data(), (size_t)g.nv * 4, cudaMemcpyHostToDevice));
+  FusedTabs& ft = pl->ftabs;
+  ft.du = du; ft.dv = dv;
+  ft.tw_u = pl->tw_u.p; ft.tw_v = pl->tw_v.p;
+  ft.rev_u = (const int*)pl->rev_u.p; ft.rev_v = (const int*)pl->rev_v.p; ft.pos_v = (const int*)pl->pos_v.p;
+  ft.a_lo = 0; ft.a_len = g.nu; ft.b_lo = 0; ft.b_len = g.nv;
+  // opt in to large dynamic shared memory
+  CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  if (sizeof(T) == 4) {
+    CK(cudaFuncSetAttribute(k_cols_fwd<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CK(cudaFuncSetAttribute(k_cols_inv<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  } else {
+    CK(cudaFuncSetAttribute(k_cols_fwd<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CK(cudaFuncSetAttribute(k_cols_inv<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  }
+  pl->fused = true;
+  return PFBG_OK;
+}
+
+static int cufft_setup(pfbg_plan* pl) {
+  if (pl->fft_ok) return PFBG_OK;
+  const GParams& g = pl->gp;
+  CKFFT(cufftCreate(&pl->fft));
+  pl->fft_ok = true;
+  long long n[2] = {g.nu, g.nv};
+  size_t ws = 0;
+  cufftResult r = cufftMakePlanMany64(pl->fft, 2, n, nullptr, 1, 0, nullptr, 1, 0,
+                                      pl->precision == PFBG_F32 ? CUFFT_C2C : CUFFT_Z2Z, g.nplanes, &ws);
+  if (r != CUFFT_SUCCESS)
+    return fail(PFBG_ERR_CUFFT, "cufftMakePlanMany64(%d x %d, batch %d) failed (%d)", g.nu, g.nv, g.nplanes, (int)r);
+  pl->fft_work = ws;
+  pl->total_bytes += ws;
+  return PFBG_OK;
+}
+
+// circular window covering every flagged 32-cell group: complement of the longest run of clear groups
+static void window_from_flags(const std::vector<int>& f, int size, int& lo, int& len) {
+  const int ng = (int)f.size();
+  int best_len = 0, best_start = 0, any = 0;
+  for (int v : f) any |= v;
+  if (!any) { lo = 0; len = 32 <= size ? 32 : size; return; }
+  // scan twice around the circle for the longest clear run
+  int run = 0;
+  for (int i = 0; i < 2 * ng; ++i) {
+    if (!f[i % ng]) {
+      ++run;
+      if (run > best_len && run <= ng) { best_len = run; best_start = i - run + 1; }
+    } else run = 0;
+  }
+  if (best_len >= ng) { lo = 0; len = size; return; }
+  int first = (best_start + best_len) % ng;  // first flagged group after the gap
+  lo = first * 32;
+  len = (ng - best_len) * 32;
+  if (len > size) len = size;
 }
 
 extern "C" int pfbg_plan_get_info(const pfbg_plan* pl, pfbg_plan_info* info) {
@@ -408,6 +548,29 @@ extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fsc
       pl->use_runs = true;
     }
   }
+  // active cell windows for the pruned transforms
+  if (pl->fused) {
+    FusedTabs& ft = pl->ftabs;
+    ft.a_lo = 0; ft.a_len = g.nu; ft.b_lo = 0; ft.b_len = g.nv;
+    if (pl->use_runs) {
+      const int ngu = g.nu / 32, ngv = g.nv / 32;
+      CKRC(dev_alloc(pl, pl->cellflags, (size_t)(ngu + ngv) * 4));
+      CK(cudaMemsetAsync(pl->cellflags.p, 0, (size_t)(ngu + ngv) * 4, s));
+      unsigned grd = (unsigned)((nact + 255) / 256);
+      int* uf = (int*)pl->cellflags.p;
+      if (pl->precision == PFBG_F32)
+        k_mark_cells<VisRec<float>><<<grd, 256, 0, s>>>((const VisRec<float>*)pl->recs.p, (int64_t)nact, g.W, g.nu, g.nv, uf, uf + ngu);
+      else
+        k_mark_cells<VisRec<double>><<<grd, 256, 0, s>>>((const VisRec<double>*)pl->recs.p, (int64_t)nact, g.W, g.nu, g.nv, uf, uf + ngu);
+      LAUNCHED();
+      std::vector<int> fl(ngu + ngv);
+      CK(cudaMemcpyAsync(fl.data(), pl->cellflags.p, fl.size() * 4, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      std::vector<int> fu(fl.begin(), fl.begin() + ngu), fv(fl.begin() + ngu, fl.end());
+      window_from_flags(fu, g.nu, ft.a_lo, ft.a_len);
+      window_from_flags(fv, g.nv, ft.b_lo, ft.b_len);
+    }
+  }
   pl->bound = true;
   return PFBG_OK;
 }
@@ -520,7 +683,73 @@ static int run_grid2img(pfbg_plan* pl, cudaStream_t s, const void* beam, const v
   return PFBG_OK;
 }
 
+template <typename T>
+static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam) {
+  using C = typename cplx_of<T>::type;
+  constexpr int CC = (int)(32 / sizeof(C));
+  const GParams& g = pl->gp;
+  const FusedTabs& ft = pl->ftabs;
+  k_rows_fwd<T><<<dim3(g.nx, g.nplanes), ROWS_THREADS, (size_t)g.nv * sizeof(C), s>>>(
+      g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, (C*)pl->grid.p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  k_cols_fwd<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, (size_t)g.nu * CC * sizeof(C), s>>>(g, ft, (C*)pl->grid.p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+
+template <typename T>
+static int run_fused_inv(pfbg_plan* pl, cudaStream_t s, const void* beam, const void* xin, double inv_wsum, double eta,
+                         void* out) {
+  using C = typename cplx_of<T>::type;
+  constexpr int CC = (int)(32 / sizeof(C));
+  const GParams& g = pl->gp;
+  const FusedTabs& ft = pl->ftabs;
+  k_cols_inv<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, (size_t)g.nu * CC * sizeof(C), s>>>(g, ft, (C*)pl->grid.p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  k_rows_inv<T><<<g.nx, RINV_THREADS, (size_t)g.nv * sizeof(C), s>>>(g, ft, (const C*)pl->grid.p, (const T*)pl->corr.p,
+                                                                     (const T*)beam, (const T*)xin, inv_wsum, eta, (T*)out);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+
+template <typename T>
+static int run_zero_window(pfbg_plan* pl, cudaStream_t s) {
+  using C = typename cplx_of<T>::type;
+  const GParams& g = pl->gp;
+  const FusedTabs& ft = pl->ftabs;
+  int bx = (ft.b_len + 1023) / 1024;
+  k_zero_window<C><<<dim3(bx, ft.a_len, g.nplanes), 256, 0, s>>>((C*)pl->grid.p, g.nu, g.nv, ft.a_lo, ft.a_len, ft.b_lo, ft.b_len);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+
 #define DISPATCH(fn, ...) (pl->precision == PFBG_F32 ? fn<float>(__VA_ARGS__) : fn<double>(__VA_ARGS__))
+
+// image -> screened, transformed plane stack (degrid direction)
+static int image_to_planes(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam) {
+  if (pl->fused) return DISPATCH(run_fused_fwd, pl, s, x, beam);
+  CKRC(cufft_setup(pl));
+  CKRC(DISPATCH(run_img2grid, pl, s, x, beam));
+  return fft_exec(pl, s, CUFFT_FORWARD);
+}
+// plane stack -> image with the fused epilogue (grid direction)
+static int planes_to_image(pfbg_plan* pl, cudaStream_t s, const void* beam, const void* xin, double inv_wsum,
+                           double eta, void* out) {
+  if (pl->fused) return DISPATCH(run_fused_inv, pl, s, beam, xin, inv_wsum, eta, out);
+  CKRC(cufft_setup(pl));
+  CKRC(fft_exec(pl, s, CUFFT_INVERSE));
+  return DISPATCH(run_grid2img, pl, s, beam, xin, inv_wsum, eta, out);
+}
+static int zero_planes(pfbg_plan* pl, cudaStream_t s) {
+  if (pl->fused) return DISPATCH(run_zero_window, pl, s);
+  CK(cudaMemsetAsync(pl->grid.p, 0, pl->grid.bytes, s));
+  return PFBG_OK;
+}
 
 extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t vis_cs, const void* wgt,
                          void* dirty, uint32_t flags, void* stream) {
@@ -544,14 +773,12 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
   }
   if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
   mark(pl, s);
-  CK(cudaMemsetAsync(pl->grid.p, 0, pl->grid.bytes, s));
+  CKRC(zero_planes(pl, s));
   CKRC(DISPATCH(run_spread, pl, s, dvis, vis_rs, vis_cs, dwgt, 0, 1));
-  mark(pl, s);
-  CKRC(fft_exec(pl, s, CUFFT_INVERSE));
   mark(pl, s);
   void* dout = dirty;
   if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
-  CKRC(DISPATCH(run_grid2img, pl, s, nullptr, nullptr, 1.0, 0.0, dout));
+  CKRC(planes_to_image(pl, s, nullptr, nullptr, 1.0, 0.0, dout));
   mark(pl, s);
   if (!dev) {
     CK(cudaMemcpyAsync(dirty, dout, img_bytes, cudaMemcpyDeviceToHost, s));
@@ -583,9 +810,7 @@ extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const vo
     if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
   }
   mark(pl, s);
-  CKRC(DISPATCH(run_img2grid, pl, s, dimg, nullptr));
-  mark(pl, s);
-  CKRC(fft_exec(pl, s, CUFFT_FORWARD));
+  CKRC(image_to_planes(pl, s, dimg, nullptr));
   mark(pl, s);
   void* dvis = vis;
   if (!dev && pl->nvis > 0) { CKRC(dev_alloc(pl, pl->vis_stage, vis_bytes)); dvis = pl->vis_stage.p; }
@@ -620,20 +845,18 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   const void* dwgt = pl->has_wgt ? pl->wgt.p : nullptr;
   mark(pl, s);
   // R (beam * x): pad + screen, FFT, gather (phase factors cancel against the adjoint)
-  CKRC(DISPATCH(run_img2grid, pl, s, dx, dbeam));
-  CKRC(fft_exec(pl, s, CUFFT_FORWARD));
+  CKRC(image_to_planes(pl, s, dx, dbeam));
   mark(pl, s);
   CKRC(DISPATCH(run_gather, pl, s, nullptr, nullptr, pl->mvis.p, 0));
   mark(pl, s);
   // R^H W: spread (weights applied on load), FFT, screen + crop + epilogue
-  CK(cudaMemsetAsync(pl->grid.p, 0, pl->grid.bytes, s));
+  CKRC(zero_planes(pl, s));
   mark(pl, s);
   CKRC(DISPATCH(run_spread, pl, s, pl->mvis.p, 0, 0, dwgt, 1, 0));
   mark(pl, s);
-  CKRC(fft_exec(pl, s, CUFFT_INVERSE));
   void* dout = out;
   if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
-  CKRC(DISPATCH(run_grid2img, pl, s, dbeam, eta != 0.0 ? dx : nullptr, wsum > 0.0 ? 1.0 / wsum : 1.0, eta, dout));
+  CKRC(planes_to_image(pl, s, dbeam, eta != 0.0 ? dx : nullptr, wsum > 0.0 ? 1.0 / wsum : 1.0, eta, dout));
   mark(pl, s);
   if (!dev) {
     CK(cudaMemcpyAsync(out, dout, img_bytes, cudaMemcpyDeviceToHost, s));
@@ -791,4 +1014,45 @@ extern "C" int pfbg_counts_to_weights(int32_t precision, int32_t device, void* c
   }
   CK(cudaStreamSynchronize(s));
   return PFBG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// unit-test hook for the shared-memory FFT engine (fft.cuh)
+// ---------------------------------------------------------------------------
+template <typename T>
+static int debug_fft_t(int n, int batch, const void* in, void* out, int mode, int inverse) {
+  FftDesc d;
+  if (!factorize(n, d)) return fail(PFBG_ERR_ARG, "n=%d is not 2^a 3^b 5^c 7^d", n);
+  size_t bytes = (size_t)n * sizeof(cx2<T>);
+  if (bytes > kMaxSmem) return fail(PFBG_ERR_ARG, "n=%d does not fit shared memory", n);
+  std::vector<cx2<T>> tw(n);
+  for (int t = 0; t < n; ++t) {
+    double ang = -2.0 * M_PI * (double)t / (double)n;
+    tw[t].x = (T)cos(ang);
+    tw[t].y = (T)sin(ang);
+  }
+  std::vector<int> rev, pos;
+  digit_tables(d, rev, pos);
+  TmpBufs t;
+  void *dtw, *drev, *dpos, *din, *dout;
+  CKRC(t.get(&dtw, tw.data(), bytes, false, true, 0));
+  CKRC(t.get(&drev, rev.data(), (size_t)n * 4, false, true, 0));
+  CKRC(t.get(&dpos, pos.data(), (size_t)n * 4, false, true, 0));
+  CKRC(t.get(&din, in, bytes * batch, false, true, 0));
+  CKRC(t.get(&dout, out, bytes * batch, false, false, 0));
+  CK(cudaFuncSetAttribute(k_fft_debug<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  k_fft_debug<T><<<batch, 256, bytes>>>(d, (const cx2<T>*)dtw, (const int*)drev, (const int*)dpos, (const cx2<T>*)din,
+                                        (cx2<T>*)dout, mode, inverse);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, bytes * batch, cudaMemcpyDeviceToHost));
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_debug_fft1d(int32_t precision, int32_t device, int32_t n, int32_t batch, const void* in,
+                                void* out, int32_t mode, int32_t inverse) {
+  if (!in || !out || n < 2 || batch < 1) return fail(PFBG_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(device));
+  return precision == PFBG_F32 ? debug_fft_t<float>(n, batch, in, out, mode, inverse)
+                               : debug_fft_t<double>(n, batch, in, out, mode, inverse);
 }
