@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libpfbgrid.so")
+LIB_PATH = os.environ.get("PFBG_LIB") or os.path.join(HERE, "libpfbgrid.so")  # PFBG_LIB: A/B builds
 CSRC = os.path.join(HERE, "csrc")
 
 PFBG_F32, PFBG_F64 = 0, 1

@@ -23,6 +23,22 @@ struct FftDesc {
 };
 
 template <typename T> struct cx2 { T x, y; };
+
+// Shared-memory index padding: one spare element after every 128 bytes, so that the power-of-two
+// strides of the late stages (and the digit-reversed scatter) spread over all 32 banks.
+template <typename T> __device__ __host__ __forceinline__ int fft_pad(int e) {
+  // +1 element per 128 B: spreads the small power-of-two strides of the late stages.  (A deeper
+  // skew that also spreads the digit-reversed scatter was measured 20 % SLOWER on B200: these
+  // kernels are issue-bound and the extra index arithmetic costs more than the conflicts.)
+#ifdef FFT_PAD_V2
+  return e + (e >> (sizeof(T) == 4 ? 4 : 3)) + (e >> 7) + (e >> 11);
+#else
+  return e + (e >> (sizeof(T) == 4 ? 4 : 3));
+#endif
+}
+template <typename T> __device__ __host__ __forceinline__ size_t fft_smem_bytes(int nelem) {
+  return (size_t)(fft_pad<T>(nelem - 1) + 1) * sizeof(cx2<T>);
+}
 template <typename T> __device__ __forceinline__ cx2<T> cmul(cx2<T> a, cx2<T> b) {
   return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }
@@ -147,33 +163,64 @@ template <typename T> struct SmallDft<T, 7> {
 //   DIF: butterfly, then output m *= W_L^{k m};   DIT: input m *= W_L^{k m}, then butterfly
 // tw[t] = e^{-2 pi i t/N} (global memory, L1/L2 resident), tstride = N / L.
 // ---------------------------------------------------------------------------
+// w^m from the binary powers w1, w2, w4, w8 of ONE table load (product depth <= 3, few registers)
+template <typename T, int M_>
+__device__ __forceinline__ cx2<T> twiddle_pow(const cx2<T>& w1, const cx2<T>& w2, const cx2<T>& w4, const cx2<T>& w8) {
+  cx2<T> r = {(T)1, (T)0};
+  bool have = false;
+  if (M_ & 8) { r = w8; have = true; }
+  if (M_ & 4) { r = have ? cmul(r, w4) : w4; have = true; }
+  if (M_ & 2) { r = have ? cmul(r, w2) : w2; have = true; }
+  if (M_ & 1) { r = have ? cmul(r, w1) : w1; have = true; }
+  return r;
+}
+template <typename T, int R, int M_>
+struct TwApply {
+  __device__ static __forceinline__ void run(cx2<T>* x, const cx2<T>& w1, const cx2<T>& w2, const cx2<T>& w4,
+                                             const cx2<T>& w8) {
+    x[M_] = cmul(x[M_], twiddle_pow<T, M_>(w1, w2, w4, w8));
+    TwApply<T, R, M_ + 1>::run(x, w1, w2, w4, w8);
+  }
+};
+template <typename T, int R>
+struct TwApply<T, R, R> {
+  __device__ static __forceinline__ void run(cx2<T>*, const cx2<T>&, const cx2<T>&, const cx2<T>&, const cx2<T>&) {}
+};
+template <typename T, int R>
+__device__ __forceinline__ void apply_twiddles(cx2<T>* x, cx2<T> w1) {
+  cx2<T> w2 = w1, w4 = w1, w8 = w1;
+  if (R > 2) w2 = cmul(w1, w1);
+  if (R > 4) w4 = cmul(w2, w2);
+  if (R > 8) w8 = cmul(w4, w4);
+  TwApply<T, R, 1>::run(x, w1, w2, w4, w8);
+}
+
 template <typename T, int R, int C, bool DIT>
 __device__ __forceinline__ void fft_stage(cx2<T>* __restrict__ s, const cx2<T>* __restrict__ tw, int N, int L,
                                           int tid, int nthr) {
   const int M = L / R;
   const int tstride = N / L;
   const int nbf = (N / R) * C;
+  const bool pow2 = (M & (M - 1)) == 0;
+  const int lgM = 31 - __clz(M);
   for (int w = tid; w < nbf; w += nthr) {
     const int c = (C == 1) ? 0 : (w % C);
     const int bk = (C == 1) ? w : (w / C);
+#ifdef FFT_NO_POW2
     const int g = bk / M;
+#else
+    const int g = pow2 ? (bk >> lgM) : (bk / M);
+#endif
     const int k = bk - g * M;
-    cx2<T>* base = s + ((size_t)(g * L + k)) * C + c;
+    const int e0 = (g * L + k) * C + c;
     cx2<T> x[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) x[m] = base[(size_t)m * M * C];
-    const int t1 = k * tstride;
-    if (DIT && k != 0) {
-#pragma unroll
-      for (int m = 1; m < R; ++m) x[m] = cmul(x[m], tw[m * t1]);
-    }
+    for (int m = 0; m < R; ++m) x[m] = s[fft_pad<T>(e0 + m * M * C)];
+    if (DIT && k != 0) apply_twiddles<T, R>(x, tw[k * tstride]);
     SmallDft<T, R>::run(x);
-    if (!DIT && k != 0) {
+    if (!DIT && k != 0) apply_twiddles<T, R>(x, tw[k * tstride]);
 #pragma unroll
-      for (int m = 1; m < R; ++m) x[m] = cmul(x[m], tw[m * t1]);
-    }
-#pragma unroll
-    for (int m = 0; m < R; ++m) base[(size_t)m * M * C] = x[m];
+    for (int m = 0; m < R; ++m) s[fft_pad<T>(e0 + m * M * C)] = x[m];
   }
 }
 
@@ -226,13 +273,13 @@ __global__ void k_fft_debug(FftDesc d, const cx2<T>* __restrict__ tw, const int*
   for (int n = tid; n < N; n += nthr) {
     cx2<T> v = src[n];
     v.y *= sg;
-    s[mode ? posmap[n] : n] = v;
+    s[fft_pad<T>(mode ? posmap[n] : n)] = v;
   }
   __syncthreads();
   if (mode) fft_dit<T, 1>(s, tw, d, tid, nthr);
   else fft_dif<T, 1>(s, tw, d, tid, nthr);
   for (int p = tid; p < N; p += nthr) {
-    cx2<T> v = s[p];
+    cx2<T> v = s[fft_pad<T>(p)];
     v.y *= sg;
     dst[mode ? p : rev[p]] = v;
   }

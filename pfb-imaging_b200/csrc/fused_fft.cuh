@@ -32,25 +32,24 @@ __device__ __forceinline__ bool in_window(int n, int lo, int len, int size) {
   return rel < len;
 }
 
-#define ROWS_THREADS 256
-#define RINV_THREADS 512
-#define RINV_MAXPER 16     /* ceil(nv / RINV_THREADS) <= 16  (nv <= 8192) */
+#define ROWS_MAX_THREADS 256
+
 
 // --------------------------------------------------------------------------- degrid direction
 template <typename T>
-__global__ void __launch_bounds__(ROWS_THREADS)
+__global__ void __launch_bounds__(ROWS_MAX_THREADS)
 k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict__ beam, const T* __restrict__ corr,
            typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
-  const int tid = threadIdx.x, i = blockIdx.x, q = blockIdx.y;
+  const int tid = threadIdx.x, nthr = blockDim.x, i = blockIdx.x, q = blockIdx.y;
   const int nv = p.nv, hy = p.ny / 2;
   const int ip = i - p.nx / 2;
   const int a = ip < 0 ? ip + p.nu : ip;
-  for (int n = tid; n < nv; n += ROWS_THREADS) s[n] = {(T)0, (T)0};
+  for (int n = tid; n < nv; n += nthr) s[fft_pad<T>(n)] = {(T)0, (T)0};
   __syncthreads();
   const double wq = p.w0 + q * p.dw;
-  for (int j = tid; j < p.ny; j += ROWS_THREADS) {
+  for (int j = tid; j < p.ny; j += nthr) {
     const int64_t pix = (int64_t)i * p.ny + j;
     T val = x[pix] * corr[pix];
     if (beam) val *= beam[pix];
@@ -61,13 +60,13 @@ k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict
       v = {val * c, val * sn};
     }
     const int jp = j - hy;
-    s[ft.pos_v[jp < 0 ? jp + nv : jp]] = v;
+    s[fft_pad<T>(ft.pos_v[jp < 0 ? jp + nv : jp])] = v;
   }
   __syncthreads();
-  fft_dit<T, 1>(s, (const cx2<T>*)ft.tw_v, ft.dv, tid, ROWS_THREADS);
+  fft_dit<T, 1>(s, (const cx2<T>*)ft.tw_v, ft.dv, tid, nthr);
   cx2<T>* dst = reinterpret_cast<cx2<T>*>(grid) + ((int64_t)q * p.nu + a) * nv;
-  for (int n = tid; n < nv; n += ROWS_THREADS)
-    if (in_window(n, ft.b_lo, ft.b_len, nv)) dst[n] = s[n];
+  for (int n = tid; n < nv; n += nthr)
+    if (in_window(n, ft.b_lo, ft.b_len, nv)) dst[n] = s[fft_pad<T>(n)];
 }
 
 // column block of C columns starting at b0; rows of the image band only are read
@@ -83,14 +82,14 @@ k_cols_fwd(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
   for (int w = tid; w < nu * C; w += nthr) {
     const int a = w / C, c = w - a * C;
     const bool band = a < hx || a >= nu - hx;
-    s[w] = band ? g[(int64_t)a * p.nv + c] : cx2<T>{(T)0, (T)0};
+    s[fft_pad<T>(w)] = band ? g[(int64_t)a * p.nv + c] : cx2<T>{(T)0, (T)0};
   }
   __syncthreads();
   fft_dif<T, C>(s, (const cx2<T>*)ft.tw_u, ft.du, tid, nthr);
   for (int w = tid; w < nu * C; w += nthr) {
     const int pos = w / C, c = w - pos * C;
     const int k = ft.rev_u[pos];
-    if (in_window(k, ft.a_lo, ft.a_len, nu)) g[(int64_t)k * p.nv + c] = s[w];
+    if (in_window(k, ft.a_lo, ft.a_len, nu)) g[(int64_t)k * p.nv + c] = s[fft_pad<T>(w)];
   }
 }
 
@@ -111,7 +110,7 @@ k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
       v = g[(int64_t)a * p.nv + c];
       v.y = -v.y;  // inverse = conj o forward o conj
     }
-    s[w] = v;
+    s[fft_pad<T>(w)] = v;
   }
   __syncthreads();
   fft_dif<T, C>(s, (const cx2<T>*)ft.tw_u, ft.du, tid, nthr);
@@ -119,76 +118,62 @@ k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
     const int pos = w / C, c = w - pos * C;
     const int k = ft.rev_u[pos];
     if (k < hx || k >= nu - hx) {
-      cx2<T> v = s[w];
+      cx2<T> v = s[fft_pad<T>(w)];
       v.y = -v.y;
       g[(int64_t)k * p.nv + c] = v;
     }
   }
 }
 
+// One CTA per (plane, image row): read the row (active window only), inverse FFT along v, apply the
+// conjugate w-screen to the ny kept outputs and add their real parts to the fp64 accumulation image
+// (RED.F64; CTAs of one row are adjacent in the grid, so the 32 KB image row stays in L2).
 template <typename T>
-__global__ void __launch_bounds__(RINV_THREADS)
-k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict__ grid,
-           const T* __restrict__ corr, const T* __restrict__ beam, const T* __restrict__ xin, double inv_wsum,
-           double eta, T* __restrict__ out) {
+__global__ void __launch_bounds__(ROWS_MAX_THREADS)
+k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict__ grid, double* __restrict__ accimg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
-  const int tid = threadIdx.x, i = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x, q = blockIdx.x, i = blockIdx.y;
   const int nv = p.nv, hy = p.ny / 2;
   const int ip = i - p.nx / 2;
   const int a = ip < 0 ? ip + p.nu : ip;
-  // positions owned by this thread: pos = tid + m*RINV_THREADS; k = rev_v[pos]; kept if k is an image column
-  int jcol[RINV_MAXPER];
-  double nuv[RINV_MAXPER], acc[RINV_MAXPER];
-#pragma unroll
-  for (int m = 0; m < RINV_MAXPER; ++m) {
-    const int pos = tid + m * RINV_THREADS;
-    jcol[m] = -1;
-    acc[m] = 0.0;
-    nuv[m] = 0.0;
-    if (pos < nv) {
-      const int k = ft.rev_v[pos];
-      if (k < hy) jcol[m] = k + hy;
-      else if (k >= nv - hy) jcol[m] = k - nv + hy;
-      if (jcol[m] >= 0 && p.do_wgridding) nuv[m] = pixel_nm1(p, i, jcol[m]) + p.nshift;
-    }
+  const cx2<T>* src = reinterpret_cast<const cx2<T>*>(grid) + ((int64_t)q * p.nu + a) * nv;
+  for (int n = tid; n < nv; n += nthr) {
+    cx2<T> v = {(T)0, (T)0};  // columns outside the window are known to be zero
+    if (in_window(n, ft.b_lo, ft.b_len, nv)) { v = src[n]; v.y = -v.y; }
+    s[fft_pad<T>(n)] = v;
   }
-  for (int q = 0; q < p.nplanes; ++q) {
-    const cx2<T>* src = reinterpret_cast<const cx2<T>*>(grid) + ((int64_t)q * p.nu + a) * nv;
-    for (int n = tid; n < nv; n += RINV_THREADS) {
-      cx2<T> v = {(T)0, (T)0};  // columns outside the window are known to be zero
-      if (in_window(n, ft.b_lo, ft.b_len, nv)) { v = src[n]; v.y = -v.y; }
-      s[n] = v;
+  __syncthreads();
+  fft_dif<T, 1>(s, (const cx2<T>*)ft.tw_v, ft.dv, tid, nthr);
+  const double wq = p.w0 + q * p.dw;
+  double* dst = accimg + (int64_t)i * p.ny;
+  for (int j = tid; j < p.ny; j += nthr) {
+    const int jp = j - hy;
+    const cx2<T> v = s[fft_pad<T>(ft.pos_v[jp < 0 ? jp + nv : jp])];  // conj(v) is the inverse transform
+    double r;
+    if (p.do_wgridding) {
+      T c, sn;
+      cis_turns(wq * (pixel_nm1(p, i, j) + p.nshift), c, sn);
+      r = (double)(v.x * c - v.y * sn);  // Re( conj(v) e^{-i theta} )
+    } else {
+      r = (double)v.x;
     }
-    __syncthreads();
-    fft_dif<T, 1>(s, (const cx2<T>*)ft.tw_v, ft.dv, tid, RINV_THREADS);
-    const double wq = p.w0 + q * p.dw;
-#pragma unroll
-    for (int m = 0; m < RINV_MAXPER; ++m) {
-      if (jcol[m] >= 0) {
-        const cx2<T> v = s[tid + m * RINV_THREADS];  // conj(v) is the inverse transform
-        if (p.do_wgridding) {
-          T c, sn;
-          cis_turns(wq * nuv[m], c, sn);
-          acc[m] += (double)(v.x * c - v.y * sn);  // Re( conj(v) * e^{-i theta} ) = v.x c - v.y s  (v.y is -Im)
-        } else {
-          acc[m] += (double)v.x;
-        }
-      }
-    }
-    __syncthreads();
+    atomicAdd(dst + j, r);
   }
-#pragma unroll
-  for (int m = 0; m < RINV_MAXPER; ++m) {
-    if (jcol[m] >= 0) {
-      const int64_t pix = (int64_t)i * p.ny + jcol[m];
-      double r = acc[m] * (double)corr[pix];
-      if (beam) r *= (double)beam[pix];
-      r *= inv_wsum;
-      if (xin) r += eta * (double)xin[pix];
-      out[pix] = (T)r;
-    }
-  }
+}
+
+// out = acc * corr [* beam] * inv_wsum [+ eta * xin]
+template <typename T>
+__global__ void k_finish_image(int64_t npix, const double* __restrict__ acc, const T* __restrict__ corr,
+                               const T* __restrict__ beam, const T* __restrict__ xin, double inv_wsum, double eta,
+                               T* __restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= npix) return;
+  double r = acc[k] * (double)corr[k];
+  if (beam) r *= (double)beam[k];
+  r *= inv_wsum;
+  if (xin) r += eta * (double)xin[k];
+  out[k] = (T)r;
 }
 
 // mark the 32-cell groups of rows / columns touched by the bound samples (host derives the windows)

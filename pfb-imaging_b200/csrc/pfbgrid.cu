@@ -90,7 +90,7 @@ struct pfbg_plan {
   DevBuf vis_stage, wgt_stage;
   DevBuf flag;
   // fused FFT path (fused_fft.cuh)
-  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, cellflags;
+  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, cellflags, accimg;
   FusedTabs ftabs{};
   bool fused = false;          // tables built and sizes fit shared memory
   int col_c = 4;               // columns per CTA in the column passes
@@ -142,7 +142,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx,
-                   &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->cellflags, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
+                   &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->cellflags, &pl->accimg, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
   if (pl->ev_ok)
@@ -306,8 +306,8 @@ static int fused_setup_t(pfbg_plan* pl) {
   const char* env = getenv("PFBG_FFT");
   if (env && strcmp(env, "cufft") == 0) return PFBG_OK;
   pl->col_c = (int)(32 / sizeof(C));
-  if ((size_t)g.nv * sizeof(C) > kMaxSmem || g.nv > RINV_THREADS * RINV_MAXPER) return PFBG_OK;
-  if ((size_t)g.nu * pl->col_c * sizeof(C) > kMaxSmem) return PFBG_OK;
+  if (fft_smem_bytes<T>(g.nv) > kMaxSmem) return PFBG_OK;
+  if (fft_smem_bytes<T>(g.nu * pl->col_c) > kMaxSmem) return PFBG_OK;
   FftDesc du, dv;
   if (!factorize(g.nu, du) || !factorize(g.nv, dv)) return PFBG_OK;
   std::vector<int> rev, pos;
@@ -329,6 +329,9 @@ static int fused_setup_t(pfbg_plan* pl) {
   // opt in to large dynamic shared memory
   CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CKRC(dev_alloc(pl, pl->accimg, (size_t)g.nx * g.ny * sizeof(double)));
   if (sizeof(T) == 4) {
     CK(cudaFuncSetAttribute(k_cols_fwd<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     CK(cudaFuncSetAttribute(k_cols_inv<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -683,17 +686,30 @@ static int run_grid2img(pfbg_plan* pl, cudaStream_t s, const void* beam, const v
   return PFBG_OK;
 }
 
+// threads per CTA for a row transform: the multiple of 32 (<= cap, >= cap/2) that balances the
+// radix-16 stage best (n/16 butterflies)
+static int row_threads(int n, int cap) {
+  int nb = n / 16, best = cap;
+  double best_eff = 0.0;
+  for (int t = cap; t >= cap / 2; t -= 32) {
+    int per = (nb + t - 1) / t;
+    double eff = (double)nb / ((double)per * t);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = t; }
+  }
+  return best;
+}
+
 template <typename T>
 static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam) {
   using C = typename cplx_of<T>::type;
   constexpr int CC = (int)(32 / sizeof(C));
   const GParams& g = pl->gp;
   const FusedTabs& ft = pl->ftabs;
-  k_rows_fwd<T><<<dim3(g.nx, g.nplanes), ROWS_THREADS, (size_t)g.nv * sizeof(C), s>>>(
+  k_rows_fwd<T><<<dim3(g.nx, g.nplanes), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
       g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
-  k_cols_fwd<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, (size_t)g.nu * CC * sizeof(C), s>>>(g, ft, (C*)pl->grid.p);
+  k_cols_fwd<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, fft_smem_bytes<T>(g.nu * CC), s>>>(g, ft, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
   return PFBG_OK;
@@ -706,11 +722,17 @@ static int run_fused_inv(pfbg_plan* pl, cudaStream_t s, const void* beam, const 
   constexpr int CC = (int)(32 / sizeof(C));
   const GParams& g = pl->gp;
   const FusedTabs& ft = pl->ftabs;
-  k_cols_inv<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, (size_t)g.nu * CC * sizeof(C), s>>>(g, ft, (C*)pl->grid.p);
+  k_cols_inv<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, fft_smem_bytes<T>(g.nu * CC), s>>>(g, ft, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
-  k_rows_inv<T><<<g.nx, RINV_THREADS, (size_t)g.nv * sizeof(C), s>>>(g, ft, (const C*)pl->grid.p, (const T*)pl->corr.p,
-                                                                     (const T*)beam, (const T*)xin, inv_wsum, eta, (T*)out);
+  const int64_t npix = (int64_t)g.nx * g.ny;
+  CK(cudaMemsetAsync(pl->accimg.p, 0, (size_t)npix * sizeof(double), s));
+  k_rows_inv<T><<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+      g, ft, (const C*)pl->grid.p, (double*)pl->accimg.p);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  k_finish_image<T><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(npix, (const double*)pl->accimg.p, (const T*)pl->corr.p,
+                                                                (const T*)beam, (const T*)xin, inv_wsum, eta, (T*)out);
   LAUNCHED();
   CK(cudaGetLastError());
   return PFBG_OK;
@@ -1024,7 +1046,7 @@ static int debug_fft_t(int n, int batch, const void* in, void* out, int mode, in
   FftDesc d;
   if (!factorize(n, d)) return fail(PFBG_ERR_ARG, "n=%d is not 2^a 3^b 5^c 7^d", n);
   size_t bytes = (size_t)n * sizeof(cx2<T>);
-  if (bytes > kMaxSmem) return fail(PFBG_ERR_ARG, "n=%d does not fit shared memory", n);
+  if (fft_smem_bytes<T>(n) > kMaxSmem) return fail(PFBG_ERR_ARG, "n=%d does not fit shared memory", n);
   std::vector<cx2<T>> tw(n);
   for (int t = 0; t < n; ++t) {
     double ang = -2.0 * M_PI * (double)t / (double)n;
@@ -1041,7 +1063,7 @@ static int debug_fft_t(int n, int batch, const void* in, void* out, int mode, in
   CKRC(t.get(&din, in, bytes * batch, false, true, 0));
   CKRC(t.get(&dout, out, bytes * batch, false, false, 0));
   CK(cudaFuncSetAttribute(k_fft_debug<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-  k_fft_debug<T><<<batch, 256, bytes>>>(d, (const cx2<T>*)dtw, (const int*)drev, (const int*)dpos, (const cx2<T>*)din,
+  k_fft_debug<T><<<batch, 256, fft_smem_bytes<T>(n)>>>(d, (const cx2<T>*)dtw, (const int*)drev, (const int*)dpos, (const cx2<T>*)din,
                                         (cx2<T>*)dout, mode, inverse);
   LAUNCHED();
   CK(cudaGetLastError());

@@ -153,9 +153,9 @@ def _correction(n, nbig, W, beta):
 #   * run kernels (W <= 8): issue-bound, ~constant per sample whatever W is;
 #   * direct kernels (W > 8): one atomic / gather per footprint cell;
 #   * plane work (zero / FFT / screen): per complex cell of the oversampled stack.
-COST_VIS_RUNS = {"single": 2.6e-10, "double": 6.0e-10}
+COST_VIS_RUNS = {"single": 1.35e-10, "double": 4.0e-10}
 COST_CELL_UPDATE = {"single": 7.0e-13, "double": 5.0e-12}
-COST_GRID_CELL = {"single": 1.5e-11, "double": 2.9e-11}
+COST_GRID_CELL = {"single": 8.0e-12, "double": 2.0e-11}
 RUNS_MAX_W = 8
 
 

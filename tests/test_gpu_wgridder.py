@@ -150,7 +150,7 @@ def test_api_semantics(gpu):
     a = W.vis2dirty(uvw=uvw_ro, freq=p["freq"], vis=ones, wgt=p["wgt"], npix_x=32, npix_y=32,
                     pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=1e-6)
     b = W.vis2dirty(vis=np.ones(p["vis"].shape, dtype=np.complex128), wgt=p["wgt"], npix_x=32, npix_y=32, **com)
-    assert np.array_equal(a, b)
+    np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-11 * np.abs(b).max())  # atomics: order varies
     # empty input: zero rows
     z = W.vis2dirty(uvw=np.zeros((0, 3)), freq=p["freq"], vis=np.zeros((0, 2), dtype=np.complex128), npix_x=32,
                     npix_y=32, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=1e-6)
