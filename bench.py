@@ -27,6 +27,9 @@ WORKLOADS = {
     # configs[0]: the reference's own CPU-runnable case
     "c1": dict(nx=2048, ntime=62, nchan=8, precision="double", epsilon=1e-5,
                name="C1: 2048^2, 1.0M vis, fp64, eps=1e-5, single band"),
+    # pfb's production default: double precision, epsilon=1e-7 (core/grid.py:50), C2 geometry
+    "c2d": dict(nx=4096, ntime=775, nchan=16, precision="double", epsilon=1e-7,
+                name="C2 geometry in fp64 at pfb's default eps=1e-7: 4096^2, 25.0M vis/band"),
 }
 
 

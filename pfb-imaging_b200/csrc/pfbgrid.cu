@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pfbgrid.h"
@@ -89,6 +90,14 @@ struct pfbg_plan {
   DevBuf img_in, img_out, img_beam;  // staging for host-pointer calls
   DevBuf vis_stage, wgt_stage;
   DevBuf flag;
+  // pinned host staging for host-pointer calls (pageable user arrays are copied through these by
+  // several threads, chunk by chunk, overlapped with the DMA)
+  void* h_in = nullptr;
+  size_t h_in_bytes = 0;
+  void* h_out = nullptr;
+  size_t h_out_bytes = 0;
+  cudaEvent_t stage_ev[16]{};
+  bool stage_ev_ok = false;
   // fused FFT path (fused_fft.cuh)
   DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, cellflags, accimg;
   FusedTabs ftabs{};
@@ -147,6 +156,10 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   for (DevBuf* b : all) dev_free(pl, *b);
   if (pl->ev_ok)
     for (auto& e : pl->ev) cudaEventDestroy(e);
+  if (pl->stage_ev_ok)
+    for (auto& e : pl->stage_ev) cudaEventDestroy(e);
+  if (pl->h_in) cudaFreeHost(pl->h_in);
+  if (pl->h_out) cudaFreeHost(pl->h_out);
   delete pl;
   return PFBG_OK;
 }
@@ -421,12 +434,93 @@ extern "C" int pfbg_get_timings(pfbg_plan* pl, float* ms, int32_t n, int32_t* n_
 // ---------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------
+static int host_threads() {
+  static int n = [] {
+    const char* e = getenv("PFBG_COPY_THREADS");
+    int v = e ? atoi(e) : 0;
+    if (v <= 0) {
+      v = (int)std::thread::hardware_concurrency() / 2;
+      if (v > 8) v = 8;
+    }
+    return v < 1 ? 1 : v;
+  }();
+  return n;
+}
+
+static void par_memcpy(void* dst, const void* src, size_t n) {
+  const int nt = host_threads();
+  if (nt == 1 || n < (size_t)(1 << 20)) { memcpy(dst, src, n); return; }
+  std::vector<std::thread> th;
+  size_t per = ((n / nt) + 63) & ~(size_t)63;
+  for (int t = 0; t < nt; ++t) {
+    size_t off = (size_t)t * per;
+    if (off >= n) break;
+    size_t len = off + per > n ? n - off : per;
+    th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+  }
+  for (auto& t : th) t.join();
+}
+
+static int pinned(void*& p, size_t& have, size_t need) {
+  if (have >= need) return PFBG_OK;
+  if (p) {
+    cudaDeviceSynchronize();  // earlier async copies may still read the old buffer
+    cudaFreeHost(p);
+  }
+  p = nullptr; have = 0;
+  cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+  if (e != cudaSuccess) { p = nullptr; return fail(PFBG_ERR_NOMEM, "cudaHostAlloc of %zu bytes failed: %s", need, cudaGetErrorString(e)); }
+  have = need;
+  return PFBG_OK;
+}
+
+static const size_t kChunk = (size_t)8 << 20;
+
+// host -> device through the pinned buffer: CPU copy of chunk c+1 overlaps the DMA of chunk c
+static int h2d_staged(pfbg_plan* pl, void* dst, const void* src, size_t bytes, cudaStream_t s, size_t pin_off = 0) {
+  if (bytes == 0) return PFBG_OK;
+  CKRC(pinned(pl->h_in, pl->h_in_bytes, pin_off + bytes));
+  // the pinned buffer may still feed an earlier async copy on this stream
+  if (pin_off == 0) CK(cudaStreamSynchronize(s));
+  for (size_t off = 0; off < bytes; off += kChunk) {
+    size_t len = off + kChunk > bytes ? bytes - off : kChunk;
+    par_memcpy((char*)pl->h_in + pin_off + off, (const char*)src + off, len);
+    CK(cudaMemcpyAsync((char*)dst + off, (char*)pl->h_in + pin_off + off, len, cudaMemcpyHostToDevice, s));
+  }
+  return PFBG_OK;
+}
+
+// device -> host: DMA every chunk into the pinned buffer, copy chunk c out while c+1 is in flight
+static int d2h_staged(pfbg_plan* pl, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return PFBG_OK;
+  CKRC(pinned(pl->h_out, pl->h_out_bytes, bytes));
+  if (!pl->stage_ev_ok) {
+    for (auto& e : pl->stage_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pl->stage_ev_ok = true;
+  }
+  const size_t nchunk = (bytes + kChunk - 1) / kChunk;
+  for (size_t base = 0; base < nchunk; base += 16) {
+    const size_t nb = nchunk - base < 16 ? nchunk - base : 16;
+    for (size_t c = 0; c < nb; ++c) {
+      size_t off = (base + c) * kChunk, len = off + kChunk > bytes ? bytes - off : kChunk;
+      CK(cudaMemcpyAsync((char*)pl->h_out + off, (const char*)src + off, len, cudaMemcpyDeviceToHost, s));
+      CK(cudaEventRecord(pl->stage_ev[c], s));
+    }
+    for (size_t c = 0; c < nb; ++c) {
+      size_t off = (base + c) * kChunk, len = off + kChunk > bytes ? bytes - off : kChunk;
+      CK(cudaEventSynchronize(pl->stage_ev[c]));
+      par_memcpy((char*)dst + off, (char*)pl->h_out + off, len);
+    }
+  }
+  return PFBG_OK;
+}
+
 static int fetch(pfbg_plan* pl, DevBuf& stage, const void* src, size_t bytes, bool dev, cudaStream_t s,
-                 const void** out) {
+                 const void** out, size_t pin_off = 0) {
   // device pointers are used in place; host pointers are staged on the stream
   if (dev) { *out = src; return PFBG_OK; }
   CKRC(dev_alloc(pl, stage, bytes));
-  CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, s));
+  CKRC(h2d_staged(pl, stage.p, src, bytes, s, pin_off));
   *out = stage.p;
   return PFBG_OK;
 }
@@ -447,6 +541,15 @@ static int run_blocks(const pfbg_plan* pl, int64_t nact, int warps_per_cta, int 
   int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
   int64_t want = (nslice + warps_per_cta - 1) / warps_per_cta;
   int64_t cap = (int64_t)sm * ctas_per_sm;  // a multiple of the SM count: one full wave of resident CTAs
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+static int wide_blocks(const pfbg_plan* pl, int64_t nact, int team) {
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
+  int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  int64_t want = (nslice * team + WIDE_WARPS - 1) / WIDE_WARPS;
+  int64_t cap = (int64_t)sm * 2;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -535,7 +638,7 @@ extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fsc
   {
     const char* fd = getenv("PFBG_FORCE_DIRECT");
     bool force_direct = fd && fd[0] == '1';
-    if (!force_direct && g.W <= 8 && g.nu <= 32768 && g.nv <= 32768 && nact > 0) {
+    if (!force_direct && g.W <= 16 && g.nu <= 32768 && g.nv <= 32768 && nact > 0) {
       size_t rsz = pl->precision == PFBG_F32 ? sizeof(VisRec<float>) : sizeof(VisRec<double>);
       CKRC(dev_alloc(pl, pl->recs, (size_t)nact * rsz));
       unsigned grd = (unsigned)((nact + 255) / 256);
@@ -627,7 +730,18 @@ template <typename T>
 static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs, int64_t cs, const void* wgt,
                       int vis_sorted, int apply_phase) {
   using C = typename cplx_of<T>::type;
-  if (pl->nactive > 0 && pl->use_runs) {
+  if (pl->nactive > 0 && pl->use_runs && pl->gp.W > 8) {
+    if (pl->gp.W <= 12)
+      k_grid_runs_wide<T, 3, 6, 4><<<wide_blocks(pl, pl->nactive, 4), WIDE_WARPS * 32, 0, s>>>(
+          pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
+          vis_sorted, apply_phase);
+    else
+      k_grid_runs_wide<T, 2, 8, 8><<<wide_blocks(pl, pl->nactive, 8), WIDE_WARPS * 32, 0, s>>>(
+          pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
+          vis_sorted, apply_phase);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  } else if (pl->nactive > 0 && pl->use_runs) {
     k_grid_runs<T><<<run_blocks(pl, pl->nactive, RUN_WARPS, 3), RUN_WARPS * 32, 0, s>>>(
         pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
         vis_sorted, apply_phase);
@@ -644,9 +758,24 @@ static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs
 }
 
 template <typename T>
-static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_out, void* out_sorted, int apply_phase) {
+static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_out, void* out_sorted, int apply_phase,
+                      int vis_zeroed = 0) {
   using C = typename cplx_of<T>::type;
-  if (pl->nactive > 0 && pl->use_runs) {
+  if (pl->nactive > 0 && pl->use_runs && pl->gp.W > 8) {
+    // the R warps of a team add their row-partials atomically: start from zero
+    if (out_sorted) CK(cudaMemsetAsync(out_sorted, 0, (size_t)pl->nactive * sizeof(C), s));
+    else if (!pl->has_mask || (vis_zeroed == 0)) CK(cudaMemsetAsync(vis_out, 0, (size_t)pl->nvis * sizeof(C), s));
+    if (pl->gp.W <= 12)
+      k_degrid_runs_wide<T, 3, 6, 4><<<wide_blocks(pl, pl->nactive, 4), WIDE_WARPS * 32, 0, s>>>(
+          pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
+          (C*)out_sorted, apply_phase);
+    else
+      k_degrid_runs_wide<T, 2, 8, 8><<<wide_blocks(pl, pl->nactive, 8), WIDE_WARPS * 32, 0, s>>>(
+          pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
+          (C*)out_sorted, apply_phase);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  } else if (pl->nactive > 0 && pl->use_runs) {
     k_degrid_runs<T><<<run_blocks(pl, pl->nactive, DEG_WARPS, 4), DEG_WARPS * 32, 0, s>>>(
         pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
         (C*)out_sorted, apply_phase);
@@ -790,8 +919,9 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
   if (!dev && pl->nvis > 0) {
     bool bcast = (vis_rs == 0 && vis_cs == 0);
     if (!bcast && !(vis_cs == 1 && vis_rs == pl->gp.nchan)) return fail(PFBG_ERR_ARG, "host vis must be C-contiguous or a broadcast scalar");
-    CKRC(fetch(pl, pl->vis_stage, vis, bcast ? 2 * rb : (size_t)pl->nvis * 2 * rb, false, s, &dvis));
-    if (wgt) CKRC(fetch(pl, pl->wgt_stage, wgt, (size_t)pl->nvis * rb, false, s, &dwgt));
+    const size_t vb = bcast ? 2 * rb : (size_t)pl->nvis * 2 * rb;
+    CKRC(fetch(pl, pl->vis_stage, vis, vb, false, s, &dvis));
+    if (wgt) CKRC(fetch(pl, pl->wgt_stage, wgt, (size_t)pl->nvis * rb, false, s, &dwgt, (vb + 4095) & ~(size_t)4095));
   }
   if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
   mark(pl, s);
@@ -802,10 +932,7 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
   if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
   CKRC(planes_to_image(pl, s, nullptr, nullptr, 1.0, 0.0, dout));
   mark(pl, s);
-  if (!dev) {
-    CK(cudaMemcpyAsync(dirty, dout, img_bytes, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-  }
+  if (!dev) CKRC(d2h_staged(pl, dirty, dout, img_bytes, s));
   mark(pl, s);
   return PFBG_OK;
 }
@@ -828,7 +955,7 @@ extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const vo
   const void* dwgt = nullptr;
   if (flags & PFBG_APPLY_WGT) {
     dwgt = wgt;
-    if (wgt && !dev) CKRC(fetch(pl, pl->wgt_stage, wgt, (size_t)pl->nvis * rb, false, s, &dwgt));
+    if (wgt && !dev) CKRC(fetch(pl, pl->wgt_stage, wgt, (size_t)pl->nvis * rb, false, s, &dwgt, (img_bytes + 4095) & ~(size_t)4095));
     if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
   }
   mark(pl, s);
@@ -837,14 +964,12 @@ extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const vo
   void* dvis = vis;
   if (!dev && pl->nvis > 0) { CKRC(dev_alloc(pl, pl->vis_stage, vis_bytes)); dvis = pl->vis_stage.p; }
   if (pl->nvis > 0) {
-    if (pl->has_mask && !(flags & PFBG_NO_MASK_ZERO)) CK(cudaMemsetAsync(dvis, 0, vis_bytes, s));
-    CKRC(DISPATCH(run_gather, pl, s, dwgt, dvis, nullptr, 1));
+    const int zeroed = (pl->has_mask && !(flags & PFBG_NO_MASK_ZERO)) ? 1 : 0;
+    if (zeroed) CK(cudaMemsetAsync(dvis, 0, vis_bytes, s));
+    CKRC(DISPATCH(run_gather, pl, s, dwgt, dvis, nullptr, 1, zeroed));
   }
   mark(pl, s);
-  if (!dev && pl->nvis > 0) {
-    CK(cudaMemcpyAsync(vis, dvis, vis_bytes, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-  }
+  if (!dev && pl->nvis > 0) CKRC(d2h_staged(pl, vis, dvis, vis_bytes, s));
   mark(pl, s);
   return PFBG_OK;
 }
@@ -862,9 +987,26 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   mark(pl, s);
   const void *dx = x, *dbeam = beam;
   CKRC(fetch(pl, pl->img_in, x, img_bytes, dev, s, &dx));
-  if (beam) CKRC(fetch(pl, pl->img_beam, beam, img_bytes, dev, s, &dbeam));
+  if (beam) CKRC(fetch(pl, pl->img_beam, beam, img_bytes, dev, s, &dbeam, (img_bytes + 4095) & ~(size_t)4095));
   CKRC(dev_alloc(pl, pl->mvis, (size_t)(pl->nactive ? pl->nactive : 1) * 2 * rb));
   const void* dwgt = pl->has_wgt ? pl->wgt.p : nullptr;
+  if (!dev) {
+    // `if not x.any(): return zeros` (operators/hessian.py:47-48), checked on the device copy
+    const int64_t npix = (int64_t)pl->gp.nx * pl->gp.ny;
+    CK(cudaMemsetAsync(pl->flag.p, 0, 4, s));
+    if (pl->precision == PFBG_F32)
+      k_any_nonzero<float><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>((const float*)dx, npix, (int*)pl->flag.p);
+    else
+      k_any_nonzero<double><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>((const double*)dx, npix, (int*)pl->flag.p);
+    LAUNCHED();
+    int nz = 1;
+    CK(cudaMemcpyAsync(&nz, pl->flag.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (!nz) {
+      memset(out, 0, img_bytes);
+      return PFBG_OK;
+    }
+  }
   mark(pl, s);
   // R (beam * x): pad + screen, FFT, gather (phase factors cancel against the adjoint)
   CKRC(image_to_planes(pl, s, dx, dbeam));
@@ -880,10 +1022,7 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
   CKRC(planes_to_image(pl, s, dbeam, eta != 0.0 ? dx : nullptr, wsum > 0.0 ? 1.0 / wsum : 1.0, eta, dout));
   mark(pl, s);
-  if (!dev) {
-    CK(cudaMemcpyAsync(out, dout, img_bytes, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-  }
+  if (!dev) CKRC(d2h_staged(pl, out, dout, img_bytes, s));
   mark(pl, s);
   return PFBG_OK;
 }

@@ -307,3 +307,251 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
     }
   }
 }
+
+// ===========================================================================
+// Wide-support run kernels (9 <= W <= 16; the fp64 production settings, epsilon <= 1e-7).
+//
+// Same scheme as above, but the footprint no longer fits one warp's registers, so a TEAM of R
+// warps shares every run: warp r of the team owns the u-rows  i = r*RPW .. r*RPW+RPW-1  and walks
+// the same slice of samples independently (no inter-warp synchronisation: each warp stages the
+// records and evaluates the taps it needs itself).  Lane = (j, q2) with j = v-offset (0..15) and
+// q2 = plane slot (0..1); a lane holds RPW rows x NQ planes (q = q2 + 2*qq).
+//   9..12 : RPW = 3, NQ = 6, R = 4        13..16 : RPW = 2, NQ = 8, R = 8
+// ===========================================================================
+template <typename T, int RPW, int NQ>
+struct WideCfg {
+  static constexpr int NB = 16;              // samples staged per batch
+  static constexpr int NT = RPW + 32;        // taps per sample and warp: RPW u-taps, 16 v-taps, 16 w-taps
+};
+
+template <typename T, int RPW, int NQ>
+__device__ __forceinline__ void wide_taps(const GParams& p, const T (*x0s)[4], T (*taps)[RPW + 32], int nb, int lane,
+                                          int row0, T bscale, T xs) {
+  constexpr int NT = RPW + 32;
+  for (int idx = lane; idx < NT * nb; idx += 32) {
+    const int v = idx / NT, t = idx - v * NT;
+    int axis, k;
+    if (t < RPW) { axis = 0; k = row0 + t; }
+    else if (t < RPW + 16) { axis = 1; k = t - RPW; }
+    else { axis = 2; k = t - RPW - 16; }
+    T val = es_fast((x0s[v][axis] + (T)k) * xs, bscale);
+    if (axis == 2 && !p.do_wgridding) val = (k == 0) ? (T)1 : (T)0;
+    taps[v][t] = val;
+  }
+}
+
+template <typename T, int RPW, int NQ>
+__device__ __forceinline__ void wide_flush(const GParams& p, typename cplx_of<T>::type* __restrict__ grid,
+                                           T (&accr)[RPW][NQ], T (&acci)[RPW][NQ], uint64_t origin, int j, int q2,
+                                           int row0) {
+  const int W = p.W, npl = p.do_wgridding ? W : 1;
+  int iv = (int)(origin & 0xffffu) + j;
+  int iu0 = (int)((origin >> 16) & 0xffffu);
+  int ip = (int)(origin >> 32);
+  if (iv >= p.nv) iv -= p.nv;
+  const int plane_sz = p.nu * p.nv;
+  const bool jok = j < W;
+#pragma unroll
+  for (int qq = 0; qq < NQ; ++qq) {
+    const int q = q2 + 2 * qq;
+    const bool ok = jok && q < npl;
+    typename cplx_of<T>::type* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
+#pragma unroll
+    for (int ii = 0; ii < RPW; ++ii) {
+      const int i = row0 + ii;
+      if (ok && i < W) {
+        int iu = iu0 + i;
+        if (iu >= p.nu) iu -= p.nu;
+        atomic_add_c(gq + iu * p.nv, accr[ii][qq], acci[ii][qq]);
+      }
+      accr[ii][qq] = 0;
+      acci[ii][qq] = 0;
+    }
+  }
+}
+
+#define WIDE_WARPS 8
+
+template <typename T, int RPW, int NQ, int R>
+__global__ void __launch_bounds__(WIDE_WARPS * 32)
+k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
+                 const typename cplx_of<T>::type* __restrict__ vis, int64_t vis_rs, int64_t vis_cs,
+                 const T* __restrict__ wgt, typename cplx_of<T>::type* __restrict__ grid, int vis_sorted,
+                 int apply_phase) {
+  using C = typename cplx_of<T>::type;
+  constexpr int NB = WideCfg<T, RPW, NQ>::NB, NT = WideCfg<T, RPW, NQ>::NT;
+  __shared__ T taps[WIDE_WARPS][NB][NT];
+  __shared__ __align__(16) T x0s[WIDE_WARPS][NB][4];
+  __shared__ C amp[WIDE_WARPS][NB];
+  __shared__ uint64_t orgs[WIDE_WARPS][NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 15, q2 = lane >> 4;
+  const int64_t gwarp = (int64_t)blockIdx.x * WIDE_WARPS + warp;
+  const int row0 = (int)(gwarp % R) * RPW;
+  const T bscale = es_scale((T)p.beta), xs = (T)(2.0 / p.W);
+  T accr[RPW][NQ], acci[RPW][NQ];
+#pragma unroll
+  for (int ii = 0; ii < RPW; ++ii)
+#pragma unroll
+    for (int qq = 0; qq < NQ; ++qq) { accr[ii][qq] = 0; acci[ii][qq] = 0; }
+  uint64_t cur = ~0ull;
+  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  const int64_t nteams = ((int64_t)gridDim.x * WIDE_WARPS) / R;
+  for (int64_t sl = gwarp / R; sl < nslice; sl += nteams) {
+    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+      const int nb = (int)min((int64_t)NB, kend - k0);
+      if (lane < nb) {
+        const int64_t k = k0 + lane;
+        VisRec<T> r = recs[k];
+        C a;
+        if (vis_sorted) a = vis[k];
+        else {
+          int64_t row = r.idx / p.nchan;
+          int chan = (int)(r.idx - row * p.nchan);
+          a = vis[row * vis_rs + chan * vis_cs];
+        }
+        T w = wgt ? wgt[r.idx] : (T)1;
+        T pc = apply_phase ? r.pc : (T)1, ps = apply_phase ? r.ps : (T)0;
+        C s;
+        s.x = (a.x * pc - a.y * ps) * w;
+        s.y = (a.x * ps + a.y * pc) * w;
+        amp[warp][lane] = s;
+        x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
+        orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
+      }
+      __syncwarp();
+      wide_taps<T, RPW, NQ>(p, x0s[warp], taps[warp], nb, lane, row0, bscale, xs);
+      __syncwarp();
+      for (int v = 0; v < nb; ++v) {
+        const uint64_t org = orgs[warp][v];
+        if (org != cur) {
+          if (cur != ~0ull) wide_flush<T, RPW, NQ>(p, grid, accr, acci, cur, j, q2, row0);
+          cur = org;
+        }
+        const T* tp = taps[warp][v];
+        const T tv = tp[RPW + j];
+        const C a = amp[warp][v];
+        const T ar = a.x * tv, ai = a.y * tv;
+        T ur[RPW], ui[RPW];
+#pragma unroll
+        for (int ii = 0; ii < RPW; ++ii) { ur[ii] = ar * tp[ii]; ui[ii] = ai * tp[ii]; }
+#pragma unroll
+        for (int qq = 0; qq < NQ; ++qq) {
+          const T wq = tp[RPW + 16 + q2 + 2 * qq];
+#pragma unroll
+          for (int ii = 0; ii < RPW; ++ii) {
+            accr[ii][qq] += ur[ii] * wq;
+            acci[ii][qq] += ui[ii] * wq;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (cur != ~0ull) wide_flush<T, RPW, NQ>(p, grid, accr, acci, cur, j, q2, row0);
+}
+
+// degridding: each warp of the team produces the partial sum over its rows; partials of the R
+// warps are combined with one atomicAdd per sample and warp into a zero-initialised output.
+template <typename T, int RPW, int NQ, int R>
+__global__ void __launch_bounds__(WIDE_WARPS * 32)
+k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
+                   const typename cplx_of<T>::type* __restrict__ grid, const T* __restrict__ wgt,
+                   typename cplx_of<T>::type* __restrict__ vis_out,
+                   typename cplx_of<T>::type* __restrict__ out_sorted, int apply_phase) {
+  using C = typename cplx_of<T>::type;
+  constexpr int NB = WideCfg<T, RPW, NQ>::NB, NT = WideCfg<T, RPW, NQ>::NT;
+  __shared__ T taps[WIDE_WARPS][NB][NT];
+  __shared__ __align__(16) T x0s[WIDE_WARPS][NB][4];
+  __shared__ uint64_t orgs[WIDE_WARPS][NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 15, q2 = lane >> 4;
+  const int64_t gwarp = (int64_t)blockIdx.x * WIDE_WARPS + warp;
+  const int row0 = (int)(gwarp % R) * RPW;
+  const int W = p.W, npl = p.do_wgridding ? W : 1;
+  const T bscale = es_scale((T)p.beta), xs = (T)(2.0 / p.W);
+  const int plane_sz = p.nu * p.nv;
+  T gr[RPW][NQ], gi[RPW][NQ];
+#pragma unroll
+  for (int ii = 0; ii < RPW; ++ii)
+#pragma unroll
+    for (int qq = 0; qq < NQ; ++qq) { gr[ii][qq] = 0; gi[ii][qq] = 0; }
+  uint64_t cur = ~0ull;
+  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  const int64_t nteams = ((int64_t)gridDim.x * WIDE_WARPS) / R;
+  for (int64_t sl = gwarp / R; sl < nslice; sl += nteams) {
+    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+      const int nb = (int)min((int64_t)NB, kend - k0);
+      VisRec<T> r;
+      if (lane < nb) {
+        r = recs[k0 + lane];
+        x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
+        orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
+      }
+      __syncwarp();
+      wide_taps<T, RPW, NQ>(p, x0s[warp], taps[warp], nb, lane, row0, bscale, xs);
+      __syncwarp();
+      T myr = 0, myi = 0;  // lane v keeps the team-partial of sample v
+      for (int v = 0; v < nb; ++v) {
+        const uint64_t org = orgs[warp][v];
+        if (org != cur) {
+          cur = org;
+          int iv = (int)(org & 0xffffu) + j;
+          int iu0 = (int)((org >> 16) & 0xffffu);
+          int ip = (int)(org >> 32);
+          if (iv >= p.nv) iv -= p.nv;
+          const bool jok = j < W;
+#pragma unroll
+          for (int qq = 0; qq < NQ; ++qq) {
+            const int q = q2 + 2 * qq;
+            const bool ok = jok && q < npl;
+            const C* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
+#pragma unroll
+            for (int ii = 0; ii < RPW; ++ii) {
+              const int i = row0 + ii;
+              C val; val.x = 0; val.y = 0;
+              if (ok && i < W) {
+                int iu = iu0 + i;
+                if (iu >= p.nu) iu -= p.nu;
+                val = gq[iu * p.nv];
+              }
+              gr[ii][qq] = val.x; gi[ii][qq] = val.y;
+            }
+          }
+        }
+        const T* tp = taps[warp][v];
+        T sr = 0, si = 0;
+#pragma unroll
+        for (int qq = 0; qq < NQ; ++qq) {
+          T pr = 0, pi = 0;
+#pragma unroll
+          for (int ii = 0; ii < RPW; ++ii) { pr += gr[ii][qq] * tp[ii]; pi += gi[ii][qq] * tp[ii]; }
+          const T wq = tp[RPW + 16 + q2 + 2 * qq];
+          sr += pr * wq; si += pi * wq;
+        }
+        const T tv = tp[RPW + j];
+        sr *= tv; si *= tv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sr += __shfl_xor_sync(0xffffffffu, sr, o);
+          si += __shfl_xor_sync(0xffffffffu, si, o);
+        }
+        if (lane == v) { myr = sr; myi = si; }
+      }
+      if (lane < nb) {
+        T re = myr, im = myi;
+        if (apply_phase) {
+          re = myr * r.pc + myi * r.ps;
+          im = myi * r.pc - myr * r.ps;
+        }
+        if (wgt) { T w = wgt[r.idx]; re *= w; im *= w; }
+        C* dst = out_sorted ? (out_sorted + k0 + lane) : (vis_out + r.idx);
+        atomicAdd(&dst->x, re);
+        atomicAdd(&dst->y, im);
+      }
+      __syncwarp();
+    }
+  }
+}

@@ -160,8 +160,10 @@ def hessian_slice(x, xout=None, uvw=None, weight=None, vis_mask=None, freq=None,
     (operators/hessian.py:15-100).  One fused device pass: the model visibilities
     never come back to the host."""
     x = np.asarray(x)
-    if not x.any():
+    if x.size == 0:
         return np.zeros_like(x)
+    # the all-zero short circuit of hessian.py:47-48 is taken on the device copy inside
+    # pfbg_hessian (a 64 MB numpy .any() costs as much as half a Hessian apply)
     nx, ny = x.shape
     prec = _precision_of_real(x.dtype)
     rdt = x.dtype
@@ -308,8 +310,6 @@ class BandHessian:
 
     def dot(self, x):
         x = np.ascontiguousarray(x, dtype=self.gp.rdt)
-        if not x.any():
-            return np.zeros_like(x)
         return self.gp.hessian(x, beam=self.beam, wsum=self.wsum, eta=self.eta)
 
     hdot = dot  # self-adjoint

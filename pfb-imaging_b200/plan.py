@@ -160,9 +160,10 @@ RUNS_MAX_W = 8
 
 
 def vis_cost(precision, W, ndim):
+    """Run kernels: one warp per run for W <= 8, a team of 4 (W <= 12) or 8 (W <= 16) warps beyond."""
     if W <= RUNS_MAX_W:
         return COST_VIS_RUNS[precision]
-    return (W ** ndim) * COST_CELL_UPDATE[precision]
+    return COST_VIS_RUNS[precision] * (5.0 if W <= 12 else 9.0)
 
 
 # Largest kernel support per precision.  In single precision the grid
