@@ -27,7 +27,8 @@ from .wgridder import GridderPlan, dirty2vis, plan_for, vis2dirty
 
 __all__ = [
     "wgridder_conventions", "vis2im", "im2vis", "hessian_slice", "residual_from_partitions",
-    "compute_residual_arrays", "image_data_products_arrays", "clear_plan_cache", "BandHessian",
+    "compute_residual_arrays", "image_data_products_arrays", "grid_partition", "eval_beam", "clear_plan_cache",
+    "BandHessian",
 ]
 
 
@@ -286,6 +287,86 @@ def image_data_products_arrays(uvw, freq, vis, wgt, mask, nx, ny, nx_psf, ny_psf
                 gp.grid(psf_vis, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c])
         out["psf"] = psf
         out["psfhat"] = np.fft.rfft2(np.fft.ifftshift(psf, axes=(1, 2)), axes=(1, 2))
+    return out
+
+
+def eval_beam(beam_image, l_in, m_in, l_out, m_out):
+    """Linear interpolation of the small-grid beam onto the image grid (utils/beam.py:75-89)."""
+    if l_out.ndim == 2:
+        ll, mm = l_out, m_out
+    elif l_out.ndim == 1:
+        ll, mm = np.meshgrid(l_out, m_out, indexing="ij")
+    else:
+        raise ValueError("Only 1 or 2D coordinates supported for beam evaluation")
+    if (beam_image == 1.0).all():
+        return np.ones_like(ll)
+    from scipy.interpolate import RegularGridInterpolator
+
+    beamo = RegularGridInterpolator((l_in, m_in), beam_image, bounds_error=False, method="linear", fill_value=1.0)
+    return beamo((ll, mm))
+
+
+def _vals(obj, name):
+    v = getattr(obj, name)
+    return v.values if hasattr(v, "values") else np.asarray(v)
+
+
+def grid_partition(part, counts, nx, ny, nx_psf, ny_psf, cell_rad, robustness=None, nx_pad=None, ny_pad=None,
+                   l0=0.0, m0=0.0, nthreads=1, epsilon=1e-7, do_wgridding=True, double_accum=True, fit_psf=None):
+    """Per-partition image-space products (operators/gridder.py:760-923): imaging weights from the
+    reduced counts grid, then DIRTY, PSF, PSFHAT, BEAM, WSUM and the imaging WEIGHT.
+
+    `part` is duck-typed: attributes ``UVW, VIS, WEIGHT, MASK, FREQ, BEAM, l_beam, m_beam`` exposing
+    ``.values`` (xarray) or plain arrays.  ``PSFPARSN`` needs the reference's jax/scikit-image
+    ``fitcleanbeam`` (out of scope); pass ``fit_psf`` to supply it, otherwise the key is omitted."""
+    from .weighting import counts_to_weights
+
+    flip_u, flip_v, flip_w, x0, y0 = wgridder_conventions(l0, m0)
+    signu = -1.0 if flip_u else 1.0
+    signv = -1.0 if flip_v else 1.0
+    signx = -1.0 if flip_u else 1.0
+    signy = -1.0 if flip_v else 1.0
+    n = np.sqrt(1 - x0**2 - y0**2)
+    uvw = _vals(part, "UVW")
+    vis = _vals(part, "VIS")
+    wgt = _vals(part, "WEIGHT").copy()
+    mask = _vals(part, "MASK")
+    freq = _vals(part, "FREQ")
+    ncorr = wgt.shape[0]
+    if robustness is not None:
+        wgt = counts_to_weights(counts.copy(), uvw, freq, wgt, mask, nx_pad, ny_pad, cell_rad, cell_rad, robustness,
+                                usign=1.0 if flip_u else -1.0, vsign=1.0 if flip_v else -1.0)
+    wsum = wgt[:, mask.astype(bool)].sum(axis=-1)
+
+    x = (-nx / 2 + np.arange(nx)) * cell_rad + x0
+    y = (-ny / 2 + np.arange(ny)) * cell_rad + y0
+    xx, yy = np.meshgrid(np.rad2deg(x), np.rad2deg(y), indexing="ij")
+    bsmall = _vals(part, "BEAM")
+    beam = np.zeros((ncorr, nx, ny), dtype=float)
+    for c in range(ncorr):
+        beam[c] = eval_beam(bsmall[c], _vals(part, "l_beam"), _vals(part, "m_beam"), xx, yy)
+
+    common = dict(pixsize_x=cell_rad, pixsize_y=cell_rad, center_x=x0, center_y=y0, epsilon=epsilon, flip_u=flip_u,
+                  flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=False, sigma_min=1.1,
+                  sigma_max=3.0, precision="double", mask=mask)
+    dirty = np.zeros((ncorr, nx, ny), dtype=float)
+    with plan_for(uvw, freq, npix_x=nx, npix_y=ny, **common) as gp:
+        for c in range(ncorr):
+            gp.grid(np.require(vis[c], dtype=np.complex128), wgt=np.require(wgt[c], dtype=np.float64), dirty=dirty[c])
+    if x0 or y0:
+        freqfactor = 2j * np.pi * freq[None, :] / 299792458.0  # sign as written at gridder.py:878
+        psf_vis = np.exp(freqfactor * (signu * uvw[:, 0:1] * x0 * signx + signv * uvw[:, 1:2] * y0 * signy
+                                       - uvw[:, 2:] * (n - 1)))
+    else:
+        psf_vis = np.broadcast_to(np.ones((1,), dtype=np.complex128), (uvw.shape[0], freq.size))
+    psf = np.zeros((ncorr, nx_psf, ny_psf), dtype=float)
+    with plan_for(uvw, freq, npix_x=nx_psf, npix_y=ny_psf, **common) as gp:
+        for c in range(ncorr):
+            gp.grid(psf_vis, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c])
+    psfhat = np.fft.rfft2(np.fft.ifftshift(psf, axes=(1, 2)), axes=(1, 2))  # r2c, forward, unnormalised (:912)
+    out = {"DIRTY": dirty, "PSF": psf, "PSFHAT": psfhat, "BEAM": beam, "WSUM": wsum, "WEIGHT": wgt}
+    if fit_psf is not None:
+        out["PSFPARSN"] = np.array(fit_psf(psf, level=0.5, pixsize=1.0))
     return out
 
 
