@@ -203,6 +203,9 @@ __device__ __forceinline__ void fft_stage(cx2<T>* __restrict__ s, const cx2<T>* 
   const int nbf = (N / R) * C;
   const bool pow2 = (M & (M - 1)) == 0;
   const int lgM = 31 - __clz(M);
+  constexpr int PERIOD = sizeof(T) == 4 ? 16 : 8;
+  const bool lin = ((M * C) % PERIOD) == 0;
+  const int pstride = M * C + (M * C) / PERIOD;
   for (int w = tid; w < nbf; w += nthr) {
     const int c = (C == 1) ? 0 : (w % C);
     const int bk = (C == 1) ? w : (w / C);
@@ -214,13 +217,26 @@ __device__ __forceinline__ void fft_stage(cx2<T>* __restrict__ s, const cx2<T>* 
     const int k = bk - g * M;
     const int e0 = (g * L + k) * C + c;
     cx2<T> x[R];
+    // padded address of e0 + m*M*C: when the stride is a multiple of the padding period the pad term
+    // is linear in m, so one padded base + a constant padded stride replaces R index computations
+    const int a0 = fft_pad<T>(e0);
+    if (lin) {
 #pragma unroll
-    for (int m = 0; m < R; ++m) x[m] = s[fft_pad<T>(e0 + m * M * C)];
+      for (int m = 0; m < R; ++m) x[m] = s[a0 + m * pstride];
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; ++m) x[m] = s[fft_pad<T>(e0 + m * M * C)];
+    }
     if (DIT && k != 0) apply_twiddles<T, R>(x, tw[k * tstride]);
     SmallDft<T, R>::run(x);
     if (!DIT && k != 0) apply_twiddles<T, R>(x, tw[k * tstride]);
+    if (lin) {
 #pragma unroll
-    for (int m = 0; m < R; ++m) s[fft_pad<T>(e0 + m * M * C)] = x[m];
+      for (int m = 0; m < R; ++m) s[a0 + m * pstride] = x[m];
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; ++m) s[fft_pad<T>(e0 + m * M * C)] = x[m];
+    }
   }
 }
 

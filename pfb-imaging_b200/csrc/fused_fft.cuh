@@ -22,6 +22,7 @@ struct FusedTabs {
   const int* rev_u;          // pos -> k
   const int* rev_v;
   const int* pos_v;          // k -> pos (DIT input scatter)
+  const double* nutab;       // (nx,ny) fp64: n - 1 + nshift per pixel (w-screen phase = w_p * nutab, up to 1e3 turns)
   // cells any bound sample can touch: rows [a_lo, a_lo+a_len) and columns [b_lo, b_lo+b_len), circular
   int a_lo, a_len, b_lo, b_len;
 };
@@ -37,7 +38,7 @@ __device__ __forceinline__ bool in_window(int n, int lo, int len, int size) {
 
 // --------------------------------------------------------------------------- degrid direction
 template <typename T>
-__global__ void __launch_bounds__(ROWS_MAX_THREADS)
+__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 1))
 k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict__ beam, const T* __restrict__ corr,
            typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -56,7 +57,7 @@ k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict
     cx2<T> v = {val, (T)0};
     if (p.do_wgridding && val != (T)0) {
       T c, sn;
-      cis_turns(wq * (pixel_nm1(p, i, j) + p.nshift), c, sn);
+      cis_turns(wq * ft.nutab[pix], c, sn);
       v = {val * c, val * sn};
     }
     const int jp = j - hy;
@@ -129,7 +130,7 @@ k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
 // conjugate w-screen to the ny kept outputs and add their real parts to the fp64 accumulation image
 // (RED.F64; CTAs of one row are adjacent in the grid, so the 32 KB image row stays in L2).
 template <typename T>
-__global__ void __launch_bounds__(ROWS_MAX_THREADS)
+__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 1))
 k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict__ grid, double* __restrict__ accimg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
@@ -153,7 +154,7 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
     double r;
     if (p.do_wgridding) {
       T c, sn;
-      cis_turns(wq * (pixel_nm1(p, i, j) + p.nshift), c, sn);
+      cis_turns(wq * ft.nutab[(int64_t)i * p.ny + j], c, sn);
       r = (double)(v.x * c - v.y * sn);  // Re( conj(v) e^{-i theta} )
     } else {
       r = (double)v.x;
@@ -174,6 +175,13 @@ __global__ void k_finish_image(int64_t npix, const double* __restrict__ acc, con
   r *= inv_wsum;
   if (xin) r += eta * (double)xin[k];
   out[k] = (T)r;
+}
+
+__global__ void k_nu_table(GParams p, double* __restrict__ nutab) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= p.ny) return;
+  nutab[(int64_t)i * p.ny + j] = pixel_nm1(p, i, j) + p.nshift;
 }
 
 // mark the 32-cell groups of rows / columns touched by the bound samples (host derives the windows)

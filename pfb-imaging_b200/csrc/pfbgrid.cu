@@ -99,7 +99,7 @@ struct pfbg_plan {
   cudaEvent_t stage_ev[16]{};
   bool stage_ev_ok = false;
   // fused FFT path (fused_fft.cuh)
-  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, cellflags, accimg;
+  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, cellflags, accimg, nutab;
   FusedTabs ftabs{};
   bool fused = false;          // tables built and sizes fit shared memory
   int col_c = 4;               // columns per CTA in the column passes
@@ -151,7 +151,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx,
-                   &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->cellflags, &pl->accimg, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
+                   &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->cellflags, &pl->accimg, &pl->nutab, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
   if (pl->ev_ok)
@@ -345,6 +345,11 @@ static int fused_setup_t(pfbg_plan* pl) {
   CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CKRC(dev_alloc(pl, pl->accimg, (size_t)g.nx * g.ny * sizeof(double)));
+  CKRC(dev_alloc(pl, pl->nutab, (size_t)g.nx * g.ny * sizeof(double)));
+  k_nu_table<<<dim3((g.ny + 127) / 128, g.nx), 128>>>(g, (double*)pl->nutab.p);
+  LAUNCHED();
+  CK(cudaDeviceSynchronize());
+  ft.nutab = (const double*)pl->nutab.p;
   if (sizeof(T) == 4) {
     CK(cudaFuncSetAttribute(k_cols_fwd<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     CK(cudaFuncSetAttribute(k_cols_inv<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
