@@ -22,8 +22,8 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[1]/[2] geometry, one band per GPU
-    "c2": dict(nx=4096, ntime=775, nchan=16, precision="single", epsilon=1e-5,
-               name="pfb grid/sara C2: 4096^2, 8-band MeerKAT-like, 25.0M vis/band, fp32, eps=1e-5, one band per GPU"),
+    "c2": dict(nx=4096, ntime=775, nchan=16, precision="single", epsilon=1e-5, nbands=8,
+               name="pfb grid/sara C2: 8 bands x 4096^2, 25.0M vis/band (200M vis), MeerKAT-like, fp32, eps=1e-5"),
     # configs[0]: the reference's own CPU-runnable case
     "c1": dict(nx=2048, ntime=62, nchan=8, precision="double", epsilon=1e-5,
                name="C1: 2048^2, 1.0M vis, fp64, eps=1e-5, single band"),
@@ -145,11 +145,23 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def assign_bands(costs, world):
+    """Longest-processing-time-first partition of the bands over the ranks."""
+    order = sorted(range(len(costs)), key=lambda b: -costs[b])
+    load, owner = [0.0] * world, {}
+    for b in order:
+        r = min(range(world), key=lambda k: load[k])
+        owner[b] = r
+        load[r] += costs[b]
+    return owner
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
 
-    from pfb_imaging_b200 import _lib, operators as ops, wgridder as W
+    from pfb_imaging_b200 import _lib, operators as ops, synth, wgridder as W
+    from pfb_imaging_b200.plan import make_plan, w_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -159,26 +171,45 @@ def run_ours(args, cfg):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-
-    band = rank % 8
-    d, cell, x = make_inputs(cfg, band)
-    uvw, freq = d["uvw"], d["freq"]
-    nvis = uvw.shape[0] * freq.size
     p = 4 if cfg["precision"] == "single" else 8
-    gp = W.plan_for(uvw, freq, npix_x=cfg["nx"], npix_y=cfg["nx"], pixsize_x=cell, pixsize_y=cell,
-                    epsilon=cfg["epsilon"], flip_v=True, divide_by_n=False, precision=cfg["precision"],
-                    mask=d["mask"], sigma_min=1.1, sigma_max=3.0, device=local)
-    gp.bind_weights(d["wgt"])
-    info = gp.info()
-    wsum = float(d["wgt"].sum(dtype=np.float64))
+    nbands = cfg.get("nbands", 1)
+    # Default = weak scaling: every GPU owns one complete job (all `nbands` bands of the config, i.e.
+    # BASELINE.json configs[1] at N=1), so N GPUs image N jobs with no data-path collective.
+    # --strong partitions ONE job's bands over the ranks instead (limited by band heterogeneity:
+    # sum(ms_per_band)/max(ms_per_band), both reported in the JSON line).
+    strong = bool(args.strong) and nbands >= world and nbands > 1
+    if strong:
+        # the job is the whole multi-band config: partition its bands over the ranks (strong scaling)
+        probe, cell0, _ = make_inputs(cfg, 0)
+        costs = []
+        for b in range(nbands):
+            fr = synth.band_freqs(b, 8, cfg["nchan"])
+            wmin, wmax = w_range(probe["uvw"], fr)
+            pl = make_plan(nx=cfg["nx"], ny=cfg["nx"], pixsize_x=cell0, pixsize_y=cell0, epsilon=cfg["epsilon"],
+                           flip_v=True, divide_by_n=False, sigma_min=1.1, sigma_max=3.0, precision=cfg["precision"],
+                           wmin=wmin, wmax=wmax, nvis=probe["uvw"].shape[0] * cfg["nchan"])
+            costs.append(pl.est_cost)
+        owner = assign_bands(costs, world)
+        my_bands = [b for b in range(nbands) if owner[b] == rank]
+    else:
+        my_bands = list(range(nbands)) if nbands > 1 else [rank % 8]
 
-    tdt = torch.float32 if p == 4 else torch.float64
-    x_d = torch.from_numpy(x).to(dev)
-    out_d = torch.empty_like(x_d)
+    bands = []
+    for b in my_bands:
+        d, cell, x = make_inputs(cfg, b)
+        gp = W.plan_for(d["uvw"], d["freq"], npix_x=cfg["nx"], npix_y=cfg["nx"], pixsize_x=cell, pixsize_y=cell,
+                        epsilon=cfg["epsilon"], flip_v=True, divide_by_n=False, precision=cfg["precision"],
+                        mask=d["mask"], sigma_min=1.1, sigma_max=3.0, device=local)
+        gp.bind_weights(d["wgt"])
+        x_d = torch.from_numpy(x).to(dev)
+        bands.append(dict(b=b, d=d, cell=cell, x=x, gp=gp, x_d=x_d, out_d=torch.empty_like(x_d),
+                          wsum=float(d["wgt"].sum(dtype=np.float64)), nvis=d["uvw"].shape[0] * d["freq"].size))
+    nvis_local = sum(bd["nvis"] for bd in bands)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_dev():
-        gp.hessian_dev(x_d.data_ptr(), None, wsum, 0.0, out_d.data_ptr(), stream)
+        for bd in bands:
+            bd["gp"].hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(), stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -208,40 +239,62 @@ def run_ours(args, cfg):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    nvis_all = torch.tensor([float(nvis)], dtype=torch.float64, device=dev)
+    nvis_all = torch.tensor([float(nvis_local)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(nvis_all, op=dist.ReduceOp.SUM)
     value = float(nvis_all.item()) / (ms_step * 1e-3) / 1e6
 
-    # ---- per-phase timing of the dominant kernel (events inside the library, same stream) ---
-    gp.set_profiling(True)
-    phase = []
-    for _ in range(3):
-        step_dev()
-        torch.cuda.synchronize()
-        phase.append(gp.timings())
-    gp.set_profiling(False)
-    ph = np.median(np.array(phase), axis=0).tolist()
+    # ---- per-phase timing (events inside the library, same stream), summed over my bands ---
     names = ["stage_in", "pad_screen_fft", "degrid", "zero_grid", "spread", "fft_crop_screen", "stage_out"]
-    phases = dict(zip(names, ph))
+    phases = dict.fromkeys(names, 0.0)
+    per_band = {}
+    for bd in bands:
+        gp = bd["gp"]
+        gp.set_profiling(True)
+        rec = []
+        for _ in range(3):
+            gp.hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(), stream)
+            torch.cuda.synchronize()
+            rec.append(gp.timings())
+        gp.set_profiling(False)
+        ph = np.median(np.array(rec), axis=0).tolist()
+        per_band[bd["b"]] = round(float(sum(ph)), 3)
+        for k, v in zip(names, ph):
+            phases[k] += v
 
     # ---- end to end through the operator call a pfb solver makes (host numpy in/out) ------
-    kw = dict(uvw=uvw, weight=d["wgt"], vis_mask=d["mask"], freq=freq, cell=cell, epsilon=cfg["epsilon"],
-              wsum=wsum, flip_v=True)
+    ops._CACHE_SIZE = max(ops._CACHE_SIZE, len(bands))
     ops.clear_plan_cache()
-    xo = np.empty_like(x)
+
+    def step_e2e():
+        for bd in bands:
+            d = bd["d"]
+            ops.hessian_slice(bd["x"], xout=bd["xo"], uvw=d["uvw"], weight=d["wgt"], vis_mask=d["mask"], freq=d["freq"],
+                              cell=bd["cell"], epsilon=cfg["epsilon"], wsum=bd["wsum"], flip_v=True)
+
+    for bd in bands:
+        bd["gp"].close()  # free the device-resident plans before the operator-level cache binds its own
+        bd["xo"] = np.empty_like(bd["x"])
     for _ in range(2):
-        ops.hessian_slice(x, xout=xo, **kw)  # first call binds the band (like load_band); later calls hit the cache
+        step_e2e()  # first call binds the band (like load_band); later calls hit the plan cache
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ops.hessian_slice(x, xout=xo, **kw)
+        step_e2e()
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) / args.steps
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = float(nvis_all.item()) / float(te.item()) / 1e6
+    info = None
+    if bands:
+        gp0 = ops._cached_plan(bands[0]["d"]["uvw"], bands[0]["d"]["freq"], bands[0]["d"]["mask"], bands[0]["d"]["wgt"],
+                               npix_x=cfg["nx"], npix_y=cfg["nx"], pixsize_x=float(bands[0]["cell"]),
+                               pixsize_y=float(bands[0]["cell"]), center_x=0.0, center_y=0.0, epsilon=float(cfg["epsilon"]),
+                               flip_u=False, flip_v=True, flip_w=False, do_wgridding=True, divide_by_n=False,
+                               precision=cfg["precision"])
+        info = gp0.info()
     ops.clear_plan_cache()
 
     if rank == 0:
@@ -252,51 +305,60 @@ def run_ours(args, cfg):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        B = algorithmic_bytes(info, nvis, freq.size, p)
+        nchan = cfg["nchan"]
+        # SURVEY §8(d) byte model summed over rank 0's bands (plans differ slightly per band; use band-0-of-rank plan)
+        B = sum(algorithmic_bytes(info, bd["nvis"], nchan, p) for bd in bands)
         kernel_phase = {"spread": "k_grid_runs (spreading kernel)", "degrid": "k_degrid_runs (gathering kernel)",
                         "pad_screen_fft": "k_rows_fwd + k_cols_fwd (fused pad/screen/FFT)",
                         "fft_crop_screen": "k_cols_inv + k_rows_inv (fused FFT/screen/crop)"}
         dom = max(kernel_phase, key=lambda k: phases.get(k, 0.0))
         # roofline of the gridding (spreading) kernel, the hand-written kernel SURVEY §8(d) models per sample
-        kb = spread_kernel_bytes(info, nvis, freq.size, p)
-        k_ms = phases.get("spread", float("nan"))
+        kb = sum(spread_kernel_bytes(info, bd["nvis"], nchan, p) for bd in bands) / len(bands)
+        k_ms = phases.get("spread", float("nan")) / len(bands)
         traffic = None
         try:  # measured DRAM bytes per launch from the committed ncu --set full capture of this workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tr.get(args.workload, {}).get("k_grid_runs")
         except Exception:
             pass
+        my_ms = ms_total / args.steps
         roof = {
-            "bound": "hbm", "kernel": "k_grid_runs (spreading kernel, one launch per Hessian apply)",
+            "bound": "hbm", "kernel": "k_grid_runs (spreading kernel, one launch per band and Hessian apply)",
             "achieved": kb / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": kb / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": kb,
             "note": "run kernels are issue-bound (ncu: DRAM throughput ~5 %, issue slots ~75 %); the plane stack stays L2-resident",
-            "step_algorithmic_bytes": B, "step_achieved": B / (ms_step * 1e-3) / 1e9,
-            "step_frac": B / (ms_step * 1e-3) / 1e9 / peak, "step_frac_of_nominal_8TBs": B / (ms_step * 1e-3) / 1e9 / 8000.0,
-            "dominant_phase": dom, "dominant_phase_kernels": kernel_phase[dom], "phases_ms": phases,
+            "step_algorithmic_bytes_rank0": B, "step_achieved_rank0": B / (my_ms * 1e-3) / 1e9,
+            "step_frac": B / (my_ms * 1e-3) / 1e9 / peak, "step_frac_of_nominal_8TBs": B / (my_ms * 1e-3) / 1e9 / 8000.0,
+            "dominant_phase": dom, "dominant_phase_kernels": kernel_phase[dom], "phases_ms_rank0": phases,
+            "ms_per_band_rank0": per_band,
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            c = cpu_hessian_sample(cfg, band, args.cpu_row_step)
+            c = cpu_hessian_sample(cfg, bands[0]["b"], args.cpu_row_step)
             cpu = {"value": c["value"], "unit": "Mvis/s", "cores": c["cores"], "kind": "port",
-                   "sample": (f"every {args.cpu_row_step}th row for the per-visibility loops ({c['nvis_sample']} of {c['nvis_full']} vis, "
-                              f"extrapolated), plane FFTs at full size; fp64 C/OpenMP restatement + scipy.fft (ducc0 unavailable); "
-                              f"planes {c['t_planes']:.1f}s, vis(sample) {c['t_vis_sample']:.1f}s")}
-        img_bytes = int(x.nbytes)
+                   "sample": (f"band {bands[0]['b']} only; every {args.cpu_row_step}th row for the per-visibility loops ({c['nvis_sample']} of "
+                              f"{c['nvis_full']} vis, extrapolated), plane FFTs at full size; fp64 C/OpenMP restatement + scipy.fft "
+                              f"(ducc0 unavailable); planes {c['t_planes']:.1f}s, vis(sample) {c['t_vis_sample']:.1f}s")}
+        img_bytes = int(sum(bd["x"].nbytes for bd in bands))
         line = {
             "metric": "Mvis/s per Hessian apply (degrid+grid)", "value": value, "unit": "Mvis/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if p == 4 else "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "bands": world, "nvis_per_band": nvis, "l2": "inputs larger than L2 (plane stack %.1f GB per band)" % (info["grid_bytes"] / 1e9),
-                       "plan": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "beta")},
-                       "parallelism": f"band-sharded x{world}, no data-path collective"},
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32" if p == 4 else "f64",
+            "data": "synthetic",
+            "config": {"workload": cfg["name"], "bands_total": nbands if strong else nbands * world,
+                       "bands_on_rank0": [bd["b"] for bd in bands],
+                       "strong_scaling_bound_one_job": round(sum(per_band.values()) / max(per_band.values()), 2),
+                       "nvis_total": int(nvis_all.item()),
+                       "l2": "inputs larger than L2 (plane stack %.1f GB per band)" % (info["grid_bytes"] / 1e9),
+                       "plan_first_band": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "beta")},
+                       "parallelism": (f"{nbands} bands of one job LPT-partitioned over {world} GPU(s)" if strong else
+                                       f"{world} job(s) of {nbands} band(s), one job per GPU") + ", no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "Mvis/s", "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
-                    "call": "operators.hessian_slice(x, uvw=, weight=, vis_mask=, freq=, ...) with host numpy in/out; band geometry pinned on first call"},
+                    "call": "operators.hessian_slice(x, uvw=, weight=, vis_mask=, freq=, ...) per band with host numpy in/out; band geometry pinned on first call"},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    gp.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -310,6 +372,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-row-step", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="partition ONE job's bands over the GPUs (strong scaling)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
