@@ -104,6 +104,7 @@ struct pfbg_plan {
   bool fused = false;          // tables built and sizes fit shared memory
   int col_c = 4;               // columns per CTA in the column passes
   cufftHandle fft = 0;
+  int fft_batch = 1;           // planes per cuFFT execution (a divisor of nplanes; bounds the work area)
   bool fft_ok = false;
   size_t fft_work = 0;
   int64_t nrow = 0, nvis = 0, nactive = 0;
@@ -318,7 +319,14 @@ static int fused_setup_t(pfbg_plan* pl) {
   pl->fused = false;
   const char* env = getenv("PFBG_FFT");
   if (env && strcmp(env, "cufft") == 0) return PFBG_OK;
+  // columns per CTA in the column passes: a full 32-byte sector per row if that fits shared memory,
+  // otherwise narrower blocks (half / quarter sectors; L2 merges the neighbours) for large grids
   pl->col_c = (int)(32 / sizeof(C));
+  while (pl->col_c > 1 && fft_smem_bytes<T>(g.nu * pl->col_c) > kMaxSmem) pl->col_c /= 2;
+  // measured on B200 (15360^2 x 63 planes): with narrower-than-sector column blocks and one row CTA
+  // per SM the fused kernels lose to cuFFT (710 ms vs 520 ms per apply), so large grids stay on cuFFT
+  // unless PFBG_FFT=fused asks for them
+  if (pl->col_c != (int)(32 / sizeof(C)) && !(env && strcmp(env, "fused") == 0)) return PFBG_OK;
   if (fft_smem_bytes<T>(g.nv) > kMaxSmem) return PFBG_OK;
   if (fft_smem_bytes<T>(g.nu * pl->col_c) > kMaxSmem) return PFBG_OK;
   FftDesc du, dv;
@@ -350,13 +358,12 @@ static int fused_setup_t(pfbg_plan* pl) {
   LAUNCHED();
   CK(cudaDeviceSynchronize());
   ft.nutab = (const double*)pl->nutab.p;
-  if (sizeof(T) == 4) {
-    CK(cudaFuncSetAttribute(k_cols_fwd<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    CK(cudaFuncSetAttribute(k_cols_inv<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-  } else {
-    CK(cudaFuncSetAttribute(k_cols_fwd<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    CK(cudaFuncSetAttribute(k_cols_inv<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-  }
+  CK(cudaFuncSetAttribute(k_cols_fwd<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_cols_inv<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_cols_fwd<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_cols_inv<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_cols_fwd<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_cols_inv<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   pl->fused = true;
   return PFBG_OK;
 }
@@ -368,10 +375,16 @@ static int cufft_setup(pfbg_plan* pl) {
   pl->fft_ok = true;
   long long n[2] = {g.nu, g.nv};
   size_t ws = 0;
+  // cuFFT's work area is about one batch of planes: keep a batch below ~8 GB so that very large
+  // stacks (e.g. 15360^2 x 64 planes = 121 GB) still fit the 180 GB of HBM
+  const size_t plane_bytes = (size_t)g.nu * g.nv * 2 * real_bytes(pl);
+  int batch = g.nplanes;
+  while (batch > 1 && ((size_t)batch * plane_bytes > ((size_t)8 << 30) || g.nplanes % batch)) --batch;
+  pl->fft_batch = batch;
   cufftResult r = cufftMakePlanMany64(pl->fft, 2, n, nullptr, 1, 0, nullptr, 1, 0,
-                                      pl->precision == PFBG_F32 ? CUFFT_C2C : CUFFT_Z2Z, g.nplanes, &ws);
+                                      pl->precision == PFBG_F32 ? CUFFT_C2C : CUFFT_Z2Z, batch, &ws);
   if (r != CUFFT_SUCCESS)
-    return fail(PFBG_ERR_CUFFT, "cufftMakePlanMany64(%d x %d, batch %d) failed (%d)", g.nu, g.nv, g.nplanes, (int)r);
+    return fail(PFBG_ERR_CUFFT, "cufftMakePlanMany64(%d x %d, batch %d) failed (%d)", g.nu, g.nv, batch, (int)r);
   pl->fft_work = ws;
   pl->total_bytes += ws;
   return PFBG_OK;
@@ -532,11 +545,17 @@ static int fetch(pfbg_plan* pl, DevBuf& stage, const void* src, size_t bytes, bo
 
 static int fft_exec(pfbg_plan* pl, cudaStream_t s, int dir) {
   CKFFT(cufftSetStream(pl->fft, s));
-  if (pl->precision == PFBG_F32)
-    CKFFT(cufftExecC2C(pl->fft, (cufftComplex*)pl->grid.p, (cufftComplex*)pl->grid.p, dir));
-  else
-    CKFFT(cufftExecZ2Z(pl->fft, (cufftDoubleComplex*)pl->grid.p, (cufftDoubleComplex*)pl->grid.p, dir));
-  LAUNCHED();
+  const size_t plane = (size_t)pl->gp.nu * pl->gp.nv;
+  for (int p0 = 0; p0 < pl->gp.nplanes; p0 += pl->fft_batch) {
+    if (pl->precision == PFBG_F32) {
+      cufftComplex* g = (cufftComplex*)pl->grid.p + (size_t)p0 * plane;
+      CKFFT(cufftExecC2C(pl->fft, g, g, dir));
+    } else {
+      cufftDoubleComplex* g = (cufftDoubleComplex*)pl->grid.p + (size_t)p0 * plane;
+      CKFFT(cufftExecZ2Z(pl->fft, g, g, dir));
+    }
+    LAUNCHED();
+  }
   return PFBG_OK;
 }
 
@@ -836,14 +855,18 @@ static int row_threads(int n, int cap) {
 template <typename T>
 static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam) {
   using C = typename cplx_of<T>::type;
-  constexpr int CC = (int)(32 / sizeof(C));
+  const int CC = pl->col_c;
   const GParams& g = pl->gp;
   const FusedTabs& ft = pl->ftabs;
   k_rows_fwd<T><<<dim3(g.nx, g.nplanes), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
       g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
-  k_cols_fwd<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, fft_smem_bytes<T>(g.nu * CC), s>>>(g, ft, (C*)pl->grid.p);
+  const dim3 cgrid(ft.b_len / CC, g.nplanes);
+  const size_t csm = fft_smem_bytes<T>(g.nu * CC);
+  if (CC == 4) k_cols_fwd<T, 4><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
+  else if (CC == 2) k_cols_fwd<T, 2><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
+  else k_cols_fwd<T, 1><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
   return PFBG_OK;
@@ -853,10 +876,14 @@ template <typename T>
 static int run_fused_inv(pfbg_plan* pl, cudaStream_t s, const void* beam, const void* xin, double inv_wsum, double eta,
                          void* out) {
   using C = typename cplx_of<T>::type;
-  constexpr int CC = (int)(32 / sizeof(C));
+  const int CC = pl->col_c;
   const GParams& g = pl->gp;
   const FusedTabs& ft = pl->ftabs;
-  k_cols_inv<T, CC><<<dim3(ft.b_len / CC, g.nplanes), 512, fft_smem_bytes<T>(g.nu * CC), s>>>(g, ft, (C*)pl->grid.p);
+  const dim3 cgrid(ft.b_len / CC, g.nplanes);
+  const size_t csm = fft_smem_bytes<T>(g.nu * CC);
+  if (CC == 4) k_cols_inv<T, 4><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
+  else if (CC == 2) k_cols_inv<T, 2><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
+  else k_cols_inv<T, 1><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
   const int64_t npix = (int64_t)g.nx * g.ny;
