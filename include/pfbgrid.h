@@ -94,6 +94,10 @@ int pfbg_device_count(int32_t* count);
 int pfbg_plan_create(const pfbg_plan_desc* desc, pfbg_plan** out);
 int pfbg_plan_destroy(pfbg_plan* plan);
 int pfbg_plan_get_info(const pfbg_plan* plan, pfbg_plan_info* info);
+/* Re-target a plan to another w-plane range (w0, nplanes); everything that depends only on the image
+ * geometry, sigma and W is kept.  Unbinds the visibilities.  Used to pool plans across the thousands of
+ * small snapshot images of `pfb hci` (utils/stokes2im.py:635-683). */
+int pfbg_plan_set_wrange(pfbg_plan* plan, double w0, int32_t nplanes);
 
 /*
  * Kernel 1: upload uvw (nrow,3) f64, fscale (nchan) f64 = freq/c, optional mask

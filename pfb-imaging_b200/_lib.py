@@ -59,6 +59,7 @@ SIGNATURES = {
     "pfbg_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(_vp)]),
     "pfbg_plan_destroy": (C.c_int, [_vp]),
     "pfbg_plan_get_info": (C.c_int, [_vp, C.POINTER(PlanInfo)]),
+    "pfbg_plan_set_wrange": (C.c_int, [_vp, _dbl, _i32]),
     "pfbg_bind_vis": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32, _vp]),
     "pfbg_bind_weights": (C.c_int, [_vp, _vp, _u32, _vp]),
     "pfbg_bin_dump": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

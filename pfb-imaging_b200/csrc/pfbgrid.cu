@@ -90,6 +90,7 @@ struct pfbg_plan {
   DevBuf img_in, img_out, img_beam;  // staging for host-pointer calls
   DevBuf vis_stage, wgt_stage;
   DevBuf flag;
+  DevBuf srt_ka, srt_kb, srt_va, srt_vb, srt_tmp;  // sort scratch, kept between bindings when small (snapshot imaging)
   // pinned host staging for host-pointer calls (pageable user arrays are copied through these by
   // several threads, chunk by chunk, overlapped with the DMA)
   void* h_in = nullptr;
@@ -151,7 +152,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   if (!pl) return PFBG_OK;
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
-  DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx,
+  DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx, &pl->srt_ka, &pl->srt_kb, &pl->srt_va, &pl->srt_vb, &pl->srt_tmp,
                    &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->cellflags, &pl->accimg, &pl->nutab, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
@@ -411,6 +412,34 @@ static void window_from_flags(const std::vector<int>& f, int size, int& lo, int&
   if (len > size) len = size;
 }
 
+// Re-target a plan to another w-range (same image geometry, sigma, W: corr / dw / nshift unchanged).
+// Lets one plan object serve many snapshots (pfb hci): no reallocation unless the stack must grow.
+extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  GParams& g = pl->gp;
+  if (!g.do_wgridding) {
+    if (nplanes != 1) return fail(PFBG_ERR_ARG, "nplanes must be 1 without w-gridding");
+    return PFBG_OK;
+  }
+  if (nplanes < g.W) return fail(PFBG_ERR_ARG, "nplanes=%d too small for W=%d", nplanes, g.W);
+  CK(cudaSetDevice(pl->device));
+  const size_t need = (size_t)nplanes * g.nu * g.nv * 2 * real_bytes(pl);
+  if (need > pl->grid.bytes) {
+    CK(cudaDeviceSynchronize());
+    CKRC(dev_alloc(pl, pl->grid, need));
+  }
+  if (nplanes != g.nplanes && pl->fft_ok) {  // the cuFFT batch depends on the plane count: rebuild lazily
+    cufftDestroy(pl->fft);
+    pl->fft_ok = false;
+    pl->total_bytes -= pl->fft_work;
+    pl->fft_work = 0;
+  }
+  g.w0 = w0;
+  g.nplanes = nplanes;
+  pl->bound = false;
+  return PFBG_OK;
+}
+
 extern "C" int pfbg_plan_get_info(const pfbg_plan* pl, pfbg_plan_info* info) {
   if (!pl || !info) return fail(PFBG_ERR_ARG, "null argument");
   memset(info, 0, sizeof *info);
@@ -622,8 +651,12 @@ extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fsc
   uint64_t maxkey = (uint64_t)g.ntile_u * g.ntile_v * (uint64_t)g.nplanes * (PFBG_TILE * PFBG_TILE);
   int bits = 1;
   while ((1ull << bits) <= maxkey) ++bits;  // inactive key = maxkey needs `bits` bits
-  DevBuf keys_a, keys_b, vals_a, vals_b, tmp;
-  auto cleanup = [&]() { dev_free(pl, keys_a); dev_free(pl, keys_b); dev_free(pl, vals_a); dev_free(pl, vals_b); dev_free(pl, tmp); };
+  DevBuf &keys_a = pl->srt_ka, &keys_b = pl->srt_kb, &vals_a = pl->srt_va, &vals_b = pl->srt_vb, &tmp = pl->srt_tmp;
+  const bool keep_scratch = nvis <= (int64_t)(4 << 20);  // <= 100 MB of scratch: keep it for the next binding
+  auto cleanup = [&]() {
+    if (keep_scratch) return;
+    dev_free(pl, keys_a); dev_free(pl, keys_b); dev_free(pl, vals_a); dev_free(pl, vals_b); dev_free(pl, tmp);
+  };
   int rc;
   if ((rc = dev_alloc(pl, keys_a, nvis * 8)) || (rc = dev_alloc(pl, keys_b, nvis * 8)) ||
       (rc = dev_alloc(pl, vals_a, nvis * 4)) || (rc = dev_alloc(pl, vals_b, nvis * 4))) { cleanup(); return rc; }

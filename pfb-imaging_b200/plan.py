@@ -21,6 +21,7 @@ Conventions (pinned by ``tests/test_hessian_approx.py:23-67`` and
 
 from __future__ import annotations
 
+import functools
 import math
 from dataclasses import dataclass, field
 
@@ -144,9 +145,21 @@ def w_range(uvw, freq, wsign=1.0):
     return min(cands), max(cands)
 
 
+@functools.lru_cache(maxsize=64)
 def _correction(n, nbig, W, beta):
     ip = np.arange(n) - n // 2
-    return 1.0 / kt.kernel_ft(ip / float(nbig), W, beta)
+    out = 1.0 / kt.kernel_ft(ip / float(nbig), W, beta)
+    out.setflags(write=False)
+    return out
+
+
+@functools.lru_cache(maxsize=4)
+def _gl_half(n):
+    gx, gw = leggauss(2 * n)
+    gx, gw = gx[n:].copy(), gw[n:].copy()  # positive half; the integrand is even
+    gx.setflags(write=False)
+    gw.setflags(write=False)
+    return gx, gw
 
 
 # Cost model (seconds, one direction), calibrated on B200 (DESIGN.md "plan cost model"):
@@ -273,8 +286,7 @@ def make_plan(
     else:
         w0 = 0.0
 
-    gx, gw = leggauss(2 * N_GL)
-    gl_x, gl_w = gx[N_GL:].copy(), gw[N_GL:].copy()  # positive half; integrand is even
+    gl_x, gl_w = _gl_half(N_GL)
 
     return Plan(
         precision=precision, nx=nx, ny=ny, nu=nu, nv=nv, W=W, beta=float(beta), sigma=float(s),

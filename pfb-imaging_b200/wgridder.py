@@ -220,6 +220,44 @@ class GridderPlan:
         return [ms[i] for i in range(n.value)]
 
 
+# ---------------------------------------------------------------------------
+# plan pool for the one-shot entry points: a plan is re-used whenever image geometry, sigma and W
+# agree (only the w-plane range and the bound samples change), which removes all per-call device /
+# pinned allocations and table set-up.  This is what makes thousands of small snapshot images
+# (pfb hci, utils/stokes2im.py:635-683) affordable.
+# ---------------------------------------------------------------------------
+_POOL: dict = {}
+_POOL_MAX = int(__import__("os").environ.get("PFBG_PLAN_POOL", "8"))
+
+
+def _pool_key(p: Plan, device):
+    return (device, p.precision, p.nx, p.ny, p.nu, p.nv, p.W, round(p.beta, 12), p.pixsize_x, p.pixsize_y,
+            p.center_x, p.center_y, p.usign, p.vsign, p.wsign, p.do_wgridding, p.divide_by_n, p.dw, p.nshift)
+
+
+def clear_plan_pool():
+    for lst in _POOL.values():
+        for gp in lst:
+            gp.close()
+    _POOL.clear()
+
+
+class _Pooled:
+    """Context manager handing out a pooled GridderPlan and taking it back afterwards."""
+
+    def __init__(self, gp, key):
+        self.gp, self.key = gp, key
+
+    def __enter__(self):
+        return self.gp
+
+    def __exit__(self, et, ev, tb):
+        if et is not None or _POOL_MAX <= 0 or sum(len(v) for v in _POOL.values()) >= _POOL_MAX:
+            self.gp.close()
+        else:
+            _POOL.setdefault(self.key, []).append(self.gp)
+
+
 def _precision_of(dtype, what):
     dt = np.dtype(dtype)
     if dt in (np.dtype(np.complex64), np.dtype(np.float32)):
@@ -231,7 +269,8 @@ def _precision_of(dtype, what):
 
 def plan_for(uvw, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
              flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
-             sigma_min=1.1, sigma_max=2.6, precision="double", mask=None, device=None, **force) -> GridderPlan:
+             sigma_min=1.1, sigma_max=2.6, precision="double", mask=None, device=None, pooled=False,
+             **force) -> GridderPlan:
     """Build a plan for the geometry and bind (uvw, freq, mask) to it."""
     uvw = np.asarray(uvw)
     freq = np.asarray(freq)
@@ -240,6 +279,22 @@ def plan_for(uvw, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, c
                   center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w,
                   do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min, sigma_max=sigma_max,
                   precision=precision, wmin=wmin, wmax=wmax, nvis=uvw.shape[0] * freq.size, **force)
+    if pooled and _POOL_MAX > 0:
+        dev = current_device() if device is None else int(device)
+        key = _pool_key(p, dev)
+        free = _POOL.get(key)
+        if free:
+            gp = free.pop()
+            _lib.check(gp._lib.pfbg_plan_set_wrange(gp._h, p.w0, p.nplanes))
+            gp.plan = p
+        else:
+            gp = GridderPlan(p, device=dev)
+        try:
+            gp.bind(uvw, freq, mask)
+        except Exception:
+            gp.close()
+            raise
+        return _Pooled(gp, key)
     gp = GridderPlan(p, device=device)
     try:
         gp.bind(uvw, freq, mask)
@@ -264,7 +319,7 @@ def vis2dirty(*, uvw, freq, vis, wgt=None, mask=None, npix_x, npix_y, pixsize_x,
     with plan_for(uvw, freq, npix_x=npix_x, npix_y=npix_y, pixsize_x=pixsize_x, pixsize_y=pixsize_y,
                   center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v,
                   flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min,
-                  sigma_max=sigma_max, precision=prec, mask=mask) as gp:
+                  sigma_max=sigma_max, precision=prec, mask=mask, pooled=True) as gp:
         return gp.grid(vis, wgt=wgt, dirty=dirty)
 
 
@@ -279,5 +334,5 @@ def dirty2vis(*, uvw, freq, dirty, wgt=None, mask=None, pixsize_x, pixsize_y, ce
     with plan_for(uvw, freq, npix_x=dirty.shape[0], npix_y=dirty.shape[1], pixsize_x=pixsize_x,
                   pixsize_y=pixsize_y, center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u,
                   flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=divide_by_n,
-                  sigma_min=sigma_min, sigma_max=sigma_max, precision=prec, mask=mask) as gp:
+                  sigma_min=sigma_min, sigma_max=sigma_max, precision=prec, mask=mask, pooled=True) as gp:
         return gp.degrid(dirty, wgt=wgt, vis=vis)

@@ -270,3 +270,25 @@ def test_full_size_properties_c1(gpu):
     hx, hy, hxy = gp.hessian(x), gp.hessian(y), gp.hessian(2.0 * x - 3.0 * y)
     assert rel_l2(hxy, 2.0 * hx - 3.0 * hy) <= 1e-11
     gp.close()
+
+
+def test_plan_pool_reuse_matches_fresh_plans(gpu):
+    """One-shot calls re-use pooled plans across different w-ranges / row counts (pfb hci pattern,
+    /root/reference/src/pfb_imaging/utils/stokes2im.py:635-683): results must equal those of fresh plans."""
+    W.clear_plan_pool()
+    outs = []
+    probs = [small_problem(nrow=300 + 50 * k, nchan=2, nx=64, ny=64, seed=k, wscale=0.5 + k) for k in range(4)]
+    for p in probs:
+        outs.append(W.vis2dirty(uvw=p["uvw"], freq=p["freq"], vis=p["vis"], wgt=p["wgt"], mask=p["mask"], npix_x=64,
+                                npix_y=64, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=1e-7, flip_v=True,
+                                sigma_min=2.0, sigma_max=2.0))
+    assert sum(len(v) for v in W._POOL.values()) >= 1
+    for p, o in zip(probs, outs):
+        with W.plan_for(p["uvw"], p["freq"], npix_x=64, npix_y=64, pixsize_x=p["cell"], pixsize_y=p["cell"],
+                        epsilon=1e-7, flip_v=True, sigma_min=2.0, sigma_max=2.0, mask=p["mask"]) as gp:
+            ref = gp.grid(p["vis"], p["wgt"])
+        assert rel_l2(o, ref) <= 1e-12
+        dref = dft.dft_vis2dirty(p["uvw"], p["freq"], p["vis"], p["wgt"], p["mask"], 64, 64, p["cell"], p["cell"], 0, 0,
+                                 False, True, False, True, True)
+        assert rel_l2(o, dref) <= 1e-7
+    W.clear_plan_pool()
