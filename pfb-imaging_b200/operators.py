@@ -28,7 +28,7 @@ from .wgridder import GridderPlan, dirty2vis, plan_for, vis2dirty
 __all__ = [
     "wgridder_conventions", "vis2im", "im2vis", "hessian_slice", "residual_from_partitions",
     "compute_residual_arrays", "image_data_products_arrays", "grid_partition", "eval_beam", "clear_plan_cache",
-    "BandHessian",
+    "BandHessian", "BandPool",
 ]
 
 
@@ -404,3 +404,52 @@ class BandHessian:
 
     def close(self):
         self.gp.close()
+
+
+class BandPool:
+    """Cube-level facade over per-band pinned operators: the B200 counterpart of ``BandWorkerPool``
+    (operators/band_worker.py:209-319) for the roles on the hot path — ``hess_dot``, ``hess_cg`` and the
+    exact ``residual``.  Bands this process does not own (``dist.local_bands``) are skipped; with
+    ``gather=True`` the (nband, ...) result is completed on every rank by one all-reduce."""
+
+    def __init__(self, band_ops, nband=None, gather=False):
+        from . import dist
+
+        self.ops = dict(band_ops) if isinstance(band_ops, dict) else dict(enumerate(band_ops))
+        self.nband = (max(self.ops) + 1) if nband is None else nband
+        self.gather = gather and dist.world_size() > 1
+        self._dist = dist
+
+    def _finish(self, out):
+        return self._dist.allreduce_sum(out) if self.gather else out
+
+    def hess_dot(self, x):
+        """x: (nband, nx, ny) -> H x, band by band (band_worker.py:276-281)."""
+        out = np.zeros_like(x)
+        for b, op in self.ops.items():
+            out[b] = op.dot(x[b])
+        return self._finish(out)
+
+    def hess_cg(self, rhs, x0=None, tol=1e-5, maxit=500, minit=1, verbosity=0):
+        """Per-band CG solve of H_b x_b = rhs_b (band_worker.py:124-140, 282-287)."""
+        from .solvers import pcg
+
+        out = np.zeros_like(rhs)
+        for b, op in self.ops.items():
+            xb = None if x0 is None else np.array(x0[b], copy=True)
+            out[b] = pcg(op.dot, np.ascontiguousarray(rhs[b]), x0=xb, tol=tol, maxit=maxit, minit=minit,
+                         verbosity=verbosity)
+        return self._finish(out)
+
+    def residual(self, model, dirty, cell_rad=None, epsilon=None, do_wgridding=None, double_accum=None):
+        """model, dirty: (nband, nx, ny) -> dirty - R^H W R (beam * model) (band_worker.py:167-180, 305-308).
+        Geometry / epsilon are those the band operators were built with; the extra arguments are accepted
+        for signature compatibility."""
+        out = np.zeros_like(dirty)
+        for b, op in self.ops.items():
+            out[b] = op.residual(dirty[b], model[b])
+        return self._finish(out)
+
+    def close(self):
+        for op in self.ops.values():
+            op.close()

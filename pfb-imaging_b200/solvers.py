@@ -1,0 +1,100 @@
+"""Callers of the Hessian on the hot path: conjugate gradients and the power method, with the
+scalar reductions routed through an optional cross-band all-reduce.
+
+Counterparts in the reference (/root/reference/src/pfb_imaging):
+  pcg            opt/pcg.py:202-314  (python-loop CG; `pcg_numba` :88-199 is the fused variant)
+  power_method   opt/power_method.py:40-92
+  norm_diff      opt/pcg.py:70-85
+The iteration contracts are kept: `eps = ||x - x_prev|| / ||x||`, at least `minit` and at most
+`maxit` iterations, stop after 5 stalled iterations; the power method stops on the relative change of
+the Rayleigh quotient.  When the cube is band-sharded (each rank holds its own bands, dist.py), pass
+`reduce=dist.allreduce_sum`: every dot product / norm then becomes ONE small all-reduce
+(2-3 doubles per iteration), which is all the communication these loops need.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def _identity(v):
+    return v
+
+
+def _dots(reduce, *pairs):
+    """Real parts of <a,b> for each pair, summed over ranks with one message."""
+    loc = np.array([float(np.vdot(a, b).real) for a, b in pairs], dtype=np.float64)
+    return reduce(loc) if reduce is not None else loc
+
+
+def norm_diff(x, xp, reduce=None):
+    d2, x2 = _dots(reduce, (x - xp, x - xp), (x, x))
+    return float(np.sqrt(d2 / x2)) if x2 > 0 else 0.0
+
+
+def pcg(aop, b, x0=None, precond=None, tol=1e-5, maxit=500, minit=100, verbosity=1, report_freq=10, backtrack=True,
+        return_resid=False, reduce=None):
+    """Preconditioned conjugate gradients for ``aop(x) = b`` (aop symmetric positive definite).
+
+    `x0` is updated in place and returned, like the reference."""
+    x = np.zeros(b.shape, dtype=b.dtype) if x0 is None else x0
+    minv = _identity if precond is None else precond
+    r = aop(x) - b
+    y = minv(r)
+    if not _dots(reduce, (y, y))[0] > 0.0:
+        if verbosity:
+            print("Initial residual is zero")
+        return (x, r) if return_resid else x
+    p = -y
+    rho = _dots(reduce, (r, y))[0]
+    phi0 = rho if (np.isfinite(rho) and rho != 0.0) else 1.0
+    k, eps, stalls = 0, 1.0, 0
+    xprev = np.empty_like(x)
+    while (eps > tol or k < minit) and k < maxit and stalls < 5:
+        np.copyto(xprev, x)
+        ap = aop(p)
+        rho, pap = _dots(reduce, (r, y), (p, ap))
+        alpha = rho / pap
+        x += alpha * p
+        r = r + alpha * ap
+        y = minv(r)
+        rho_next = _dots(reduce, (r, y))[0]
+        p *= rho_next / rho
+        p -= y
+        k += 1
+        eps_prev, eps = eps, norm_diff(x, xprev, reduce)
+        if abs(eps_prev - eps) < 1e-3 * tol:
+            stalls += 1
+        if verbosity > 1 and k % report_freq == 0:
+            print(f"At iteration {k} eps = {eps:.3e}, phi = {rho_next / phi0:.3e}")
+    if verbosity:
+        if k >= maxit:
+            print(f"Max iters reached. eps = {eps:.3e}")
+        elif stalls >= 5:
+            print(f"Stalled after {k} iterations with eps = {eps:.3e}")
+        else:
+            print(f"Success, converged after {k} iterations")
+    return (x, r) if return_resid else x
+
+
+def power_method(aop, imsize, b0=None, tol=1e-5, maxit=250, verbosity=1, report_freq=25, reduce=None, seed=None):
+    """Largest eigenvalue (spectral norm) of a symmetric operator and its eigenvector."""
+    if b0 is None:
+        b = np.random.default_rng(seed).standard_normal(imsize)
+    else:
+        b = np.array(b0, dtype=np.float64, copy=True)
+    b /= np.sqrt(_dots(reduce, (b, b))[0])
+    beta, eps, k = 1.0, 1.0, 0
+    while eps > tol and k < maxit:
+        ab = aop(b)
+        num, den, nrm2 = _dots(reduce, (b, ab), (b, b), (ab, ab))
+        beta_prev, beta = beta, num / den
+        b = ab / np.sqrt(nrm2)
+        eps = abs(beta - beta_prev) / abs(beta_prev)
+        k += 1
+        if verbosity > 1 and k % report_freq == 0:
+            print(f"At iteration {k} eps = {eps:.3e}")
+    if verbosity:
+        print(f"Maximum iterations reached. eps = {eps:.3e}, beta = {beta:.3e}" if k == maxit
+              else f"Success, converged after {k} iterations. beta = {beta:.3e}")
+    return beta, b
