@@ -166,6 +166,22 @@ int pfbg_counts_to_weights(int32_t precision, int32_t device, void* counts, cons
                            void* stream);
 
 /*
+ * PSF-convolution Hessian on the device (operators/hessian.py:103-143 hessian_psf_slice,
+ * operators/psf.py:8-31 psf_convolve_slice):
+ *     out = beam * crop( IFFT( FFT( pad(beam * x) ) * khat ) ) + eta * x
+ * x, beam, out: (nx,ny) real of `precision`; khat: complex of `precision`, either the r2c half spectrum
+ * (nx_psf, ny_psf/2+1) of a real kernel (PSFHAT / abspsf) or the full (nx_psf, ny_psf) spectrum.
+ * Padded sizes may contain the factors 2, 3, 5, 7, 11 (ducc0.fft.good_size).
+ */
+typedef struct pfbg_conv pfbg_conv;
+int pfbg_conv_create(int32_t precision, int32_t device, int32_t nx, int32_t ny, int32_t nx_psf, int32_t ny_psf,
+                     pfbg_conv** out);
+int pfbg_conv_destroy(pfbg_conv* conv);
+int pfbg_conv_set_kernel(pfbg_conv* conv, const void* khat, int32_t half, uint32_t flags, void* stream);
+int pfbg_conv_apply(pfbg_conv* conv, const void* x, const void* beam, double eta, void* out, uint32_t flags,
+                    void* stream);
+
+/*
  * Unit-test hook for the in-shared-memory FFT engine behind the fused plane transforms:
  * `batch` transforms of length n (2^a 3^b 5^c 7^d), complex of `precision`, host pointers.
  * mode 0 = decimation in frequency, 1 = decimation in time; inverse != 0 -> e^{+2 pi i nk/n}.

@@ -133,6 +133,17 @@ template <> __device__ __forceinline__ void root_of_unity<7>(int m, double& c, d
                            -0.43388373911755812048, -0.97492791218182360702, -0.78183148246802980871};
   c = C[m]; s = S[m];
 }
+template <> __device__ __forceinline__ void root_of_unity<11>(int m, double& c, double& s) {
+  constexpr double C[11] = {1.0, 0.84125353283118120551, 0.41541501300188643508, -0.14231483827328500480,
+                            -0.65486073394528498959, -0.95949297361449736865, -0.95949297361449736865,
+                            -0.65486073394528498959, -0.14231483827328500480, 0.41541501300188643508,
+                            0.84125353283118120551};
+  constexpr double S[11] = {0.0, 0.54064081745559755543, 0.90963199535451833011, 0.98982144188093279524,
+                            0.75574957435425826890, 0.28173255684142967104, -0.28173255684142967104,
+                            -0.75574957435425826890, -0.98982144188093279524, -0.90963199535451833011,
+                            -0.54064081745559755543};
+  c = C[m]; s = S[m];
+}
 template <typename T, int R> __device__ __forceinline__ void dft_direct(cx2<T>* x) {
   cx2<T> y[R];
 #pragma unroll
@@ -156,6 +167,9 @@ template <typename T> struct SmallDft<T, 5> {
 };
 template <typename T> struct SmallDft<T, 7> {
   __device__ static __forceinline__ void run(cx2<T>* x) { dft_direct<T, 7>(x); }
+};
+template <typename T> struct SmallDft<T, 11> {  // ducc0.fft.good_size admits the factor 11 (PSF grids)
+  __device__ static __forceinline__ void run(cx2<T>* x) { dft_direct<T, 11>(x); }
 };
 
 // ---------------------------------------------------------------------------
@@ -249,7 +263,8 @@ __device__ __forceinline__ void fft_stage_dispatch(int r, cx2<T>* s, const cx2<T
     case 2: fft_stage<T, 2, C, DIT>(s, tw, N, L, tid, nthr); break;
     case 3: fft_stage<T, 3, C, DIT>(s, tw, N, L, tid, nthr); break;
     case 5: fft_stage<T, 5, C, DIT>(s, tw, N, L, tid, nthr); break;
-    default: fft_stage<T, 7, C, DIT>(s, tw, N, L, tid, nthr); break;
+    case 7: fft_stage<T, 7, C, DIT>(s, tw, N, L, tid, nthr); break;
+    default: fft_stage<T, 11, C, DIT>(s, tw, N, L, tid, nthr); break;
   }
 }
 

@@ -261,7 +261,7 @@ static bool factorize(int n, FftDesc& d) {
   d.n = n;
   d.nstage = 0;
   int m = n;
-  const int odd[3] = {7, 5, 3};
+  const int odd[4] = {11, 7, 5, 3};
   for (int r : odd)
     while (m % r == 0) {
       if (d.nstage >= FFT_MAX_STAGES) return false;
@@ -1281,4 +1281,173 @@ extern "C" int pfbg_debug_fft1d(int32_t precision, int32_t device, int32_t n, in
   CK(cudaSetDevice(device));
   return precision == PFBG_F32 ? debug_fft_t<float>(n, batch, in, out, mode, inverse)
                                : debug_fft_t<double>(n, batch, in, out, mode, inverse);
+}
+
+// ---------------------------------------------------------------------------
+// PSF-convolution Hessian (psfconv.cuh)
+// ---------------------------------------------------------------------------
+#include "psfconv.cuh"
+
+struct pfbg_conv {
+  int precision = 0, device = 0;
+  ConvTabs ct{};
+  int col_c = 1;
+  void *tw_u = nullptr, *tw_v = nullptr, *rev_u = nullptr, *rev_v = nullptr, *pos_v = nullptr;
+  void *khat = nullptr, *tmp = nullptr, *d_x = nullptr, *d_beam = nullptr, *d_out = nullptr;
+  bool has_kernel = false;
+};
+
+template <typename T>
+static int conv_setup_t(pfbg_conv* cv) {
+  const ConvTabs& c0 = cv->ct;
+  FftDesc du, dv;
+  if (!factorize(c0.nxp, du) || !factorize(c0.nyp, dv))
+    return fail(PFBG_ERR_ARG, "padded sizes %d x %d must be 2^a 3^b 5^c 7^d 11^e", c0.nxp, c0.nyp);
+  if (fft_smem_bytes<T>(c0.nyp) > kMaxSmem) return fail(PFBG_ERR_ARG, "ny_psf=%d too large for the shared-memory FFT", c0.nyp);
+  int cc = (int)(32 / sizeof(cx2<T>));
+  while (cc > 1 && (c0.nyp % cc || fft_smem_bytes<T>(c0.nxp * cc) > kMaxSmem)) cc /= 2;
+  if (fft_smem_bytes<T>(c0.nxp * cc) > kMaxSmem) return fail(PFBG_ERR_ARG, "nx_psf=%d too large for the shared-memory FFT", c0.nxp);
+  cv->col_c = cc;
+  auto up = [&](void** dst, const void* src, size_t bytes) -> int {
+    CK(cudaMalloc(dst, bytes));
+    CK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return PFBG_OK;
+  };
+  std::vector<cx2<T>> tw;
+  auto mk = [&](int n) {
+    tw.resize(n);
+    for (int t = 0; t < n; ++t) {
+      double ang = -2.0 * M_PI * (double)t / (double)n;
+      tw[t].x = (T)cos(ang);
+      tw[t].y = (T)sin(ang);
+    }
+  };
+  std::vector<int> rev, pos;
+  mk(c0.nxp);
+  CKRC(up(&cv->tw_u, tw.data(), tw.size() * sizeof(cx2<T>)));
+  mk(c0.nyp);
+  CKRC(up(&cv->tw_v, tw.data(), tw.size() * sizeof(cx2<T>)));
+  digit_tables(du, rev, pos);
+  CKRC(up(&cv->rev_u, rev.data(), rev.size() * 4));
+  digit_tables(dv, rev, pos);
+  CKRC(up(&cv->rev_v, rev.data(), rev.size() * 4));
+  CKRC(up(&cv->pos_v, pos.data(), pos.size() * 4));
+  const size_t rb = sizeof(T);
+  CK(cudaMalloc(&cv->khat, (size_t)c0.nxp * c0.nyp * 2 * rb));
+  CK(cudaMalloc(&cv->tmp, (size_t)c0.nx * c0.nyp * 2 * rb));
+  CK(cudaMalloc(&cv->d_x, (size_t)c0.nx * c0.ny * rb));
+  CK(cudaMalloc(&cv->d_beam, (size_t)c0.nx * c0.ny * rb));
+  CK(cudaMalloc(&cv->d_out, (size_t)c0.nx * c0.ny * rb));
+  ConvTabs& ct = cv->ct;
+  ct.du = du; ct.dv = dv;
+  ct.tw_u = cv->tw_u; ct.tw_v = cv->tw_v;
+  ct.rev_u = (const int*)cv->rev_u; ct.rev_v = (const int*)cv->rev_v; ct.pos_v = (const int*)cv->pos_v;
+  CK(cudaFuncSetAttribute(k_conv_rows_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_conv_rows_inv<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_conv_cols<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_conv_cols<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_conv_cols<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_conv_destroy(pfbg_conv* cv) {
+  if (!cv) return PFBG_OK;
+  cudaSetDevice(cv->device);
+  void* all[] = {cv->tw_u, cv->tw_v, cv->rev_u, cv->rev_v, cv->pos_v, cv->khat, cv->tmp, cv->d_x, cv->d_beam, cv->d_out};
+  for (void* p : all)
+    if (p) cudaFree(p);
+  delete cv;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_conv_create(int32_t precision, int32_t device, int32_t nx, int32_t ny, int32_t nx_psf,
+                                int32_t ny_psf, pfbg_conv** out) {
+  if (!out) return fail(PFBG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (precision != PFBG_F32 && precision != PFBG_F64) return fail(PFBG_ERR_ARG, "bad precision");
+  if (nx <= 0 || ny <= 0 || nx_psf < nx || ny_psf < ny) return fail(PFBG_ERR_ARG, "need 0 < nx <= nx_psf and 0 < ny <= ny_psf");
+  CK(cudaSetDevice(device));
+  pfbg_conv* cv = new pfbg_conv();
+  cv->precision = precision; cv->device = device;
+  cv->ct.nx = nx; cv->ct.ny = ny; cv->ct.nxp = nx_psf; cv->ct.nyp = ny_psf;
+  int rc = precision == PFBG_F32 ? conv_setup_t<float>(cv) : conv_setup_t<double>(cv);
+  if (rc) { pfbg_conv_destroy(cv); return rc; }
+  *out = cv;
+  return PFBG_OK;
+}
+
+// khat: complex multiplier of `precision`; half != 0: (nx_psf, ny_psf/2+1) half spectrum of a real kernel
+// (r2c layout: PSFHAT / abspsf), else the full (nx_psf, ny_psf) spectrum.
+extern "C" int pfbg_conv_set_kernel(pfbg_conv* cv, const void* khat, int32_t half, uint32_t flags, void* stream) {
+  if (!cv || !khat) return fail(PFBG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(cv->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const ConvTabs& ct = cv->ct;
+  const size_t cb = cv->precision == PFBG_F32 ? 8 : 16;
+  const cudaMemcpyKind kind = (flags & PFBG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (!half) {
+    CK(cudaMemcpyAsync(cv->khat, khat, (size_t)ct.nxp * ct.nyp * cb, kind, s));
+  } else {
+    const size_t hb = (size_t)ct.nxp * (ct.nyp / 2 + 1) * cb;
+    void* dh = nullptr;
+    CK(cudaMalloc(&dh, hb));
+    cudaError_t e = cudaMemcpyAsync(dh, khat, hb, kind, s);
+    if (e == cudaSuccess) {
+      dim3 grd((ct.nyp + 127) / 128, ct.nxp);
+      if (cv->precision == PFBG_F32) k_expand_half<float><<<grd, 128, 0, s>>>(ct.nxp, ct.nyp, (const cx2<float>*)dh, (cx2<float>*)cv->khat);
+      else k_expand_half<double><<<grd, 128, 0, s>>>(ct.nxp, ct.nyp, (const cx2<double>*)dh, (cx2<double>*)cv->khat);
+      LAUNCHED();
+      e = cudaStreamSynchronize(s);
+    }
+    cudaFree(dh);
+    if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "set_kernel failed: %s", cudaGetErrorString(e));
+  }
+  CK(cudaStreamSynchronize(s));
+  cv->has_kernel = true;
+  return PFBG_OK;
+}
+
+template <typename T>
+static int conv_apply_t(pfbg_conv* cv, const void* x, const void* beam, double eta, void* out, cudaStream_t s) {
+  const ConvTabs& ct = cv->ct;
+  const int rt = row_threads(ct.nyp, 256);
+  k_conv_rows_fwd<T><<<ct.nx, rt, fft_smem_bytes<T>(ct.nyp), s>>>(ct, (const T*)x, (const T*)beam, (cx2<T>*)cv->tmp);
+  LAUNCHED();
+  const int cc = cv->col_c;
+  const size_t csm = fft_smem_bytes<T>(ct.nxp * cc);
+  if (cc == 4) k_conv_cols<T, 4><<<ct.nyp / 4, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
+  else if (cc == 2) k_conv_cols<T, 2><<<ct.nyp / 2, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
+  else k_conv_cols<T, 1><<<ct.nyp, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
+  LAUNCHED();
+  const double scale = 1.0 / ((double)ct.nxp * (double)ct.nyp);
+  k_conv_rows_inv<T><<<ct.nx, rt, fft_smem_bytes<T>(ct.nyp), s>>>(ct, (const cx2<T>*)cv->tmp, (const T*)beam,
+                                                                 eta != 0.0 ? (const T*)x : nullptr, scale, eta, (T*)out);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+
+// out = beam * crop(IFFT(FFT(pad(beam * x)) * khat)) + eta * x      (beam may be NULL)
+extern "C" int pfbg_conv_apply(pfbg_conv* cv, const void* x, const void* beam, double eta, void* out, uint32_t flags,
+                               void* stream) {
+  if (!cv || !x || !out) return fail(PFBG_ERR_ARG, "null argument");
+  if (!cv->has_kernel) return fail(PFBG_ERR_STATE, "no kernel set");
+  CK(cudaSetDevice(cv->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t ib = (size_t)cv->ct.nx * cv->ct.ny * (cv->precision == PFBG_F32 ? 4 : 8);
+  const void *dx = x, *db = beam;
+  void* dout = out;
+  if (!dev) {
+    CK(cudaMemcpyAsync(cv->d_x, x, ib, cudaMemcpyHostToDevice, s));
+    dx = cv->d_x;
+    if (beam) { CK(cudaMemcpyAsync(cv->d_beam, beam, ib, cudaMemcpyHostToDevice, s)); db = cv->d_beam; }
+    dout = cv->d_out;
+  }
+  CKRC(cv->precision == PFBG_F32 ? conv_apply_t<float>(cv, dx, db, eta, dout, s) : conv_apply_t<double>(cv, dx, db, eta, dout, s));
+  if (!dev) {
+    CK(cudaMemcpyAsync(out, dout, ib, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return PFBG_OK;
 }
