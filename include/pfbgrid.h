@@ -66,7 +66,8 @@ typedef struct pfbg_plan_desc {
   double pixsize_x, pixsize_y;
   double center_x, center_y; /* after the flip rule */
   double usign, vsign, wsign; /* +-1 */
-  double w0, dw, nshift;
+  double w0, dw, nshift; /* plane p sits at w0 + p*dw; the planes must cover |w| f/c of all samples:
+                          * samples with w < 0 are folded onto -(u,v,w) with the conjugate visibility */
   const double* corr_u;  /* host (nx): 1/psihat_u */
   const double* corr_v;  /* host (ny) */
   const double* gl_x;    /* host (n_gl): Gauss-Legendre nodes on (0,1) */

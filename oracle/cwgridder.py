@@ -96,6 +96,7 @@ def vis2dirty_c(plan, uvw, freq, vis, wgt=None, mask=None, b=None, timings=None)
     a = np.asarray(vis).astype(np.complex128).ravel()[b["idx"]]
     if wgt is not None:
         a = a * np.asarray(wgt, dtype=np.float64).ravel()[b["idx"]]
+    a = np.where(b["conj"], np.conj(a), a)  # Hermitian fold (bin_indices)
     a = np.ascontiguousarray(a * np.exp(2j * np.pi * wg._vis_phase(plan, b)))
     t1 = time.perf_counter()
     grid = np.zeros((P, nu, nv), dtype=np.complex128)
@@ -151,6 +152,7 @@ def dirty2vis_c(plan, uvw, freq, dirty, mask=None, b=None, timings=None):
     lib().cw_degrid(C.c_int64(n), _p(b["order"]), _p(b["gu"]), _p(b["gv"]), _p(b["gw"]), _p(b["iu0"]), _p(b["iv0"]),
                     _p(b["ip0"]), W, C.c_double(plan.beta), nu, nv, P, int(plan.do_wgridding), _p(grid), _p(out))
     out *= np.exp(-2j * np.pi * wg._vis_phase(plan, b))
+    np.conjugate(out, out=out, where=b["conj"])
     t3 = time.perf_counter()
     nrow, nchan = np.asarray(uvw).shape[0], np.asarray(freq).size
     vis = np.zeros(nrow * nchan, dtype=np.complex128)

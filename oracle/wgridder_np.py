@@ -68,6 +68,12 @@ def bin_indices(plan, uvw, freq, mask=None):
     ut = (plan.usign * uvw[:, 0])[:, None] * s[None, :]
     vt = (plan.vsign * uvw[:, 1])[:, None] * s[None, :]
     wt = (plan.wsign * uvw[:, 2])[:, None] * s[None, :]
+    # Hermitian fold: samples with w < 0 are handled at -(u,v,w) with the conjugate visibility
+    # (valid because the image is real); the w-planes then only cover |w|.  ducc0 does the same.
+    fold = (wt < 0.0) if plan.do_wgridding else np.zeros(wt.shape, dtype=bool)
+    ut = np.where(fold, -ut, ut)
+    vt = np.where(fold, -vt, vt)
+    wt = np.where(fold, -wt, wt)
 
     def coord(t, pix, n):
         x = t * pix
@@ -105,7 +111,7 @@ def bin_indices(plan, uvw, freq, mask=None):
     return dict(
         idx=idx.astype(np.int64), iu0=iu0.astype(np.int32), iv0=iv0.astype(np.int32),
         ip0=ip0.astype(np.int32), key=key, order=order.astype(np.int64), gu=gu, gv=gv, gw=gw,
-        ut=ut.ravel()[idx], vt=vt.ravel()[idx], wt=wt.ravel()[idx],
+        ut=ut.ravel()[idx], vt=vt.ravel()[idx], wt=wt.ravel()[idx], conj=fold.ravel()[idx],
     )
 
 
@@ -179,6 +185,7 @@ def vis2dirty_np(plan, uvw, freq, vis, wgt=None, mask=None, chunk=20000):
     b = bin_indices(plan, uvw, freq, mask)
     W, P, nu, nv = plan.W, plan.nplanes, plan.nu, plan.nv
     a = np.asarray(vis).astype(np.complex128).ravel()[b["idx"]]
+    a = np.where(b["conj"], np.conj(a), a)
     if wgt is not None:
         a = a * np.asarray(wgt, dtype=np.float64).ravel()[b["idx"]]
     a = a * np.exp(2j * np.pi * _vis_phase(plan, b))
@@ -256,6 +263,7 @@ def dirty2vis_np(plan, uvw, freq, dirty, mask=None, chunk=20000):
             acc += kw[:, q] * np.einsum("nij,ni,nj->n", g, ku, kv)
         out[sl] = acc
     out *= np.exp(-2j * np.pi * _vis_phase(plan, b))
+    out = np.where(b["conj"], np.conj(out), out)
     nrow, nchan = np.asarray(uvw).shape[0], np.asarray(freq).size
     vis = np.zeros(nrow * nchan, dtype=np.complex128)
     vis[b["idx"]] = out

@@ -35,6 +35,7 @@ struct VisCoord {
   double ut, vt, wt;  // wavelengths, signs applied
   double gu, gv, gw;  // grid coordinates
   int iu0, iv0, ip0;  // first touched cell / plane
+  int conj;           // sample folded onto w >= 0: (u,v,w) -> -(u,v,w), visibility conjugated
 };
 
 __device__ __forceinline__ VisCoord vis_coord(const GParams& p, const double* __restrict__ uvw,
@@ -44,6 +45,10 @@ __device__ __forceinline__ VisCoord vis_coord(const GParams& p, const double* __
   c.ut = __dmul_rn(__dmul_rn(p.usign, uvw[3 * row + 0]), s);
   c.vt = __dmul_rn(__dmul_rn(p.vsign, uvw[3 * row + 1]), s);
   c.wt = __dmul_rn(__dmul_rn(p.wsign, uvw[3 * row + 2]), s);
+  // Hermitian fold (the image is real, so V(-u,-v,-w) = conj V(u,v,w)): samples with w < 0 are
+  // gridded at -(u,v,w) with the conjugate visibility, which halves the w-range the planes cover.
+  c.conj = 0;
+  if (p.do_wgridding && c.wt < 0.0) { c.ut = -c.ut; c.vt = -c.vt; c.wt = -c.wt; c.conj = 1; }
   axis_coord(c.ut, p.pixsize_x, p.nu, p.W, c.gu, c.iu0);
   axis_coord(c.vt, p.pixsize_y, p.nv, p.W, c.gv, c.iv0);
   if (p.do_wgridding) {

@@ -74,6 +74,7 @@ k_grid_direct(GParams p, const double* __restrict__ uvw, const double* __restric
     T w = wgt ? wgt[idx] : (T)1;
     T pc = 1, ps = 0;
     if (apply_phase) cis_turns(vis_phase_turns(p, c), pc, ps);
+    if (apply_phase && c.conj) a.y = -a.y;
     T are = (a.x * pc - a.y * ps) * w, aim = (a.x * ps + a.y * pc) * w;
     __syncwarp();
     for (int t = lane; t < 3 * W; t += 32) {
@@ -159,6 +160,7 @@ k_degrid_direct(GParams p, const double* __restrict__ uvw, const double* __restr
         re = accr * pc + acci * ps;
         im = acci * pc - accr * ps;
       }
+      if (apply_phase && c.conj) im = -im;
       if (wgt) { T w = wgt[idx]; re *= w; im *= w; }
       C o; o.x = re; o.y = im;
       if (out_sorted) out_sorted[k] = o; else vis_out[idx] = o;

@@ -27,7 +27,7 @@ template <> struct __align__(16) VisRec<float> {
   uint32_t idx;       // flat (row, chan) index
   float pc, ps;       // e^{+2 pi i (u x0 + v y0 + w nshift)}
   uint16_t iu, iv;    // wrapped first cell
-  int32_t ip;         // first plane
+  int32_t ip;         // first plane; bit 30 = folded sample (visibility conjugated)
 };
 template <> struct __align__(16) VisRec<double> {
   double x0[3];
@@ -40,8 +40,9 @@ template <> struct __align__(16) VisRec<double> {
 static_assert(sizeof(VisRec<float>) == 32, "VisRec<float> must be 32 bytes");
 static_assert(sizeof(VisRec<double>) == 64, "VisRec<double> must be 64 bytes");
 
+#define REC_CONJ_BIT 0x40000000
 __device__ __forceinline__ uint64_t pack_origin(uint32_t iu, uint32_t iv, int32_t ip) {
-  return ((uint64_t)(uint32_t)ip << 32) | ((uint64_t)iu << 16) | (uint64_t)iv;
+  return ((uint64_t)(uint32_t)(ip & ~REC_CONJ_BIT) << 32) | ((uint64_t)iu << 16) | (uint64_t)iv;
 }
 
 // kernel 1b: per-sample records in bucket order
@@ -62,7 +63,7 @@ __global__ void k_make_recs(GParams p, const double* __restrict__ uvw, const dou
   cis_turns(vis_phase_turns(p, c), r.pc, r.ps);
   r.iu = (uint16_t)wrap(c.iu0, p.nu);
   r.iv = (uint16_t)wrap(c.iv0, p.nv);
-  r.ip = c.ip0;
+  r.ip = c.ip0 | (c.conj ? REC_CONJ_BIT : 0);
   recs[k] = r;
 }
 
@@ -172,6 +173,7 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
         }
         T w = wgt ? wgt[r.idx] : (T)1;
         T pc = apply_phase ? r.pc : (T)1, ps = apply_phase ? r.ps : (T)0;
+        if (apply_phase && (r.ip & REC_CONJ_BIT)) a.y = -a.y;  // folded sample (the Hessian path stays folded)
         C s;
         s.x = (a.x * pc - a.y * ps) * w;
         s.y = (a.x * ps + a.y * pc) * w;
@@ -299,6 +301,7 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
           re = sr * r.pc + si * r.ps;
           im = si * r.pc - sr * r.ps;
         }
+        if (apply_phase && (r.ip & REC_CONJ_BIT)) im = -im;
         if (wgt) { T w = wgt[r.idx]; re *= w; im *= w; }
         C o; o.x = re; o.y = im;
         if (out_sorted) out_sorted[k0 + lane] = o; else vis_out[r.idx] = o;
@@ -413,6 +416,7 @@ k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
         }
         T w = wgt ? wgt[r.idx] : (T)1;
         T pc = apply_phase ? r.pc : (T)1, ps = apply_phase ? r.ps : (T)0;
+        if (apply_phase && (r.ip & REC_CONJ_BIT)) a.y = -a.y;  // folded sample (the Hessian path stays folded)
         C s;
         s.x = (a.x * pc - a.y * ps) * w;
         s.y = (a.x * ps + a.y * pc) * w;
@@ -546,6 +550,7 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
           re = myr * r.pc + myi * r.ps;
           im = myi * r.pc - myr * r.ps;
         }
+        if (apply_phase && (r.ip & REC_CONJ_BIT)) im = -im;
         if (wgt) { T w = wgt[r.idx]; re *= w; im *= w; }
         C* dst = out_sorted ? (out_sorted + k0 + lane) : (vis_out + r.idx);
         atomicAdd(&dst->x, re);

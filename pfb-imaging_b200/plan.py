@@ -134,15 +134,17 @@ class Plan:
 
 
 def w_range(uvw, freq, wsign=1.0):
-    """min/max of w*f/c over all rows and channels (wavelengths)."""
-    w = np.asarray(uvw)[:, 2].astype(np.float64) * wsign
+    """min/max of |w|*f/c over all rows and channels (wavelengths).
+
+    The kernels fold samples with w < 0 onto -(u,v,w) with the conjugate visibility (the image is
+    real), so the plane stack only has to cover |w|; `wsign` is therefore irrelevant and kept for
+    the call signature only.
+    """
+    w = np.abs(np.asarray(uvw)[:, 2].astype(np.float64))
     f = np.asarray(freq, dtype=np.float64)
     if w.size == 0 or f.size == 0:
         return 0.0, 0.0
-    s_lo, s_hi = f.min() / LIGHTSPEED, f.max() / LIGHTSPEED
-    wmin, wmax = float(w.min()), float(w.max())
-    cands = (wmin * s_lo, wmin * s_hi, wmax * s_lo, wmax * s_hi)
-    return min(cands), max(cands)
+    return float(w.min()) * float(f.min()) / LIGHTSPEED, float(w.max()) * float(f.max()) / LIGHTSPEED
 
 
 @functools.lru_cache(maxsize=64)
