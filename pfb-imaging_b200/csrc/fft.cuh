@@ -220,14 +220,19 @@ __device__ __forceinline__ void fft_stage(cx2<T>* __restrict__ s, const cx2<T>* 
   constexpr int PERIOD = sizeof(T) == 4 ? 16 : 8;
   const bool lin = ((M * C) % PERIOD) == 0;
   const int pstride = M * C + (M * C) / PERIOD;
+  // the twiddle of the NEXT butterfly is fetched (global memory, L2 latency) while this one is computed
+  auto k_of = [&](int w) {
+    const int bk = (C == 1) ? w : (w / C);
+    const int g = pow2 ? (bk >> lgM) : (bk / M);
+    return bk - g * M;
+  };
+  cx2<T> tw_next = tid < nbf ? tw[k_of(tid) * tstride] : cx2<T>{(T)1, (T)0};
   for (int w = tid; w < nbf; w += nthr) {
+    const cx2<T> tw_cur = tw_next;
+    if (w + nthr < nbf) tw_next = tw[k_of(w + nthr) * tstride];
     const int c = (C == 1) ? 0 : (w % C);
     const int bk = (C == 1) ? w : (w / C);
-#ifdef FFT_NO_POW2
-    const int g = bk / M;
-#else
     const int g = pow2 ? (bk >> lgM) : (bk / M);
-#endif
     const int k = bk - g * M;
     const int e0 = (g * L + k) * C + c;
     cx2<T> x[R];
@@ -241,9 +246,9 @@ __device__ __forceinline__ void fft_stage(cx2<T>* __restrict__ s, const cx2<T>* 
 #pragma unroll
       for (int m = 0; m < R; ++m) x[m] = s[fft_pad<T>(e0 + m * M * C)];
     }
-    if (DIT && k != 0) apply_twiddles<T, R>(x, tw[k * tstride]);
+    if (DIT && k != 0) apply_twiddles<T, R>(x, tw_cur);
     SmallDft<T, R>::run(x);
-    if (!DIT && k != 0) apply_twiddles<T, R>(x, tw[k * tstride]);
+    if (!DIT && k != 0) apply_twiddles<T, R>(x, tw_cur);
     if (lin) {
 #pragma unroll
       for (int m = 0; m < R; ++m) s[a0 + m * pstride] = x[m];
@@ -254,8 +259,69 @@ __device__ __forceinline__ void fft_stage(cx2<T>* __restrict__ s, const cx2<T>* 
   }
 }
 
+// Power-of-two stage with the butterfly stride M = 2^LGM known at compile time.  Every element of
+// a butterfly then sits at  pad(e0) + pad(m*M*C):  with S = R*M*C the butterfly span, e0 = A + r,
+// A a multiple of S and r < M*C, the pad term (e >> 4|3) splits exactly because M*C and S are
+// powers of two.  All shared-memory accesses become one base register + immediate offsets and the
+// index arithmetic shrinks to shifts (the generic stage spends ~40 % of its instructions on it).
+template <typename T, int R, int LGM, int C, bool DIT>
+__device__ __forceinline__ void fft_stage_p2(cx2<T>* __restrict__ s, const cx2<T>* __restrict__ tw, int N, int tid,
+                                             int nthr) {
+  constexpr int M = 1 << LGM, MC = M * C;
+  constexpr int LGC = C == 1 ? 0 : (C == 2 ? 1 : 2);
+  constexpr int LGR = R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : 4));
+  const int tstride = N >> (LGM + LGR);  // N / L, L = R * M
+  const int nbf = (N >> LGR) * C;
+  // M == 1: every twiddle is 1.  Otherwise the NEXT butterfly's twiddle is fetched while this one runs.
+  cx2<T> tw_next = (M > 1 && tid < nbf) ? tw[((tid >> LGC) & (M - 1)) * tstride] : cx2<T>{(T)1, (T)0};
+  for (int w = tid; w < nbf; w += nthr) {
+    const cx2<T> tw_cur = tw_next;
+    if (M > 1 && w + nthr < nbf) tw_next = tw[(((w + nthr) >> LGC) & (M - 1)) * tstride];
+    const int c = w & (C - 1);
+    const int bk = w >> LGC;
+    const int g = bk >> LGM, k = bk & (M - 1);
+    const int e0 = (((g << (LGM + LGR)) + k) << LGC) + c;
+    cx2<T>* __restrict__ b = s + fft_pad<T>(e0);
+    cx2<T> x[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) x[m] = b[fft_pad<T>(m * MC)];
+    if (M > 1 && DIT && k != 0) apply_twiddles<T, R>(x, tw_cur);
+    SmallDft<T, R>::run(x);
+    if (M > 1 && !DIT && k != 0) apply_twiddles<T, R>(x, tw_cur);
+#pragma unroll
+    for (int m = 0; m < R; ++m) b[fft_pad<T>(m * MC)] = x[m];
+  }
+}
+
+template <typename T, int R, int C, bool DIT>
+__device__ __forceinline__ bool fft_stage_p2_dispatch(cx2<T>* s, const cx2<T>* tw, int N, int M, int tid, int nthr) {
+  switch (M) {
+    case 1: fft_stage_p2<T, R, 0, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 2: fft_stage_p2<T, R, 1, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 4: fft_stage_p2<T, R, 2, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 8: fft_stage_p2<T, R, 3, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 16: fft_stage_p2<T, R, 4, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 32: fft_stage_p2<T, R, 5, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 64: fft_stage_p2<T, R, 6, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 128: fft_stage_p2<T, R, 7, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 256: fft_stage_p2<T, R, 8, C, DIT>(s, tw, N, tid, nthr); return true;
+    default: return false;
+  }
+}
+
 template <typename T, int C, bool DIT>
 __device__ __forceinline__ void fft_stage_dispatch(int r, cx2<T>* s, const cx2<T>* tw, int N, int L, int tid, int nthr) {
+#ifndef FFT_NO_P2
+  // factorize() puts the odd radices first, so every power-of-two stage has a power-of-two stride:
+  // radix 16 with M = 2^r 16^j, and one final stage (radix 2..16) with M = 1
+  if (r == 16) {
+    if (fft_stage_p2_dispatch<T, 16, C, DIT>(s, tw, N, L >> 4, tid, nthr)) return;
+  } else if (L == r) {
+    if (r == 8) { fft_stage_p2<T, 8, 0, C, DIT>(s, tw, N, tid, nthr); return; }
+    if (r == 4) { fft_stage_p2<T, 4, 0, C, DIT>(s, tw, N, tid, nthr); return; }
+    if (r == 2) { fft_stage_p2<T, 2, 0, C, DIT>(s, tw, N, tid, nthr); return; }
+  }
+#endif
   switch (r) {
     case 16: fft_stage<T, 16, C, DIT>(s, tw, N, L, tid, nthr); break;
     case 8: fft_stage<T, 8, C, DIT>(s, tw, N, L, tid, nthr); break;

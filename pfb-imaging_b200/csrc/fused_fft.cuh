@@ -22,6 +22,7 @@ struct FusedTabs {
   const int* rev_u;          // pos -> k
   const int* rev_v;
   const int* pos_v;          // k -> pos (DIT input scatter)
+  const int* pos_u;          // k -> pos along u (drain loops of the column kernels walk k)
   const double* nutab;       // (nx,ny) fp64: n - 1 + nshift per pixel (w-screen phase = w_p * nutab, up to 1e3 turns)
   // cells any bound sample can touch: rows [a_lo, a_lo+a_len) and columns [b_lo, b_lo+b_len), circular
   int a_lo, a_len, b_lo, b_len;
@@ -35,40 +36,147 @@ __device__ __forceinline__ bool in_window(int n, int lo, int len, int size) {
 
 #define ROWS_MAX_THREADS 256
 
+// ---- vector access helpers: the load / store loops of these kernels are latency-bound (ncu: 40-55 % of
+// the stall samples were long-scoreboard waits in the fill / drain loops), so every global access moves
+// 16 bytes and several independent accesses are in flight per thread -------------------------------
+__device__ __forceinline__ void load4(const float* __restrict__ p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const double* __restrict__ p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void load4(const int* __restrict__ p, int (&v)[4]) {
+  const int4 t = *reinterpret_cast<const int4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+// two consecutive complex values (16-byte aligned pair)
+__device__ __forceinline__ void load_pair(const cx2<float>* __restrict__ p, cx2<float>& a, cx2<float>& b) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  a = {t.x, t.y}; b = {t.z, t.w};
+}
+__device__ __forceinline__ void load_pair(const cx2<double>* __restrict__ p, cx2<double>& a, cx2<double>& b) {
+  const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 1);
+  a = {t.x, t.y}; b = {u.x, u.y};
+}
+__device__ __forceinline__ void store_pair(cx2<float>* __restrict__ p, const cx2<float>& a, const cx2<float>& b) {
+  *reinterpret_cast<float4*>(p) = make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store_pair(cx2<double>* __restrict__ p, const cx2<double>& a, const cx2<double>& b) {
+  *reinterpret_cast<double2*>(p) = make_double2(a.x, a.y);
+  *reinterpret_cast<double2*>(p + 1) = make_double2(b.x, b.y);
+}
+// one row of a column block: C complex values = 32 bytes (8 / 16 bytes for the narrow blocks)
+template <typename T, int C>
+__device__ __forceinline__ void load_row(const cx2<T>* __restrict__ p, cx2<T> (&v)[C]) {
+  if constexpr (C >= 2) {
+#pragma unroll
+    for (int c = 0; c < C; c += 2) load_pair(p + c, v[c], v[c + 1]);
+  } else {
+    v[0] = p[0];
+  }
+}
+template <typename T, int C>
+__device__ __forceinline__ void store_row(cx2<T>* __restrict__ p, const cx2<T> (&v)[C]) {
+  if constexpr (C >= 2) {
+#pragma unroll
+    for (int c = 0; c < C; c += 2) store_pair(p + c, v[c], v[c + 1]);
+  } else {
+    p[0] = v[0];
+  }
+}
 
 // --------------------------------------------------------------------------- degrid direction
+// grid = (plane, image row), plane fastest: the CTAs sharing an image row (x, corr, nu table) are
+// co-resident, so those rows are read from DRAM once instead of once per plane.
 template <typename T>
 __global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 1))
 k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict__ beam, const T* __restrict__ corr,
            typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x, i = blockIdx.x, q = blockIdx.y;
+  const int tid = threadIdx.x, nthr = blockDim.x, q = blockIdx.x, i = blockIdx.y;
   const int nv = p.nv, hy = p.ny / 2;
   const int ip = i - p.nx / 2;
   const int a = ip < 0 ? ip + p.nu : ip;
   for (int n = tid; n < nv; n += nthr) s[fft_pad<T>(n)] = {(T)0, (T)0};
   __syncthreads();
   const double wq = p.w0 + q * p.dw;
-  for (int j = tid; j < p.ny; j += nthr) {
-    const int64_t pix = (int64_t)i * p.ny + j;
-    T val = x[pix] * corr[pix];
-    if (beam) val *= beam[pix];
-    cx2<T> v = {val, (T)0};
-    if (p.do_wgridding && val != (T)0) {
-      T c, sn;
-      cis_turns(wq * ft.nutab[pix], c, sn);
-      v = {val * c, val * sn};
+  const int64_t row = (int64_t)i * p.ny;
+  const bool vec_ok = (p.ny & 7) == 0 &&
+                      (((uintptr_t)x | (uintptr_t)corr | (uintptr_t)beam) & 15) == 0;  // caller-owned device pointers
+  if (vec_ok) {
+    // 4 consecutive pixels per step (hy % 4 == 0, so a group never straddles the wrap), two steps in flight
+    const int ng = p.ny >> 2;
+    for (int g0 = tid; g0 < ng; g0 += 2 * nthr) {
+      T xv[2][4], cv[2][4], bv[2][4];
+      double nuv[2][4];
+      int pv[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g0 + u * nthr;
+        if (g < ng) {
+          const int j = 4 * g;
+          load4(x + row + j, xv[u]);
+          load4(corr + row + j, cv[u]);
+          if (beam) load4(beam + row + j, bv[u]);
+          if (p.do_wgridding) load4(ft.nutab + row + j, nuv[u]);
+          const int jp = j - hy;
+          load4(ft.pos_v + (jp < 0 ? jp + nv : jp), pv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (g0 + u * nthr < ng) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            T val = xv[u][e] * cv[u][e];
+            if (beam) val *= bv[u][e];
+            cx2<T> v = {val, (T)0};
+            if (p.do_wgridding && val != (T)0) {
+              T c, sn;
+              cis_turns(wq * nuv[u][e], c, sn);
+              v = {val * c, val * sn};
+            }
+            s[fft_pad<T>(pv[u][e])] = v;
+          }
+        }
+      }
     }
-    const int jp = j - hy;
-    s[fft_pad<T>(ft.pos_v[jp < 0 ? jp + nv : jp])] = v;
+  } else {
+    for (int j = tid; j < p.ny; j += nthr) {
+      const int64_t pix = row + j;
+      T val = x[pix] * corr[pix];
+      if (beam) val *= beam[pix];
+      cx2<T> v = {val, (T)0};
+      if (p.do_wgridding && val != (T)0) {
+        T c, sn;
+        cis_turns(wq * ft.nutab[pix], c, sn);
+        v = {val * c, val * sn};
+      }
+      const int jp = j - hy;
+      s[fft_pad<T>(ft.pos_v[jp < 0 ? jp + nv : jp])] = v;
+    }
   }
   __syncthreads();
   fft_dit<T, 1>(s, (const cx2<T>*)ft.tw_v, ft.dv, tid, nthr);
+  // only the active columns are written (window bounds are multiples of 32)
   cx2<T>* dst = reinterpret_cast<cx2<T>*>(grid) + ((int64_t)q * p.nu + a) * nv;
-  for (int n = tid; n < nv; n += nthr)
-    if (in_window(n, ft.b_lo, ft.b_len, nv)) dst[n] = s[fft_pad<T>(n)];
+  const int npair = ft.b_len >> 1;
+#pragma unroll 4
+  for (int r = tid; r < npair; r += nthr) {
+    int n = ft.b_lo + 2 * r;
+    if (n >= nv) n -= nv;
+    store_pair(dst + n, s[fft_pad<T>(n)], s[fft_pad<T>(n + 1)]);
+  }
 }
+
+// Column kernels: a CTA owns a block of C columns (one 32-byte sector per grid row).  Element w of the
+// block maps to (row w / C, column w % C): consecutive lanes touch consecutive shared-memory words (no
+// bank conflicts) and the 4 (2) lanes of a row share one global sector.  COLS_U independent global
+// accesses are kept in flight per thread: with one CTA per SM nothing else hides the L2 / DRAM latency.
+#define COLS_U 8
 
 // column block of C columns starting at b0; rows of the image band only are read
 template <typename T, int C>
@@ -76,21 +184,58 @@ __global__ void __launch_bounds__(512)
 k_cols_fwd(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
+  constexpr int LGC = C == 1 ? 0 : (C == 2 ? 1 : 2);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int b0 = (ft.b_lo + blockIdx.x * C) % p.nv, q = blockIdx.y;
-  const int nu = p.nu, hx = p.nx / 2;
+  const int nu = p.nu, nx = p.nx, hx = p.nx / 2;
   cx2<T>* g = reinterpret_cast<cx2<T>*>(grid) + (int64_t)q * nu * p.nv + b0;
-  for (int w = tid; w < nu * C; w += nthr) {
-    const int a = w / C, c = w - a * C;
-    const bool band = a < hx || a >= nu - hx;
-    s[fft_pad<T>(w)] = band ? g[(int64_t)a * p.nv + c] : cx2<T>{(T)0, (T)0};
+  for (int w = tid; w < (nu - nx) * C; w += nthr) s[fft_pad<T>(hx * C + w)] = {(T)0, (T)0};
+  const int nin = nx * C;
+  for (int w0 = tid; w0 < nin; w0 += COLS_U * nthr) {
+    cx2<T> v[COLS_U];
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nin) {
+        const int r = w >> LGC, c = w & (C - 1);
+        const int a = r < hx ? r : r + (nu - nx);
+        v[u] = g[(int64_t)a * p.nv + c];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nin) {
+        const int r = w >> LGC, c = w & (C - 1);
+        const int a = r < hx ? r : r + (nu - nx);
+        s[fft_pad<T>(a * C + c)] = v[u];
+      }
+    }
   }
   __syncthreads();
   fft_dif<T, C>(s, (const cx2<T>*)ft.tw_u, ft.du, tid, nthr);
-  for (int w = tid; w < nu * C; w += nthr) {
-    const int pos = w / C, c = w - pos * C;
-    const int k = ft.rev_u[pos];
-    if (in_window(k, ft.a_lo, ft.a_len, nu)) g[(int64_t)k * p.nv + c] = s[fft_pad<T>(w)];
+  const int nout = ft.a_len * C;
+  for (int w0 = tid; w0 < nout; w0 += COLS_U * nthr) {
+    int pos[COLS_U];
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nout) {
+        int k = ft.a_lo + (w >> LGC);
+        if (k >= nu) k -= nu;
+        pos[u] = ft.pos_u[k];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nout) {
+        const int c = w & (C - 1);
+        int k = ft.a_lo + (w >> LGC);
+        if (k >= nu) k -= nu;
+        g[(int64_t)k * p.nv + c] = s[fft_pad<T>(pos[u] * C + c)];
+      }
+    }
   }
 }
 
@@ -100,28 +245,62 @@ __global__ void __launch_bounds__(512)
 k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
+  constexpr int LGC = C == 1 ? 0 : (C == 2 ? 1 : 2);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int b0 = (ft.b_lo + blockIdx.x * C) % p.nv, q = blockIdx.y;
-  const int nu = p.nu, hx = p.nx / 2;
+  const int nu = p.nu, nx = p.nx, hx = p.nx / 2;
   cx2<T>* g = reinterpret_cast<cx2<T>*>(grid) + (int64_t)q * nu * p.nv + b0;
-  for (int w = tid; w < nu * C; w += nthr) {
-    const int a = w / C, c = w - a * C;
-    cx2<T> v = {(T)0, (T)0};
-    if (in_window(a, ft.a_lo, ft.a_len, nu)) {  // rows outside the window are known to be zero
-      v = g[(int64_t)a * p.nv + c];
-      v.y = -v.y;  // inverse = conj o forward o conj
+  // rows outside the active window are known to be zero
+  for (int w = tid; w < (nu - ft.a_len) * C; w += nthr) {
+    int k = ft.a_lo + ft.a_len + (w >> LGC);
+    if (k >= nu) k -= nu;
+    s[fft_pad<T>(k * C + (w & (C - 1)))] = {(T)0, (T)0};
+  }
+  const int nin = ft.a_len * C;
+  for (int w0 = tid; w0 < nin; w0 += COLS_U * nthr) {
+    cx2<T> v[COLS_U];
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nin) {
+        int k = ft.a_lo + (w >> LGC);
+        if (k >= nu) k -= nu;
+        v[u] = g[(int64_t)k * p.nv + (w & (C - 1))];
+      }
     }
-    s[fft_pad<T>(w)] = v;
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nin) {
+        int k = ft.a_lo + (w >> LGC);
+        if (k >= nu) k -= nu;
+        s[fft_pad<T>(k * C + (w & (C - 1)))] = {v[u].x, -v[u].y};  // inverse = conj o forward o conj
+      }
+    }
   }
   __syncthreads();
   fft_dif<T, C>(s, (const cx2<T>*)ft.tw_u, ft.du, tid, nthr);
-  for (int w = tid; w < nu * C; w += nthr) {
-    const int pos = w / C, c = w - pos * C;
-    const int k = ft.rev_u[pos];
-    if (k < hx || k >= nu - hx) {
-      cx2<T> v = s[fft_pad<T>(w)];
-      v.y = -v.y;
-      g[(int64_t)k * p.nv + c] = v;
+  const int nout = nx * C;
+  for (int w0 = tid; w0 < nout; w0 += COLS_U * nthr) {
+    int pos[COLS_U];
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nout) {
+        const int r = w >> LGC;
+        pos[u] = ft.pos_u[r < hx ? r : r + (nu - nx)];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < COLS_U; ++u) {
+      const int w = w0 + u * nthr;
+      if (w < nout) {
+        const int r = w >> LGC, c = w & (C - 1);
+        const int k = r < hx ? r : r + (nu - nx);
+        cx2<T> v = s[fft_pad<T>(pos[u] * C + c)];
+        v.y = -v.y;
+        g[(int64_t)k * p.nv + c] = v;
+      }
     }
   }
 }
@@ -139,27 +318,75 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
   const int ip = i - p.nx / 2;
   const int a = ip < 0 ? ip + p.nu : ip;
   const cx2<T>* src = reinterpret_cast<const cx2<T>*>(grid) + ((int64_t)q * p.nu + a) * nv;
-  for (int n = tid; n < nv; n += nthr) {
-    cx2<T> v = {(T)0, (T)0};  // columns outside the window are known to be zero
-    if (in_window(n, ft.b_lo, ft.b_len, nv)) { v = src[n]; v.y = -v.y; }
-    s[fft_pad<T>(n)] = v;
+  // columns outside the window are known to be zero
+  for (int r = tid; r < nv - ft.b_len; r += nthr) {
+    int n = ft.b_lo + ft.b_len + r;
+    if (n >= nv) n -= nv;
+    s[fft_pad<T>(n)] = {(T)0, (T)0};
+  }
+  const int npair = ft.b_len >> 1;
+#pragma unroll 4
+  for (int r = tid; r < npair; r += nthr) {
+    int n = ft.b_lo + 2 * r;
+    if (n >= nv) n -= nv;
+    cx2<T> v0, v1;
+    load_pair(src + n, v0, v1);
+    s[fft_pad<T>(n)] = {v0.x, -v0.y};
+    s[fft_pad<T>(n + 1)] = {v1.x, -v1.y};
   }
   __syncthreads();
   fft_dif<T, 1>(s, (const cx2<T>*)ft.tw_v, ft.dv, tid, nthr);
   const double wq = p.w0 + q * p.dw;
-  double* dst = accimg + (int64_t)i * p.ny;
-  for (int j = tid; j < p.ny; j += nthr) {
-    const int jp = j - hy;
-    const cx2<T> v = s[fft_pad<T>(ft.pos_v[jp < 0 ? jp + nv : jp])];  // conj(v) is the inverse transform
-    double r;
-    if (p.do_wgridding) {
-      T c, sn;
-      cis_turns(wq * ft.nutab[(int64_t)i * p.ny + j], c, sn);
-      r = (double)(v.x * c - v.y * sn);  // Re( conj(v) e^{-i theta} )
-    } else {
-      r = (double)v.x;
+  const int64_t row = (int64_t)i * p.ny;
+  double* dst = accimg + row;
+  if ((p.ny & 7) == 0) {
+    const int ng = p.ny >> 2;
+    for (int g0 = tid; g0 < ng; g0 += 2 * nthr) {
+      double nuv[2][4];
+      int pv[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g0 + u * nthr;
+        if (g < ng) {
+          const int j = 4 * g, jp = j - hy;
+          if (p.do_wgridding) load4(ft.nutab + row + j, nuv[u]);
+          load4(ft.pos_v + (jp < 0 ? jp + nv : jp), pv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g0 + u * nthr;
+        if (g < ng) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const cx2<T> v = s[fft_pad<T>(pv[u][e])];  // conj(v) is the inverse transform
+            double r;
+            if (p.do_wgridding) {
+              T c, sn;
+              cis_turns(wq * nuv[u][e], c, sn);
+              r = (double)(v.x * c - v.y * sn);  // Re( conj(v) e^{-i theta} )
+            } else {
+              r = (double)v.x;
+            }
+            atomicAdd(dst + 4 * g + e, r);
+          }
+        }
+      }
     }
-    atomicAdd(dst + j, r);
+  } else {
+    for (int j = tid; j < p.ny; j += nthr) {
+      const int jp = j - hy;
+      const cx2<T> v = s[fft_pad<T>(ft.pos_v[jp < 0 ? jp + nv : jp])];
+      double r;
+      if (p.do_wgridding) {
+        T c, sn;
+        cis_turns(wq * ft.nutab[row + j], c, sn);
+        r = (double)(v.x * c - v.y * sn);
+      } else {
+        r = (double)v.x;
+      }
+      atomicAdd(dst + j, r);
+    }
   }
 }
 

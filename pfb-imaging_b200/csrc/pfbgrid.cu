@@ -100,7 +100,7 @@ struct pfbg_plan {
   cudaEvent_t stage_ev[16]{};
   bool stage_ev_ok = false;
   // fused FFT path (fused_fft.cuh)
-  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, cellflags, accimg, nutab;
+  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, pos_u, cellflags, accimg, nutab;
   FusedTabs ftabs{};
   bool fused = false;          // tables built and sizes fit shared memory
   int col_c = 4;               // columns per CTA in the column passes
@@ -153,7 +153,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx, &pl->srt_ka, &pl->srt_kb, &pl->srt_va, &pl->srt_vb, &pl->srt_tmp,
-                   &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->cellflags, &pl->accimg, &pl->nutab, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
+                   &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->pos_u, &pl->cellflags, &pl->accimg, &pl->nutab, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
   if (pl->ev_ok)
@@ -338,6 +338,8 @@ static int fused_setup_t(pfbg_plan* pl) {
   digit_tables(du, rev, pos);
   CKRC(dev_alloc(pl, pl->rev_u, (size_t)g.nu * 4));
   CK(cudaMemcpy(pl->rev_u.p, rev.data(), (size_t)g.nu * 4, cudaMemcpyHostToDevice));
+  CKRC(dev_alloc(pl, pl->pos_u, (size_t)g.nu * 4));
+  CK(cudaMemcpy(pl->pos_u.p, pos.data(), (size_t)g.nu * 4, cudaMemcpyHostToDevice));
   digit_tables(dv, rev, pos);
   CKRC(dev_alloc(pl, pl->rev_v, (size_t)g.nv * 4));
   CKRC(dev_alloc(pl, pl->pos_v, (size_t)g.nv * 4));
@@ -346,7 +348,7 @@ static int fused_setup_t(pfbg_plan* pl) {
   FusedTabs& ft = pl->ftabs;
   ft.du = du; ft.dv = dv;
   ft.tw_u = pl->tw_u.p; ft.tw_v = pl->tw_v.p;
-  ft.rev_u = (const int*)pl->rev_u.p; ft.rev_v = (const int*)pl->rev_v.p; ft.pos_v = (const int*)pl->pos_v.p;
+  ft.rev_u = (const int*)pl->rev_u.p; ft.rev_v = (const int*)pl->rev_v.p; ft.pos_v = (const int*)pl->pos_v.p; ft.pos_u = (const int*)pl->pos_u.p;
   ft.a_lo = 0; ft.a_len = g.nu; ft.b_lo = 0; ft.b_len = g.nv;
   // opt in to large dynamic shared memory
   CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -891,7 +893,7 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
   const int CC = pl->col_c;
   const GParams& g = pl->gp;
   const FusedTabs& ft = pl->ftabs;
-  k_rows_fwd<T><<<dim3(g.nx, g.nplanes), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+  k_rows_fwd<T><<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
       g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
