@@ -114,6 +114,34 @@ __device__ __forceinline__ double pixel_nm1(const GParams& p, int i, int j) {
   return -r2 / (sqrt(1.0 - r2) + 1.0);
 }
 
+// Packed complex helpers.  sm_100 has two-wide fp32 FMA/MUL (FFMA2 / FMUL2, scalar second operand
+// broadcast): same flop rate as FFMA but half the issue slots, which is what bounds the run kernels.
+__device__ __forceinline__ float2 cfma_s(float2 a, float s, float2 c) {  // a * s + c
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 cmul_s(float2 a, float s) {  // a * s
+  float2 d;
+  asm("{ .reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %4};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd; }"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(s));
+  return d;
+}
+__device__ __forceinline__ double2 cfma_s(double2 a, double s, double2 c) { return make_double2(a.x * s + c.x, a.y * s + c.y); }
+__device__ __forceinline__ double2 cmul_s(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+
 __device__ __forceinline__ void atomic_add_c(float2* a, float re, float im) {
   atomicAdd(a, make_float2(re, im));  // sm_90+: one vector RED
 }

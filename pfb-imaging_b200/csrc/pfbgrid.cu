@@ -323,11 +323,17 @@ static int fused_setup_t(pfbg_plan* pl) {
   // columns per CTA in the column passes: a full 32-byte sector per row if that fits shared memory,
   // otherwise narrower blocks (half / quarter sectors; L2 merges the neighbours) for large grids
   pl->col_c = (int)(32 / sizeof(C));
+  const int full_c = pl->col_c;
+  if (const char* cc = getenv("PFBG_COLC")) {  // tuning hook: narrower blocks -> more resident CTAs per SM
+    const int v = atoi(cc);
+    if (v == 1 || v == 2 || v == 4) pl->col_c = v < full_c ? v : full_c;
+  }
+  const int want_c = pl->col_c;
   while (pl->col_c > 1 && fft_smem_bytes<T>(g.nu * pl->col_c) > kMaxSmem) pl->col_c /= 2;
   // measured on B200 (15360^2 x 63 planes): with narrower-than-sector column blocks and one row CTA
   // per SM the fused kernels lose to cuFFT (710 ms vs 520 ms per apply), so large grids stay on cuFFT
   // unless PFBG_FFT=fused asks for them
-  if (pl->col_c != (int)(32 / sizeof(C)) && !(env && strcmp(env, "fused") == 0)) return PFBG_OK;
+  if (pl->col_c != want_c && !(env && strcmp(env, "fused") == 0)) return PFBG_OK;
   if (fft_smem_bytes<T>(g.nv) > kMaxSmem) return PFBG_OK;
   if (fft_smem_bytes<T>(g.nu * pl->col_c) > kMaxSmem) return PFBG_OK;
   FftDesc du, dv;

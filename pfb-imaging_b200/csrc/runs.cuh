@@ -89,6 +89,7 @@ template <> struct RunCfg<float> { static constexpr int NB = 32; };
 template <> struct RunCfg<double> { static constexpr int NB = 16; };
 
 // evaluate the 24 taps of the nb staged samples: lane t < 24 owns tap t (axis = t/8, k = t%8)
+// (fp64 path; the fp32 kernels evaluate all 24 taps of a sample in its own lane, see run_taps_lane)
 template <typename T, int NB>
 __device__ __forceinline__ void run_taps(const GParams& p, const T (*x0s)[4], T (*taps)[24], int nb, int lane,
                                          T bscale, T xs) {
@@ -105,9 +106,37 @@ __device__ __forceinline__ void run_taps(const GParams& p, const T (*x0s)[4], T 
   }
 }
 
+// lane <-> sample: all 24 taps of this lane's sample, written as six 16-byte stores.  Every lane is
+// busy and there is no loop over the batch, which halves the cost of the tap stage (ncu: the
+// lane <-> tap version was 26 % of the gridding kernel's stall samples).
+template <typename T>
+__device__ __forceinline__ void run_taps_lane(const GParams& p, const T (&x0)[3], T* __restrict__ dst, T bscale, T xs) {
+#pragma unroll
+  for (int axis = 0; axis < 3; ++axis) {
+    T t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = es_fast((x0[axis] + (T)k) * xs, bscale);
+    if (axis == 2 && !p.do_wgridding) {
+      t[0] = (T)1;
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t[k] = (T)0;
+    }
+    if constexpr (sizeof(T) == 4) {
+      float4* d4 = reinterpret_cast<float4*>(dst + axis * 8);
+      d4[0] = make_float4(t[0], t[1], t[2], t[3]);
+      d4[1] = make_float4(t[4], t[5], t[6], t[7]);
+    } else {
+      double2* d2 = reinterpret_cast<double2*>(dst + axis * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d2[k] = make_double2(t[2 * k], t[2 * k + 1]);
+    }
+  }
+}
+
+// general flush (any W <= 8, footprints that wrap around the grid edge)
 template <typename T>
 __device__ __forceinline__ void run_flush(const GParams& p, typename cplx_of<T>::type* __restrict__ grid,
-                                          T (&accr)[8][2], T (&acci)[8][2], uint64_t origin, int j, int q2) {
+                                          typename cplx_of<T>::type (&acc)[8][2], uint64_t origin, int j, int q2) {
   const int W = p.W, npl = p.do_wgridding ? W : 1;
   int iv = (int)(origin & 0xffffu) + j;
   int iu0 = (int)((origin >> 16) & 0xffffu);
@@ -115,6 +144,22 @@ __device__ __forceinline__ void run_flush(const GParams& p, typename cplx_of<T>:
   if (iv >= p.nv) iv -= p.nv;
   const int plane_sz = p.nu * p.nv;  // < 2^31 (nu, nv <= 32768 enforced by the host)
   const bool jok = j < W;
+  if (W == 8 && npl == 8 && iu0 + 8 <= p.nu) {
+    // common case: every lane owns live cells and the 8 rows do not wrap -> one pointer, constant stride
+    typename cplx_of<T>::type* g = grid + (int64_t)(ip + q2) * plane_sz + (int64_t)iu0 * p.nv + iv;
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq) {
+      typename cplx_of<T>::type* gq = g + (int64_t)(4 * qq) * plane_sz;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomic_add_c(gq, acc[i][qq].x, acc[i][qq].y);
+        gq += p.nv;
+        acc[i][qq].x = 0;
+        acc[i][qq].y = 0;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int qq = 0; qq < 2; ++qq) {
     int q = q2 + 4 * qq;
@@ -125,12 +170,67 @@ __device__ __forceinline__ void run_flush(const GParams& p, typename cplx_of<T>:
       if (ok && i < W) {
         int iu = iu0 + i;
         if (iu >= p.nu) iu -= p.nu;
-        atomic_add_c(gq + iu * p.nv, accr[i][qq], acci[i][qq]);
+        atomic_add_c(gq + iu * p.nv, acc[i][qq].x, acc[i][qq].y);
       }
-      accr[i][qq] = 0;
-      acci[i][qq] = 0;
+      acc[i][qq].x = 0;
+      acc[i][qq].y = 0;
     }
   }
+}
+
+// the run's footprint -> registers (degridding), same two paths
+template <typename T>
+__device__ __forceinline__ void run_fetch(const GParams& p, const typename cplx_of<T>::type* __restrict__ grid,
+                                          typename cplx_of<T>::type (&gv)[8][2], uint64_t origin, int j, int q2) {
+  using C = typename cplx_of<T>::type;
+  const int W = p.W, npl = p.do_wgridding ? W : 1;
+  int iv = (int)(origin & 0xffffu) + j;
+  int iu0 = (int)((origin >> 16) & 0xffffu);
+  int ip = (int)(origin >> 32);
+  if (iv >= p.nv) iv -= p.nv;
+  const int plane_sz = p.nu * p.nv;
+  const bool jok = j < W;
+  if (W == 8 && npl == 8 && iu0 + 8 <= p.nu) {
+    const C* g = grid + (int64_t)(ip + q2) * plane_sz + (int64_t)iu0 * p.nv + iv;
+#pragma unroll
+    for (int qq = 0; qq < 2; ++qq) {
+      const C* gq = g + (int64_t)(4 * qq) * plane_sz;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        gv[i][qq] = *gq;
+        gq += p.nv;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int qq = 0; qq < 2; ++qq) {
+    int q = q2 + 4 * qq;
+    bool ok = jok && q < npl;
+    const C* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      C val; val.x = 0; val.y = 0;
+      if (ok && i < W) {
+        int iu = iu0 + i;
+        if (iu >= p.nu) iu -= p.nu;
+        val = gq[iu * p.nv];
+      }
+      gv[i][qq] = val;
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t x, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)x, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(x >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// run boundaries of a staged batch as a bit mask: bit v set <=> sample v starts a new run
+__device__ __forceinline__ uint32_t run_starts(uint64_t org, uint64_t cur, int lane, int nb) {
+  uint64_t prev = shfl_u64(org, lane > 0 ? lane - 1 : 0);
+  if (lane == 0) prev = cur;
+  return __ballot_sync(0xffffffffu, lane < nb && org != prev);
 }
 
 // ---------------------------------------------------------------------------
@@ -145,25 +245,28 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
   using C = typename cplx_of<T>::type;
   constexpr int NB = RunCfg<T>::NB;
   __shared__ __align__(16) T taps[RUN_WARPS][NB][24];
-  __shared__ __align__(16) T x0s[RUN_WARPS][NB][4];
+  __shared__ __align__(16) T x0s[RUN_WARPS][sizeof(T) == 8 ? NB : 1][4];  // fp64 keeps the lane <-> tap stage
   __shared__ C amp[RUN_WARPS][NB];
-  __shared__ uint64_t orgs[RUN_WARPS][NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = lane & 7, q2 = lane >> 3;
   const T bscale = es_scale((T)p.beta), xs = (T)(2.0 / p.W);
-  T accr[8][2], acci[8][2];
+  C acc[8][2];  // (re, im) pairs: one packed FMA per cell and sample
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { accr[i][0] = accr[i][1] = 0; acci[i][0] = acci[i][1] = 0; }
+  for (int i = 0; i < 8; ++i) { acc[i][0].x = acc[i][0].y = 0; acc[i][1].x = acc[i][1].y = 0; }
   uint64_t cur = ~0ull;
   const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
   const int64_t nwarps = (int64_t)gridDim.x * RUN_WARPS;
   for (int64_t sl = (int64_t)blockIdx.x * RUN_WARPS + warp; sl < nslice; sl += nwarps) {
     const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+    // records are fetched one batch ahead (their latency hides behind the FMA stage)
+    VisRec<T> rnext;
+    if (sl * RUN_SLICE + lane < kend && lane < NB) rnext = recs[sl * RUN_SLICE + lane];
     for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
       const int nb = (int)min((int64_t)NB, kend - k0);
+      const VisRec<T> r = rnext;
+      uint64_t org = ~0ull;
       if (lane < nb) {  // (a) lane <-> sample
         const int64_t k = k0 + lane;
-        VisRec<T> r = recs[k];
         C a;
         if (vis_sorted) a = vis[k];
         else {
@@ -171,41 +274,55 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
           int chan = (int)(r.idx - row * p.nchan);
           a = vis[row * vis_rs + chan * vis_cs];
         }
-        T w = wgt ? wgt[r.idx] : (T)1;
+        const T w = wgt ? wgt[r.idx] : (T)1;
+        if (k + NB < kend) rnext = recs[k + NB];
+        if constexpr (sizeof(T) == 4) {
+          const T x0[3] = {r.x0[0], r.x0[1], r.x0[2]};
+          run_taps_lane<T>(p, x0, &taps[warp][lane][0], bscale, xs);  // independent of the loads above
+        } else {
+          x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
+        }
         T pc = apply_phase ? r.pc : (T)1, ps = apply_phase ? r.ps : (T)0;
         if (apply_phase && (r.ip & REC_CONJ_BIT)) a.y = -a.y;  // folded sample (the Hessian path stays folded)
-        C s;
-        s.x = (a.x * pc - a.y * ps) * w;
-        s.y = (a.x * ps + a.y * pc) * w;
-        amp[warp][lane] = s;
-        x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
-        orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
+        C sa;
+        sa.x = (a.x * pc - a.y * ps) * w;
+        sa.y = (a.x * ps + a.y * pc) * w;
+        amp[warp][lane] = sa;
+        org = pack_origin(r.iu, r.iv, r.ip);
       }
+      const uint32_t starts = run_starts(org, cur, lane, nb);
       __syncwarp();
-      run_taps<T, NB>(p, x0s[warp], taps[warp], nb, lane, bscale, xs);  // (b) lane <-> tap
-      __syncwarp();
-      for (int v = 0; v < nb; ++v) {  // (c) lane <-> footprint cell
-        const uint64_t org = orgs[warp][v];
-        if (org != cur) {
-          if (cur != ~0ull) run_flush<T>(p, grid, accr, acci, cur, j, q2);
-          cur = org;
+      if constexpr (sizeof(T) == 8) {
+        run_taps<T, NB>(p, x0s[warp], taps[warp], nb, lane, bscale, xs);
+        __syncwarp();
+      }
+      int v = 0;
+      while (v < nb) {  // (c) lane <-> footprint cell, one run segment at a time
+        if ((starts >> v) & 1u) {
+          if (cur != ~0ull) run_flush<T>(p, grid, acc, cur, j, q2);
+          cur = shfl_u64(org, v);
         }
-        const T* tp = taps[warp][v];
-        const T tv = tp[8 + j];
-        const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
-        const C a = amp[warp][v];
-        const T r0 = a.x * c0, i0 = a.y * c0, r1 = a.x * c1, i1 = a.y * c1;
+        const uint32_t rest = v < 31 ? (starts & (0xffffffffu << (v + 1))) : 0u;
+        const int vend = rest ? min(__ffs(rest) - 1, nb) : nb;
+#pragma unroll 2
+        for (; v < vend; ++v) {
+          const T* tp = taps[warp][v];
+          const T tv = tp[8 + j];
+          const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
+          const C a = amp[warp][v];
+          const C a0 = cmul_s(a, c0), a1 = cmul_s(a, c1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const T u = tp[i];
-          accr[i][0] += r0 * u; acci[i][0] += i0 * u;
-          accr[i][1] += r1 * u; acci[i][1] += i1 * u;
+          for (int i = 0; i < 8; ++i) {
+            const T u = tp[i];
+            acc[i][0] = cfma_s(a0, u, acc[i][0]);
+            acc[i][1] = cfma_s(a1, u, acc[i][1]);
+          }
         }
       }
       __syncwarp();
     }
   }
-  if (cur != ~0ull) run_flush<T>(p, grid, accr, acci, cur, j, q2);
+  if (cur != ~0ull) run_flush<T>(p, grid, acc, cur, j, q2);
 }
 
 // ---------------------------------------------------------------------------
@@ -220,89 +337,78 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
   using C = typename cplx_of<T>::type;
   constexpr int NB = RunCfg<T>::NB;
   __shared__ __align__(16) T taps[DEG_WARPS][NB][24];
-  __shared__ __align__(16) T x0s[DEG_WARPS][NB][4];
-  __shared__ uint64_t orgs[DEG_WARPS][NB];
+  __shared__ __align__(16) T x0s[DEG_WARPS][sizeof(T) == 8 ? NB : 1][4];
   __shared__ C part[DEG_WARPS][NB][32];  // per-sample partial sums of the 32 lanes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = lane & 7, q2 = lane >> 3;
-  const int W = p.W, npl = p.do_wgridding ? W : 1;
   const T bscale = es_scale((T)p.beta), xs = (T)(2.0 / p.W);
-  const int plane_sz = p.nu * p.nv;
-  T gr[8][2], gi[8][2];
+  C gv[8][2];  // the run's footprint as (re, im) pairs
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { gr[i][0] = gr[i][1] = 0; gi[i][0] = gi[i][1] = 0; }
+  for (int i = 0; i < 8; ++i) { gv[i][0].x = gv[i][0].y = 0; gv[i][1].x = gv[i][1].y = 0; }
   uint64_t cur = ~0ull;
   const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
   const int64_t nwarps = (int64_t)gridDim.x * DEG_WARPS;
   for (int64_t sl = (int64_t)blockIdx.x * DEG_WARPS + warp; sl < nslice; sl += nwarps) {
     const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+    VisRec<T> rnext;
+    if (sl * RUN_SLICE + lane < kend && lane < NB) rnext = recs[sl * RUN_SLICE + lane];
     for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
       const int nb = (int)min((int64_t)NB, kend - k0);
-      VisRec<T> r;
+      const VisRec<T> r = rnext;
+      uint64_t org = ~0ull;
+      T w = (T)1;
       if (lane < nb) {
-        r = recs[k0 + lane];
-        x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
-        orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
+        if (wgt) w = wgt[r.idx];  // consumed after the gather stage
+        if (k0 + lane + NB < kend) rnext = recs[k0 + lane + NB];
+        if constexpr (sizeof(T) == 4) {
+          const T x0[3] = {r.x0[0], r.x0[1], r.x0[2]};
+          run_taps_lane<T>(p, x0, &taps[warp][lane][0], bscale, xs);
+        } else {
+          x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
+        }
+        org = pack_origin(r.iu, r.iv, r.ip);
       }
+      const uint32_t starts = run_starts(org, cur, lane, nb);
       __syncwarp();
-      run_taps<T, NB>(p, x0s[warp], taps[warp], nb, lane, bscale, xs);
-      __syncwarp();
-      for (int v = 0; v < nb; ++v) {
-        const uint64_t org = orgs[warp][v];
-        if (org != cur) {  // new run: fetch its footprint once
-          cur = org;
-          int iv = (int)(org & 0xffffu) + j;
-          int iu0 = (int)((org >> 16) & 0xffffu);
-          int ip = (int)(org >> 32);
-          if (iv >= p.nv) iv -= p.nv;
-          const bool jok = j < W;
+      if constexpr (sizeof(T) == 8) {
+        run_taps<T, NB>(p, x0s[warp], taps[warp], nb, lane, bscale, xs);
+        __syncwarp();
+      }
+      int v = 0;
+      while (v < nb) {
+        if ((starts >> v) & 1u) {  // new run: fetch its footprint once
+          cur = shfl_u64(org, v);
+          run_fetch<T>(p, grid, gv, cur, j, q2);
+        }
+        const uint32_t rest = v < 31 ? (starts & (0xffffffffu << (v + 1))) : 0u;
+        const int vend = rest ? min(__ffs(rest) - 1, nb) : nb;
+#pragma unroll 2
+        for (; v < vend; ++v) {
+          const T* tp = taps[warp][v];
+          C a0 = cmul_s(gv[0][0], tp[0]), a1 = cmul_s(gv[0][1], tp[0]);
 #pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {
-            int q = q2 + 4 * qq;
-            bool ok = jok && q < npl;
-            const C* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              C val; val.x = 0; val.y = 0;
-              if (ok && i < W) {
-                int iu = iu0 + i;
-                if (iu >= p.nu) iu -= p.nu;
-                val = gq[iu * p.nv];
-              }
-              gr[i][qq] = val.x; gi[i][qq] = val.y;
-            }
+          for (int i = 1; i < 8; ++i) {
+            const T u = tp[i];
+            a0 = cfma_s(gv[i][0], u, a0);
+            a1 = cfma_s(gv[i][1], u, a1);
           }
+          const T tv = tp[8 + j];
+          const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
+          part[warp][v][lane] = cfma_s(a1, c1, cmul_s(a0, c0));
         }
-        const T* tp = taps[warp][v];
-        T a0r = 0, a0i = 0, a1r = 0, a1i = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const T u = tp[i];
-          a0r += gr[i][0] * u; a0i += gi[i][0] * u;
-          a1r += gr[i][1] * u; a1i += gi[i][1] * u;
-        }
-        const T tv = tp[8 + j];
-        const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
-        C s;
-        s.x = a0r * c0 + a1r * c1;
-        s.y = a0i * c0 + a1i * c1;
-        part[warp][v][lane] = s;
       }
       __syncwarp();
       if (lane < nb) {  // lane <-> sample again: skewed (conflict-free) sum over the 32 partials
-        T sr = 0, si = 0;
+        C sum; sum.x = 0; sum.y = 0;
 #pragma unroll 8
-        for (int l = 0; l < 32; ++l) {
-          const C s = part[warp][lane][(lane + l) & 31];
-          sr += s.x; si += s.y;
-        }
-        T re = sr, im = si;
+        for (int l = 0; l < 32; ++l) sum = cfma_s(part[warp][lane][(lane + l) & 31], (T)1, sum);
+        T re = sum.x, im = sum.y;
         if (apply_phase) {  // multiply by e^{-i t}
-          re = sr * r.pc + si * r.ps;
-          im = si * r.pc - sr * r.ps;
+          re = sum.x * r.pc + sum.y * r.ps;
+          im = sum.y * r.pc - sum.x * r.ps;
         }
         if (apply_phase && (r.ip & REC_CONJ_BIT)) im = -im;
-        if (wgt) { T w = wgt[r.idx]; re *= w; im *= w; }
+        re *= w; im *= w;
         C o; o.x = re; o.y = im;
         if (out_sorted) out_sorted[k0 + lane] = o; else vis_out[r.idx] = o;
       }
