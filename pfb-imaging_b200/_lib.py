@@ -79,6 +79,17 @@ SIGNATURES = {
     "pfbg_debug_fft1d": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32]),
     "pfbg_counts_to_weights": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                          _dbl, _dbl, _dbl, _dbl, _dbl, _u32, _vp]),
+    # include/pfbsara.h
+    "pfbs_psi_create": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "pfbs_psi_destroy": (C.c_int, [_vp]),
+    "pfbs_psi_dot": (C.c_int, [_vp, _vp, _vp, _u32, _vp]),
+    "pfbs_psi_hdot": (C.c_int, [_vp, _vp, _vp, _u32, _vp]),
+    "pfbs_dual_update": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _dbl, _i32, _i64, _vp, _i32, _vp]),
+    "pfbs_prox_21m": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _dbl, _i32, _i64, _vp]),
+    "pfbs_extrapolate": (C.c_int, [_i32, _i32, _vp, _vp, _i64, _vp]),
+    "pfbs_primal_step": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _i32, _i32, _i64, _vp]),
+    "pfbs_norm_diff": (C.c_int, [_i32, _i32, _vp, _vp, _i64, C.POINTER(_dbl), _vp]),
 }
 
 _lib = None
@@ -88,12 +99,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``csrc/pfbgrid.cu`` for sm_100a into ``libpfbgrid.so`` (in-tree)."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
     srcs.append(os.path.join(ROOT, "include", "pfbgrid.h"))
+    srcs.append(os.path.join(ROOT, "include", "pfbsara.h"))
     if not force and os.path.exists(LIB_PATH):
         if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, os.path.join(CSRC, "pfbgrid.cu"), "-o", LIB_PATH,
-           "-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    cmd = [nvcc, *NVCC_FLAGS, "--threads", "2", os.path.join(CSRC, "pfbgrid.cu"), os.path.join(CSRC, "pfbsara.cu"),
+           "-o", LIB_PATH, "-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

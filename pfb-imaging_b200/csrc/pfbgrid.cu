@@ -35,6 +35,18 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// used by the other translation units of this library (pfbsara.cu)
+int pfbg_fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+void pfbg_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 #define CK(call)                                                                           \
   do {                                                                                     \
     cudaError_t e_ = (call);                                                               \

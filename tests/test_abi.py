@@ -13,15 +13,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def header_symbols():
-    src = open(os.path.join(ROOT, "include", "pfbgrid.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(pfbg_[a-z_0-9]+)\s*\(", src)))
+    syms = set()
+    for h in ("pfbgrid.h", "pfbsara.h"):  # every header under include/
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms |= set(re.findall(r"\b(pfb[gs]_[a-z_0-9]+)\s*\(", src))
+    return sorted(syms)
 
 
 def test_header_declares_symbols():
     syms = header_symbols()
     assert "pfbg_grid" in syms and "pfbg_degrid" in syms and "pfbg_hessian" in syms and "pfbg_bind_vis" in syms
-    assert len(syms) >= 15
+    assert "pfbs_psi_dot" in syms and "pfbs_dual_update" in syms
+    assert len(syms) >= 24
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["pfbgrid.h", "pfbsara.h"]
 
 
 def test_library_exports_every_declared_symbol():
@@ -66,3 +71,11 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on the GPU-less build container")
+def test_sara_has_no_cpu_fallback():
+    from pfb_imaging_b200.sara import PsiNocopyt
+
+    with pytest.raises(RuntimeError, match="pfbgrid error"):
+        PsiNocopyt(1, 64, 64, ["self", "db1"], 1, 1)
