@@ -56,6 +56,10 @@ int pfbs_dual_update(int32_t precision, int32_t device, const void* vp, void* v,
 /* result = v * max(|sum_band v / sigma| - lam w / sigma, 0) / |sum_band v / sigma| / sigma   (0 where the sum is 0) */
 int pfbs_prox_21m(int32_t precision, int32_t device, const void* v, void* result, const void* weight, double lam,
                   double sigma, int32_t nband, int64_t ncoef, void* stream);
+/* out = a x + b y on device arrays (out may alias x or y): the element-wise steps of the forward-backward loop
+ * (opt/forward_backward.py:84-121) */
+int pfbs_axpby(int32_t precision, int32_t device, void* out, double a, const void* x, double b, const void* y,
+               int64_t n, void* stream);
 /* vp = 2 v - vp */
 int pfbs_extrapolate(int32_t precision, int32_t device, const void* v, void* vp, int64_t n, void* stream);
 /* x = xp - tau * xout, then positivity: 0 none, 1 clamp negatives, 2 zero a pixel in all (local) bands if any band <= 0 */

@@ -145,3 +145,36 @@ def primal_dual(x, v, lam, psi_dot_f, psi_hdot_f, grad, hessnorm, nu, weight, to
             break
         xp, vp = x.copy(), v.copy()
     return x, v, k, eps
+
+
+def forward_backward(x, lam, psi_dot_f, psi_hdot_f, grad, hessnorm, nu, weight, tol, maxit, positivity=0, gamma=1.0,
+                     acceleration=True):
+    """opt/forward_backward.py:84-133 (`ForwardBackward.solve` with the generic tight-frame prox)."""
+    step = 2.0 * gamma / hessnorm
+    x = x.copy()
+    xp, y = x.copy(), x.copy()
+    t, eps, k = 1.0, 1.0, 0
+    for k in range(maxit):
+        x = y - step * grad(y)
+        a = psi_dot_f(x)
+        x = x + psi_hdot_f(prox_21m(a, step * lam, 1.0, weight) - a) / nu
+        if positivity == 1:
+            x[x < 0] = 0.0
+        elif positivity == 2:
+            x[:, np.any(x <= 0, axis=0)] = 0.0
+        eps = np.sqrt(((x - xp) ** 2).sum() / max((x ** 2).sum(), 1e-12)) if x.any() else 1.0
+        if eps < tol:
+            break
+        if acceleration:
+            tp = t
+            t = (1.0 + np.sqrt(1.0 + 4.0 * tp ** 2)) / 2.0
+            y = x + (tp - 1.0) / t * (x - xp)
+        else:
+            y = x.copy()
+        xp = x.copy()
+    return x, k, eps
+
+
+def l1reweight(mcomps_sum, rmsfactor, rms_comps, alpha):
+    """utils/misc.py:750-764 given the band-summed coefficients."""
+    return (1 + rmsfactor) / (1 + np.abs(mcomps_sum) ** alpha / rms_comps[:, None, None] ** alpha)

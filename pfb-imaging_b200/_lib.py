@@ -87,6 +87,7 @@ SIGNATURES = {
     "pfbs_psi_hdot": (C.c_int, [_vp, _vp, _vp, _u32, _vp]),
     "pfbs_dual_update": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _dbl, _i32, _i64, _vp, _i32, _vp]),
     "pfbs_prox_21m": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _dbl, _i32, _i64, _vp]),
+    "pfbs_axpby": (C.c_int, [_i32, _i32, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp]),
     "pfbs_extrapolate": (C.c_int, [_i32, _i32, _vp, _vp, _i64, _vp]),
     "pfbs_primal_step": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _i32, _i32, _i64, _vp]),
     "pfbs_norm_diff": (C.c_int, [_i32, _i32, _vp, _vp, _i64, C.POINTER(_dbl), _vp]),
@@ -95,25 +96,44 @@ SIGNATURES = {
 _lib = None
 
 
+# translation units of libpfbgrid.so and the files each one includes (incremental rebuilds: the gridder
+# unit takes ~2 minutes to compile, the others seconds)
+_UNITS = {
+    "pfbgrid.cu": ["common.cuh", "fft.cuh", "fused_fft.cuh", "kernels.cuh", "psfconv.cuh", "runs.cuh", "weighting.cuh",
+                   "../../include/pfbgrid.h"],
+    "pfbsara.cu": ["sara.cuh", "../../include/pfbsara.h", "../../include/pfbgrid.h"],
+}
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile ``csrc/pfbgrid.cu`` for sm_100a into ``libpfbgrid.so`` (in-tree)."""
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(ROOT, "include", "pfbgrid.h"))
-    srcs.append(os.path.join(ROOT, "include", "pfbsara.h"))
-    if not force and os.path.exists(LIB_PATH):
-        if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-            return LIB_PATH
+    """Compile ``csrc/*.cu`` for sm_100a into ``libpfbgrid.so`` (in-tree), one object per translation unit."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "--threads", "2", os.path.join(CSRC, "pfbgrid.cu"), os.path.join(CSRC, "pfbsara.cu"),
-           "-o", LIB_PATH, "-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs, relink = [], force or not os.path.exists(LIB_PATH)
+    for unit, deps in _UNITS.items():
+        src = os.path.join(CSRC, unit)
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        stamps = [os.path.getmtime(src)] + [os.path.getmtime(os.path.normpath(os.path.join(CSRC, d))) for d in deps]
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(stamps):
+            cmd = [nvcc, *flags, "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), file=sys.stderr)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+            if verbose:
+                print(res.stderr, file=sys.stderr)
+            relink = True
+    if relink or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB_PATH, "-lcufft",
+               "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     return LIB_PATH
 
 

@@ -297,6 +297,20 @@ extern "C" int pfbs_extrapolate(int32_t precision, int32_t device, const void* v
   return PFBG_OK;
 }
 
+extern "C" int pfbs_axpby(int32_t precision, int32_t device, void* out, double a, const void* x, double b, const void* y,
+                          int64_t n, void* stream) {
+  if (!out || !x || !y) return pfbg_fail(PFBG_ERR_ARG, "null argument");
+  SCK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n <= 0) return PFBG_OK;
+  if (precision == PFBG_F32) k_axpby<float><<<nblk(n), 256, 0, s>>>((float*)out, (float)a, (const float*)x, (float)b, (const float*)y, n);
+  else if (precision == PFBG_F64) k_axpby<double><<<nblk(n), 256, 0, s>>>((double*)out, a, (const double*)x, b, (const double*)y, n);
+  else return pfbg_fail(PFBG_ERR_ARG, "bad precision");
+  pfbg_count_launch();
+  SCK(cudaGetLastError());
+  return PFBG_OK;
+}
+
 extern "C" int pfbs_primal_step(int32_t precision, int32_t device, void* x, const void* xp, const void* xout, double tau,
                                 int32_t positivity, int32_t nband, int64_t npix, void* stream) {
   if (!x || !xp || !xout) return pfbg_fail(PFBG_ERR_ARG, "null argument");

@@ -208,6 +208,13 @@ __global__ void k_extrapolate(const T* __restrict__ v, T* __restrict__ vp, int64
   if (k < n) vp[k] = (T)2 * v[k] - vp[k];
 }
 
+// out = a x + b y (out may alias x or y)
+template <typename T>
+__global__ void k_axpby(T* out, T a, const T* x, T b, const T* y, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = a * x[k] + b * y[k];
+}
+
 template <typename T>
 __global__ void k_primal_step(T* __restrict__ x, const T* __restrict__ xp, const T* __restrict__ xout, T tau,
                               int positivity, int nband, int64_t npix) {

@@ -159,6 +159,55 @@ class L21:
         vout[...] = rt.cpu().numpy()
         return vout
 
+    def prox_dev(self, v_t, out_t, w_t, lam, sigma=1.0, reduce=None):
+        """Device tensors; with `reduce` the band sum is completed across ranks before thresholding."""
+        psi = self.psi
+        torch = _torch()
+        nband, ncoef = v_t.shape[0], int(v_t[0].numel())
+        s = torch.cuda.current_stream(v_t.device).cuda_stream
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        if reduce is None:
+            _lib.check(psi._lib.pfbs_prox_21m(psi.prec, psi.device, p(v_t), p(out_t), p(w_t), float(lam), float(sigma),
+                                              nband, ncoef, s))
+            return
+        # sharded bands: ratio from the global band sum (one all-reduce), then a local scale
+        tot = v_t.sum(dim=0)
+        reduce(tot)
+        tot /= sigma
+        a = tot.abs()
+        ratio = torch.where(tot != 0, torch.clamp(a - lam * w_t / sigma, min=0.0) / torch.where(a > 0, a, torch.ones_like(a)) / sigma,
+                            torch.zeros_like(a))
+        torch.mul(v_t, ratio.unsqueeze(0), out=out_t)
+
+    # l1 reweighting (prox/l21.py:52-91, utils/misc.py:750-764): once per major cycle, host side
+    @property
+    def reweight_active(self) -> bool:
+        return getattr(self, "_rms_comps", None) is not None
+
+    def _band_sum_coeffs(self, x, reduce=None):
+        psi = self.psi
+        out = np.empty(psi.coeff_shape, psi.rdt)
+        psi.dot(np.ascontiguousarray(x, dtype=psi.rdt), out)
+        tot = out.sum(axis=0)
+        return reduce(tot) if reduce is not None else tot
+
+    def init_reweighting(self, update, reduce=None):
+        tmp = self._band_sum_coeffs(update, reduce)
+        rms = np.ones(self.psi.nbasis)
+        for i in range(self.psi.nbasis):
+            nz = tmp[i][tmp[i] != 0]
+            if nz.size:
+                rms[i] = np.std(nz)
+        self._rms_comps = rms
+
+    def update_weights(self, x, reduce=None):
+        if not self.reweight_active:
+            raise RuntimeError("init_reweighting() has not been called")
+        mcomps = np.abs(self._band_sum_coeffs(x, reduce))
+        r = self._rms_comps[:, None, None]
+        self.l1weight = (1 + self.rmsfactor) / (1 + mcomps ** self.alpha / r ** self.alpha)
+        return self.l1weight
+
     def dual_update(self, vp, v, lam, sigma=1.0):
         """Fused dual update of ``dual_update_numba_fast`` (v updated in place, numpy in / out)."""
         torch = _torch()
@@ -306,3 +355,94 @@ class PrimalDual:
             x[...] = out
             return x
         return out
+
+
+class ForwardBackward:
+    """Forward-backward splitting with optional FISTA momentum (``opt/forward_backward.py:21-133``), the cube
+    resident on the device.  Same `setup` / `set_grad` / `solve` contract and grad conventions as `PrimalDual`."""
+
+    def __init__(self, tol=1e-5, maxit=1000, report_freq=10, verbosity=1, gamma=1.0, acceleration=True, on_converge=None,
+                 positivity=0, reduce_tensor=None, reduce_scalars=None):
+        self.tol, self.maxit, self.report_freq, self.verbosity = tol, maxit, report_freq, verbosity
+        self.gamma, self.acceleration, self.on_converge = gamma, acceleration, on_converge
+        self.positivity = int(positivity)
+        self.reduce_tensor, self.reduce_scalars = reduce_tensor, reduce_scalars
+        self._grad = self._reg = None
+        self.niter, self.eps = 0, 1.0
+
+    def setup(self, prox, hessnorm: float) -> None:
+        self._reg = prox
+        self.hessnorm = hessnorm
+        self.step = 2.0 * self.gamma / hessnorm
+
+    def set_grad(self, grad) -> None:
+        self._grad = grad
+
+    def reset(self) -> None:
+        """No warm-start state beyond x itself."""
+
+    def solve(self, x, lam: float):
+        if self._reg is None:
+            raise RuntimeError("regulariser not bound; call setup() before solve()")
+        if self._grad is None:
+            raise RuntimeError("grad not set; call set_grad() before solve()")
+        torch = _torch()
+        reg, psi = self._reg, self._reg.psi
+        lib, prec, dv = psi._lib, psi.prec, psi.device
+        dev = torch.device("cuda", dv)
+        tdt = torch.float32 if psi.rdt == np.float32 else torch.float64
+        x_t = torch.from_numpy(np.ascontiguousarray(x, dtype=psi.rdt)).to(dev)
+        xp_t, y_t = x_t.clone(), x_t.clone()
+        g_t, xout_t = torch.empty_like(x_t), torch.empty_like(x_t)
+        a_t = torch.empty((psi.nband, psi.nbasis, psi.nxmax, psi.nymax), dtype=tdt, device=dev)
+        b_t = torch.empty_like(a_t)
+        w = reg.l1weight.transpose(0, 2, 1) if psi._transposed else reg.l1weight
+        w_t = torch.from_numpy(np.ascontiguousarray(w, dtype=psi.rdt)).to(dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        ax = lambda out, a, xx, b, yy: _lib.check(lib.pfbs_axpby(prec, dv, p(out), float(a), p(xx), float(b), p(yy), out.numel(), s))  # noqa: E731
+        dev_grad = getattr(self._grad, "device_apply", None)
+        nd = (C.c_double * 2)()
+        t, eps, k = 1.0, 1.0, 0
+        for k in range(self.maxit):
+            if dev_grad is not None:
+                dev_grad(y_t, g_t)
+            else:
+                g_t.copy_(torch.from_numpy(np.ascontiguousarray(self._grad(y_t.cpu().numpy()), dtype=psi.rdt)))
+            ax(x_t, 1.0, y_t, -self.step, g_t)
+            # tight-frame prox: x += Psi (prox(Psi^T x) - Psi^T x) / nu
+            psi.dot_dev(x_t, a_t, s)
+            reg.prox_dev(a_t, b_t, w_t, self.step * lam, 1.0, self.reduce_tensor)
+            ax(b_t, 1.0, b_t, -1.0, a_t)
+            psi.hdot_dev(b_t, xout_t, s)
+            ax(x_t, 1.0, x_t, 1.0 / reg.nu, xout_t)
+            if self.positivity:
+                pos = self.positivity
+                if pos == 2 and self.reduce_tensor is not None:
+                    neg = (x_t <= 0).any(dim=0).to(x_t.dtype)
+                    self.reduce_tensor(neg)
+                    x_t.mul_((neg == 0).to(x_t.dtype))
+                else:
+                    _lib.check(lib.pfbs_primal_step(prec, dv, p(x_t), p(x_t), p(x_t), 0.0, pos, psi.nband, psi.nx * psi.ny, s))
+            _lib.check(lib.pfbs_norm_diff(prec, dv, p(x_t), p(xp_t), x_t.numel(), nd, s))
+            num, den = float(nd[0]), float(nd[1])
+            if self.reduce_scalars is not None:
+                num, den = (float(v) for v in self.reduce_scalars(np.array([num, den])))
+            eps = float(np.sqrt(num / max(den, 1e-12))) if den > 0 else 1.0
+            if eps < self.tol:
+                if self.on_converge is None or self.on_converge(x_t.cpu().numpy(), k, eps):
+                    break
+            if self.acceleration:
+                tp = t
+                t = (1.0 + np.sqrt(1.0 + 4.0 * tp ** 2)) / 2.0
+                c = (tp - 1.0) / t
+                ax(y_t, 1.0 + c, x_t, -c, xp_t)
+            else:
+                y_t.copy_(x_t)
+            xp_t.copy_(x_t)
+            if not k % self.report_freq and self.verbosity > 1:
+                print(f"FB: at iteration {k} eps = {eps:.3e}")
+        self.niter, self.eps = k, eps
+        if self.verbosity:
+            print(f"FB: max iters reached, eps = {eps:.3e}" if k == self.maxit - 1 else f"FB: converged after {k} iterations")
+        return x_t.cpu().numpy()

@@ -232,3 +232,52 @@ def test_psi_full_size_identity_and_rate():
     gb = (x_t.numel() * 8 * 2 + a_t.numel() * 8 * 2) / 1e9
     print(f"\n4096^2 dot+hdot: {dt * 1e3:.2f} ms  ({gb / dt:.0f} GB/s of compulsory traffic), max err {err:.1e}")
     assert err < 1e-10
+
+
+@pytest.mark.parametrize("acceleration,positivity", [(True, 0), (False, 1), (True, 2)])
+def test_forward_backward_matches_oracle(acceleration, positivity):
+    from oracle import sara_np as so
+    from pfb_imaging_b200 import wavelet_filters as wf
+    from pfb_imaging_b200.sara import L21, ForwardBackward, PsiNocopyt
+
+    nband, nx, ny, nlevel = 2, 88, 72, 2
+    bases = ["self", "db1", "db3"]
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal((nband, nx, ny)) * 0.1
+    y[:, 30:40, 20:30] += 2.0
+    psi = PsiNocopyt(nband, nx, ny, bases, nlevel, 1)
+    reg = L21(psi, bases, nu=len(bases))
+    reg.l1weight = rng.uniform(0.5, 1.5, reg.l1weight.shape)
+    fb = ForwardBackward(tol=1e-14, maxit=15, verbosity=0, acceleration=acceleration, positivity=positivity)
+    fb.setup(reg, 1.0)
+    fb.set_grad(lambda xx: xx - y)
+    x = fb.solve(np.zeros_like(y), 0.05)
+    bk = wf.bookkeeping(nx, ny, bases, nlevel)
+    fbs = [None if b == "self" else wf.filter_bank(b) for b in bases]
+    dot = lambda xx: np.stack([so.psi_dot(xx[b], bk, fbs) for b in range(nband)])  # noqa: E731
+    hdot = lambda aa: np.stack([so.psi_hdot(aa[b], bk, fbs) for b in range(nband)])  # noqa: E731
+    xr, k, eps = so.forward_backward(np.zeros_like(y), 0.05, dot, hdot, lambda xx: xx - y, 1.0, len(bases), reg.l1weight,
+                                     1e-14, 15, positivity=positivity, acceleration=acceleration)
+    np.testing.assert_allclose(x, xr, rtol=0, atol=1e-10)
+    assert fb.niter == k
+
+
+def test_l1_reweighting_matches_formula():
+    from oracle import sara_np as so
+    from pfb_imaging_b200 import wavelet_filters as wf
+    from pfb_imaging_b200.sara import L21, Psi
+
+    nband, nx, ny = 2, 64, 48
+    bases = ["self", "db2"]
+    rng = np.random.default_rng(9)
+    upd, model = rng.standard_normal((nband, nx, ny)), rng.standard_normal((nband, nx, ny))
+    psi = Psi(nband, nx, ny, bases, 2, 1)
+    reg = L21(psi, bases, rmsfactor=0.7, alpha=2.0)
+    reg.init_reweighting(upd)
+    w = reg.update_weights(model)
+    bk = wf.bookkeeping(nx, ny, bases, 2)
+    fbs = [None, wf.filter_bank("db2")]
+    tot_u = sum(so.psi_dot(upd[b], bk, fbs, transposed=True) for b in range(nband))
+    rms = np.array([np.std(tot_u[i][tot_u[i] != 0]) for i in range(2)])
+    tot_m = sum(so.psi_dot(model[b], bk, fbs, transposed=True) for b in range(nband))
+    np.testing.assert_allclose(w, so.l1reweight(tot_m, 0.7, rms, 2.0), rtol=1e-9)
