@@ -292,3 +292,93 @@ def test_plan_pool_reuse_matches_fresh_plans(gpu):
                                  False, True, False, True, True)
         assert rel_l2(o, dref) <= 1e-7
     W.clear_plan_pool()
+
+
+@pytest.mark.parametrize("prec,eps", [("single", 1e-5), ("double", 1e-6), ("double", 1e-8)])
+def test_aliased_uv_footprints_wrap_around_the_grid(gpu, prec, eps):
+    """uv coverage three times wider than the grid: footprints straddle the periodic grid edge in u and v
+    (general flush / fetch path of the run kernels) and runs are short.  The DFT is periodic in the same way."""
+    p = small_problem(nrow=500, nchan=3, nx=80, ny=64, seed=3)
+    uvw = p["uvw"] * np.array([3.0, 3.0, 1.0])
+    rdt, cdt = (np.float32, np.complex64) if prec == "single" else (np.float64, np.complex128)
+    kw = dict(center_x=0.0, center_y=0.0, flip_u=False, flip_v=True, flip_w=False, do_wgridding=True, divide_by_n=False)
+    with W.plan_for(uvw, p["freq"], npix_x=80, npix_y=64, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=eps,
+                    precision=prec, mask=p["mask"], **kw) as gp:
+        b = wg.bin_indices(gp.plan, uvw, p["freq"], p["mask"])
+        wraps = np.count_nonzero((np.mod(b["iu0"], gp.plan.nu) + gp.plan.W > gp.plan.nu) |
+                                 (np.mod(b["iv0"], gp.plan.nv) + gp.plan.W > gp.plan.nv))
+        assert wraps > 10, "fixture no longer exercises the wrap-around path"
+        act = p["mask"] != 0
+        v = gp.degrid(p["img"].astype(rdt))
+        ref = dft.dft_dirty2vis(uvw, p["freq"], p["img"], p["cell"], p["cell"], **kw)
+        assert rel_l2(v[act], ref[act]) <= eps
+        vis, wgt = p["vis"].astype(cdt), p["wgt"].astype(rdt)
+        d = gp.grid(vis, wgt)
+        dref = dft.dft_vis2dirty(uvw, p["freq"], vis, wgt, p["mask"], 80, 64, p["cell"], p["cell"], **kw)
+        assert rel_l2(d, dref) <= eps
+
+
+def test_hermitian_fold_of_negative_w(gpu):
+    """Samples with w < 0 are gridded at -(u,v,w) with the conjugate visibility: a data set and its mirror image
+    (uvw -> -uvw, vis -> conj vis) must give the same dirty image, and degridding the mirror gives conj(vis)."""
+    p = small_problem(nrow=700, nchan=2, nx=64, ny=96, seed=8, wscale=3.0)
+    kw = dict(freq=p["freq"], pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=1e-9, flip_v=True, divide_by_n=False)
+    assert (p["uvw"][:, 2] < 0).any() and (p["uvw"][:, 2] > 0).any()
+    d1 = W.vis2dirty(uvw=p["uvw"], vis=p["vis"], wgt=p["wgt"], mask=p["mask"], npix_x=64, npix_y=96, **kw)
+    d2 = W.vis2dirty(uvw=-p["uvw"], vis=np.conj(p["vis"]), wgt=p["wgt"], mask=p["mask"], npix_x=64, npix_y=96, **kw)
+    # identical sample set after the fold; only the order of the atomic adds differs (round-off, amplified by
+    # the grid correction 1/psihat ~ 1e4 at this accuracy)
+    assert rel_l2(d2, d1) <= 1e-10
+    v1 = W.dirty2vis(uvw=p["uvw"], dirty=p["img"].T.copy(), mask=p["mask"], **kw)
+    v2 = W.dirty2vis(uvw=-p["uvw"], dirty=p["img"].T.copy(), mask=p["mask"], **kw)
+    assert rel_l2(v2, np.conj(v1)) <= 1e-10
+    # the plane stack only covers |w|
+    with W.plan_for(p["uvw"], p["freq"], npix_x=64, npix_y=96, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=1e-9,
+                    flip_v=True, divide_by_n=False) as gp:
+        wabs = np.abs(p["uvw"][:, 2:3]) * p["freq"][None, :] / 299792458.0
+        lo, hi = gp.plan.w0, gp.plan.w0 + (gp.plan.nplanes - 1) * gp.plan.dw
+        assert lo <= wabs.min() and hi >= wabs.max()
+        assert gp.plan.nplanes == int(np.ceil((wabs.max() - wabs.min()) / gp.plan.dw)) + gp.plan.W
+
+
+def test_full_size_properties_c2_band(gpu):
+    """One band of BASELINE config 2 (4096^2, 25.0 M vis, fp32, eps 1e-5): sampled DFT parity in both directions,
+    adjointness, and the fused Hessian against the composition of its halves."""
+    d = synth.make_band(775, 16, band=5, nband=8, precision="single", with_vis=True, flag_frac=0.03)
+    uvw, freq = d["uvw"], d["freq"]
+    cell = synth.default_cell(uvw, 1712e6)
+    nx = 4096
+    eps = 1e-5
+    gp = W.plan_for(uvw, freq, npix_x=nx, npix_y=nx, pixsize_x=cell, pixsize_y=cell, epsilon=eps, flip_v=True,
+                    divide_by_n=False, mask=d["mask"], sigma_min=1.1, sigma_max=3.0, precision="single")
+    x = synth.point_source_image(nx, nx, dtype=np.float32)
+    v = gp.degrid(x)
+    rows = np.random.default_rng(0).integers(0, uvw.shape[0], 200)
+    ref = dft.dft_dirty2vis(uvw, freq, x.astype(np.float64), cell, cell, 0, 0, False, True, False, True, False, rows=rows)
+    act = d["mask"][rows] != 0
+    assert rel_l2(v[rows][act], ref[act]) <= eps
+    # gridding parity on a row subset small enough for the DFT (row additivity makes the subset a valid problem)
+    sub = slice(0, uvw.shape[0], 997)
+    with W.plan_for(uvw[sub], freq, npix_x=nx, npix_y=nx, pixsize_x=cell, pixsize_y=cell, epsilon=eps, flip_v=True,
+                    divide_by_n=False, mask=d["mask"][sub], sigma_min=1.1, sigma_max=3.0, precision="single") as gs:
+        ds = gs.grid(d["vis"][sub], d["wgt"][sub])
+    rng = np.random.default_rng(1)
+    px = (rng.integers(0, nx, 48), rng.integers(0, nx, 48))
+    dref = dft.dft_vis2dirty(uvw[sub], freq, d["vis"][sub], d["wgt"][sub], d["mask"][sub], nx, nx, cell, cell, 0, 0,
+                             False, True, False, True, False, pixels=px)
+    # the contract is the L2 norm over the image; on 48 sampled pixels compare against the image-wide scale
+    assert np.linalg.norm(ds[px] - dref) / (np.sqrt(48.0) * np.sqrt(np.mean(ds.astype(np.float64) ** 2))) <= eps
+    dimg = gp.grid(d["vis"], d["wgt"])
+    a = (d["vis"] * d["wgt"] * (d["mask"] != 0)).astype(np.complex128)
+    lhs = np.vdot(v.astype(np.complex128), a).real
+    rhs = float((dimg.astype(np.float64) * x).sum())
+    # random visibilities against a sparse model: both inner products cancel to ~1e-4 of ||Rx|| ||a||, so the
+    # natural (Cauchy-Schwarz) scale is used, as in SURVEY §8(d) "adjointness ... / ||...||"
+    scale = np.linalg.norm(v.astype(np.complex128)) * np.linalg.norm(a)
+    print(f"adjointness defect {abs(lhs - rhs) / scale:.2e} of ||Rx|| ||a||, {abs(lhs - rhs) / abs(rhs):.2e} of the product")
+    assert abs(lhs - rhs) <= 1e-7 * scale
+    gp.bind_weights(d["wgt"])
+    h = gp.hessian(x)
+    h2 = gp.grid(v, d["wgt"])
+    assert rel_l2(h, h2) <= 2e-6
+    gp.close()
