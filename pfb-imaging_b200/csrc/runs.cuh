@@ -77,6 +77,16 @@ __device__ __forceinline__ float es_fast(float x, float beta_log2e) {
   return a < 0.0f ? 0.0f : e;
 }
 __device__ __forceinline__ double es_fast(double x, double beta) { return es_eval(x, beta); }
+
+// tap k (cell i0 + k) of a sample whose first cell sits at x0 = i0 - g in (-W/2, -W/2 + 1].
+// (A piecewise-polynomial form of the fp64 taps, degree W+3 as in ducc0, was measured on B200 and is NOT faster
+// than exp + sqrt: 10 16-byte coefficient loads + 19 dependent DFMAs per tap; it was dropped.)
+__device__ __forceinline__ float tap_eval(const GParams& p, float x0, int k, float bscale, float xs) {
+  return es_fast((x0 + (float)k) * xs, bscale);
+}
+__device__ __forceinline__ double tap_eval(const GParams& p, double x0, int k, double bscale, double xs) {
+  return es_fast((x0 + (double)k) * xs, bscale);
+}
 __device__ __forceinline__ float es_scale(float beta) { return beta * 1.4426950408889634f; }
 __device__ __forceinline__ double es_scale(double beta) { return beta; }
 
@@ -95,11 +105,11 @@ __device__ __forceinline__ void run_taps(const GParams& p, const T (*x0s)[4], T 
                                          T bscale, T xs) {
   if (lane < 24) {
     const int axis = lane >> 3;
-    const T kk = (T)(lane & 7);
+    const int kk = lane & 7;
     const bool flat_w = (axis == 2) && !p.do_wgridding;
 #pragma unroll 4
     for (int v = 0; v < nb; ++v) {
-      T val = es_fast((x0s[v][axis] + kk) * xs, bscale);
+      T val = tap_eval(p, x0s[v][axis], kk, bscale, xs);
       if (flat_w) val = (lane == 16) ? (T)1 : (T)0;
       taps[v][lane] = val;
     }
@@ -420,32 +430,42 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 // ===========================================================================
 // Wide-support run kernels (9 <= W <= 16; the fp64 production settings, epsilon <= 1e-7).
 //
-// Same scheme as above, but the footprint no longer fits one warp's registers, so a TEAM of R
-// warps shares every run: warp r of the team owns the u-rows  i = r*RPW .. r*RPW+RPW-1  and walks
-// the same slice of samples independently (no inter-warp synchronisation: each warp stages the
-// records and evaluates the taps it needs itself).  Lane = (j, q2) with j = v-offset (0..15) and
+// The footprint no longer fits one warp's registers, so a TEAM of R warps shares every run: warp r of
+// the team owns the u-rows  i = r*RPW .. r*RPW+RPW-1.  Lane = (j, q2) with j = v-offset (0..15) and
 // q2 = plane slot (0..1); a lane holds RPW rows x NQ planes (q = q2 + 2*qq).
 //   9..12 : RPW = 3, NQ = 6, R = 4        13..16 : RPW = 2, NQ = 8, R = 8
+// The team works on one batch of samples at a time: warp 0 stages weight * phase * vis, ALL R warps
+// evaluate the 3 W taps of the batch together (each tap once per team: in fp64 the tap evaluation costs
+// more than the FMAs, and evaluating it per warp made it 4-8 times redundant), then every warp runs the
+// FMA stage for its rows.  Named barriers (one id per team) separate the stages.
 // ===========================================================================
-template <typename T, int RPW, int NQ>
-struct WideCfg {
-  static constexpr int NB = 16;              // samples staged per batch
-  static constexpr int NT = RPW + 32;        // taps per sample and warp: RPW u-taps, 16 v-taps, 16 w-taps
-};
+#define WIDE_WARPS 8
+#define WIDE_NB 16   // samples staged per batch
+#define WIDE_NT 48   // tap slots per sample: 16 u, 16 v, 16 w (the first W of each are live)
 
-template <typename T, int RPW, int NQ>
-__device__ __forceinline__ void wide_taps(const GParams& p, const T (*x0s)[4], T (*taps)[RPW + 32], int nb, int lane,
-                                          int row0, T bscale, T xs) {
-  constexpr int NT = RPW + 32;
-  for (int idx = lane; idx < NT * nb; idx += 32) {
-    const int v = idx / NT, t = idx - v * NT;
-    int axis, k;
-    if (t < RPW) { axis = 0; k = row0 + t; }
-    else if (t < RPW + 16) { axis = 1; k = t - RPW; }
-    else { axis = 2; k = t - RPW - 16; }
-    T val = es_fast((x0s[v][axis] + (T)k) * xs, bscale);
+__device__ __forceinline__ void team_sync(int team, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(nthreads) : "memory");
+}
+
+// all threads of the team: tap t = axis * W + k of sample v
+template <typename T>
+__device__ __forceinline__ void wide_taps(const GParams& p, const T (*x0s)[4], T (*taps)[WIDE_NT], int nb, int ttid,
+                                          int tthreads, T bscale, T xs) {
+  const int W = p.W, nt = 3 * W;
+  for (int idx = ttid; idx < nt * nb; idx += tthreads) {
+    const int v = idx / nt, t = idx - v * nt;
+    const int axis = t / W, k = t - axis * W;
+    T val = tap_eval(p, x0s[v][axis], k, bscale, xs);
     if (axis == 2 && !p.do_wgridding) val = (k == 0) ? (T)1 : (T)0;
-    taps[v][t] = val;
+    taps[v][axis * 16 + k] = val;
+  }
+  if (W < 16) {  // slots beyond the support are read (times zero grid values / never flushed): keep them zero
+    const int nz = 3 * (16 - W);
+    for (int idx = ttid; idx < nz * nb; idx += tthreads) {
+      const int v = idx / nz, t = idx - v * nz;
+      const int axis = t / (16 - W), k = W + (t - axis * (16 - W));
+      taps[v][axis * 16 + k] = (T)0;
+    }
   }
 }
 
@@ -479,8 +499,6 @@ __device__ __forceinline__ void wide_flush(const GParams& p, typename cplx_of<T>
   }
 }
 
-#define WIDE_WARPS 8
-
 template <typename T, int RPW, int NQ, int R>
 __global__ void __launch_bounds__(WIDE_WARPS * 32)
 k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
@@ -488,15 +506,15 @@ k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
                  const T* __restrict__ wgt, typename cplx_of<T>::type* __restrict__ grid, int vis_sorted,
                  int apply_phase) {
   using C = typename cplx_of<T>::type;
-  constexpr int NB = WideCfg<T, RPW, NQ>::NB, NT = WideCfg<T, RPW, NQ>::NT;
-  __shared__ T taps[WIDE_WARPS][NB][NT];
-  __shared__ __align__(16) T x0s[WIDE_WARPS][NB][4];
-  __shared__ C amp[WIDE_WARPS][NB];
-  __shared__ uint64_t orgs[WIDE_WARPS][NB];
+  constexpr int NB = WIDE_NB, NTEAM = WIDE_WARPS / R;
+  __shared__ T taps[NTEAM][NB][WIDE_NT];
+  __shared__ __align__(16) T x0s[NTEAM][NB][4];
+  __shared__ C amp[NTEAM][NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp / R, r = warp - team * R;
+  const int ttid = r * 32 + lane;
   const int j = lane & 15, q2 = lane >> 4;
-  const int64_t gwarp = (int64_t)blockIdx.x * WIDE_WARPS + warp;
-  const int row0 = (int)(gwarp % R) * RPW;
+  const int row0 = r * RPW;
   const T bscale = es_scale((T)p.beta), xs = (T)(2.0 / p.W);
   T accr[RPW][NQ], acci[RPW][NQ];
 #pragma unroll
@@ -505,50 +523,53 @@ k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
     for (int qq = 0; qq < NQ; ++qq) { accr[ii][qq] = 0; acci[ii][qq] = 0; }
   uint64_t cur = ~0ull;
   const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
-  const int64_t nteams = ((int64_t)gridDim.x * WIDE_WARPS) / R;
-  for (int64_t sl = gwarp / R; sl < nslice; sl += nteams) {
+  const int64_t nteams = (int64_t)gridDim.x * NTEAM;
+  for (int64_t sl = (int64_t)blockIdx.x * NTEAM + team; sl < nslice; sl += nteams) {
     const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
     for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
       const int nb = (int)min((int64_t)NB, kend - k0);
-      if (lane < nb) {
+      uint64_t org = ~0ull;
+      if (lane < nb) {  // every warp reads the records (it needs the run origins); warp 0 stages the rest
         const int64_t k = k0 + lane;
-        VisRec<T> r = recs[k];
-        C a;
-        if (vis_sorted) a = vis[k];
-        else {
-          int64_t row = r.idx / p.nchan;
-          int chan = (int)(r.idx - row * p.nchan);
-          a = vis[row * vis_rs + chan * vis_cs];
+        const VisRec<T> rec = recs[k];
+        org = pack_origin(rec.iu, rec.iv, rec.ip);
+        if (r == 0) {
+          C a;
+          if (vis_sorted) a = vis[k];
+          else {
+            int64_t row = rec.idx / p.nchan;
+            int chan = (int)(rec.idx - row * p.nchan);
+            a = vis[row * vis_rs + chan * vis_cs];
+          }
+          T w = wgt ? wgt[rec.idx] : (T)1;
+          T pc = apply_phase ? rec.pc : (T)1, ps = apply_phase ? rec.ps : (T)0;
+          if (apply_phase && (rec.ip & REC_CONJ_BIT)) a.y = -a.y;  // folded sample (the Hessian path stays folded)
+          C sa;
+          sa.x = (a.x * pc - a.y * ps) * w;
+          sa.y = (a.x * ps + a.y * pc) * w;
+          amp[team][lane] = sa;
+          x0s[team][lane][0] = rec.x0[0]; x0s[team][lane][1] = rec.x0[1]; x0s[team][lane][2] = rec.x0[2];
         }
-        T w = wgt ? wgt[r.idx] : (T)1;
-        T pc = apply_phase ? r.pc : (T)1, ps = apply_phase ? r.ps : (T)0;
-        if (apply_phase && (r.ip & REC_CONJ_BIT)) a.y = -a.y;  // folded sample (the Hessian path stays folded)
-        C s;
-        s.x = (a.x * pc - a.y * ps) * w;
-        s.y = (a.x * ps + a.y * pc) * w;
-        amp[warp][lane] = s;
-        x0s[warp][lane][0] = r.x0[0]; x0s[warp][lane][1] = r.x0[1]; x0s[warp][lane][2] = r.x0[2];
-        orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
       }
-      __syncwarp();
-      wide_taps<T, RPW, NQ>(p, x0s[warp], taps[warp], nb, lane, row0, bscale, xs);
-      __syncwarp();
+      const uint32_t starts = run_starts(org, cur, lane, nb);
+      team_sync(team, 32 * R);
+      wide_taps<T>(p, x0s[team], taps[team], nb, ttid, 32 * R, bscale, xs);
+      team_sync(team, 32 * R);
       for (int v = 0; v < nb; ++v) {
-        const uint64_t org = orgs[warp][v];
-        if (org != cur) {
+        if ((starts >> v) & 1u) {
           if (cur != ~0ull) wide_flush<T, RPW, NQ>(p, grid, accr, acci, cur, j, q2, row0);
-          cur = org;
+          cur = shfl_u64(org, v);
         }
-        const T* tp = taps[warp][v];
-        const T tv = tp[RPW + j];
-        const C a = amp[warp][v];
+        const T* tp = taps[team][v];
+        const T tv = tp[16 + j];
+        const C a = amp[team][v];
         const T ar = a.x * tv, ai = a.y * tv;
         T ur[RPW], ui[RPW];
 #pragma unroll
-        for (int ii = 0; ii < RPW; ++ii) { ur[ii] = ar * tp[ii]; ui[ii] = ai * tp[ii]; }
+        for (int ii = 0; ii < RPW; ++ii) { ur[ii] = ar * tp[row0 + ii]; ui[ii] = ai * tp[row0 + ii]; }
 #pragma unroll
         for (int qq = 0; qq < NQ; ++qq) {
-          const T wq = tp[RPW + 16 + q2 + 2 * qq];
+          const T wq = tp[32 + q2 + 2 * qq];
 #pragma unroll
           for (int ii = 0; ii < RPW; ++ii) {
             accr[ii][qq] += ur[ii] * wq;
@@ -556,10 +577,36 @@ k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
           }
         }
       }
-      __syncwarp();
+      team_sync(team, 32 * R);  // the next batch overwrites the staging buffers
     }
   }
   if (cur != ~0ull) wide_flush<T, RPW, NQ>(p, grid, accr, acci, cur, j, q2, row0);
+}
+
+// Degridding keeps INDEPENDENT warps (measured on B200, C2 band in fp64 at epsilon 1e-7: the cooperative
+// variant with team barriers was 17 % slower here, because every new run starts with a footprint fetch whose
+// latency the barriers then serialise across the team; for gridding, whose flushes are fire-and-forget, the
+// cooperative form above is 19 % faster).  Each warp stages the records and evaluates the taps it needs itself.
+template <typename T, int RPW, int NQ>
+struct WideCfg {
+  static constexpr int NB = 16;              // samples staged per batch
+  static constexpr int NT = RPW + 32;        // taps per sample and warp: RPW u-taps, 16 v-taps, 16 w-taps
+};
+
+template <typename T, int RPW, int NQ>
+__device__ __forceinline__ void wide_taps_warp(const GParams& p, const T (*x0s)[4], T (*taps)[RPW + 32], int nb, int lane,
+                                          int row0, T bscale, T xs) {
+  constexpr int NT = RPW + 32;
+  for (int idx = lane; idx < NT * nb; idx += 32) {
+    const int v = idx / NT, t = idx - v * NT;
+    int axis, k;
+    if (t < RPW) { axis = 0; k = row0 + t; }
+    else if (t < RPW + 16) { axis = 1; k = t - RPW; }
+    else { axis = 2; k = t - RPW - 16; }
+    T val = es_fast((x0s[v][axis] + (T)k) * xs, bscale);
+    if (axis == 2 && !p.do_wgridding) val = (k == 0) ? (T)1 : (T)0;
+    taps[v][t] = val;
+  }
 }
 
 // degridding: each warp of the team produces the partial sum over its rows; partials of the R
@@ -601,7 +648,7 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
         orgs[warp][lane] = pack_origin(r.iu, r.iv, r.ip);
       }
       __syncwarp();
-      wide_taps<T, RPW, NQ>(p, x0s[warp], taps[warp], nb, lane, row0, bscale, xs);
+      wide_taps_warp<T, RPW, NQ>(p, x0s[warp], taps[warp], nb, lane, row0, bscale, xs);
       __syncwarp();
       T myr = 0, myi = 0;  // lane v keeps the team-partial of sample v
       for (int v = 0; v < nb; ++v) {
