@@ -73,7 +73,10 @@ typedef struct pfbg_plan_desc {
   const double* gl_x;    /* host (n_gl): Gauss-Legendre nodes on (0,1) */
   const double* gl_w;    /* host (n_gl) */
   int32_t n_gl;
-  int32_t reserved;
+  int32_t pmirror;       /* 0, or the number of virtual planes below plane 0 (mirror planes): then w0 == dw/2, so
+                          * plane -p-1 is the Hermitian mirror of plane p (G_{-p-1}(u,v) = conj G_p(-u,-v), the
+                          * image being real) and samples near w = 0 use the mirrored cells of planes 0..pmirror-1
+                          * instead of planes that would have to be stored and transformed */
 } pfbg_plan_desc;
 
 typedef struct pfbg_plan_info {
@@ -95,10 +98,10 @@ int pfbg_device_count(int32_t* count);
 int pfbg_plan_create(const pfbg_plan_desc* desc, pfbg_plan** out);
 int pfbg_plan_destroy(pfbg_plan* plan);
 int pfbg_plan_get_info(const pfbg_plan* plan, pfbg_plan_info* info);
-/* Re-target a plan to another w-plane range (w0, nplanes); everything that depends only on the image
+/* Re-target a plan to another w-plane range (w0, nplanes, pmirror); everything that depends only on the image
  * geometry, sigma and W is kept.  Unbinds the visibilities.  Used to pool plans across the thousands of
  * small snapshot images of `pfb hci` (utils/stokes2im.py:635-683). */
-int pfbg_plan_set_wrange(pfbg_plan* plan, double w0, int32_t nplanes);
+int pfbg_plan_set_wrange(pfbg_plan* plan, double w0, int32_t nplanes, int32_t pmirror);
 
 /*
  * Kernel 1: upload uvw (nrow,3) f64, fscale (nchan) f64 = freq/c, optional mask

@@ -67,11 +67,15 @@ void cw_grid(int64_t n, const int64_t* order, const double* gu, const double* gv
                 double re = buf[((q * side + i) * side + j) * 2], im = buf[((q * side + i) * side + j) * 2 + 1];
                 if (re != 0.0 || im != 0.0) {
                   int iv = wrapi(bv + j, nv);
-                  double* g = grid + ((int64_t)(bp + q) * plane + (int64_t)iu * nv + iv) * 2;
+                  /* planes below zero (mirror planes): Hermitian mirror of plane -p-1, see oracle/wgridder_np._mirror */
+                  int pl = bp + q, mu = iu, mv = iv;
+                  double sg = 1.0;
+                  if (pl < 0) { pl = -pl - 1; mu = iu ? nu - iu : 0; mv = iv ? nv - iv : 0; sg = -1.0; }
+                  double* g = grid + ((int64_t)pl * plane + (int64_t)mu * nv + mv) * 2;
 #pragma omp atomic
                   g[0] += re;
 #pragma omp atomic
-                  g[1] += im;
+                  g[1] += sg * im;
                 }
               }
             }
@@ -109,11 +113,14 @@ void cw_grid(int64_t n, const int64_t* order, const double* gu, const double* gv
             double re = buf[((q * side + i) * side + j) * 2], im = buf[((q * side + i) * side + j) * 2 + 1];
             if (re != 0.0 || im != 0.0) {
               int iv = wrapi(bv + j, nv);
-              double* g = grid + ((int64_t)(bp + q) * plane + (int64_t)iu * nv + iv) * 2;
+              int pl = bp + q, mu = iu, mv = iv;
+              double sg = 1.0;
+              if (pl < 0) { pl = -pl - 1; mu = iu ? nu - iu : 0; mv = iv ? nv - iv : 0; sg = -1.0; }
+              double* g = grid + ((int64_t)pl * plane + (int64_t)mu * nv + mv) * 2;
 #pragma omp atomic
               g[0] += re;
 #pragma omp atomic
-              g[1] += im;
+              g[1] += sg * im;
             }
           }
         }
@@ -142,13 +149,18 @@ void cw_degrid(int64_t n, const int64_t* order, const double* gu, const double* 
     double re = 0.0, im = 0.0;
     for (int q = 0; q < npl; ++q) {
       double pre = 0.0, pim = 0.0;
+      int pl = ip0[k] + q;
+      const int mir = pl < 0; /* mirror plane: conj of plane -p-1 at the mirrored cell */
+      if (mir) pl = -pl - 1;
       for (int i = 0; i < W; ++i) {
         int iu = wrapi(wrapi(iu0[k], nu) + i, nu);
-        const double* row = grid + ((int64_t)(ip0[k] + q) * plane + (int64_t)iu * nv) * 2;
+        if (mir) iu = iu ? nu - iu : 0;
+        const double* row = grid + ((int64_t)pl * plane + (int64_t)iu * nv) * 2;
         double rre = 0.0, rim = 0.0;
         for (int j = 0; j < W; ++j) {
-          rre += row[2 * ivs[j]] * kv[j];
-          rim += row[2 * ivs[j] + 1] * kv[j];
+          int iv = mir ? (ivs[j] ? nv - ivs[j] : 0) : ivs[j];
+          rre += row[2 * iv] * kv[j];
+          rim += (mir ? -row[2 * iv + 1] : row[2 * iv + 1]) * kv[j];
         }
         pre += rre * ku[i];
         pim += rim * ku[i];

@@ -88,7 +88,7 @@ def bin_indices(plan, uvw, freq, mask=None):
     if plan.do_wgridding:
         gw = (wt - plan.w0) / plan.dw
         ip0 = np.floor(gw - 0.5 * W).astype(np.int64) + 1
-        ip0 = np.clip(ip0, 0, plan.nplanes - W)
+        ip0 = np.clip(ip0, -int(getattr(plan, "pmirror", 0)), plan.nplanes - W)
     else:
         gw = np.zeros_like(wt)
         ip0 = np.zeros(wt.shape, dtype=np.int64)
@@ -106,7 +106,8 @@ def bin_indices(plan, uvw, freq, mask=None):
     ntv = plan.nv // TILE
     tile = (iuw // TILE) * ntv + (ivw // TILE)
     fine = (iuw % TILE) * TILE + (ivw % TILE)
-    key = ((tile * plan.nplanes + ip0) * (TILE * TILE) + fine).astype(np.uint64)
+    pm = int(getattr(plan, "pmirror", 0))
+    key = ((tile * (plan.nplanes + pm) + (ip0 + pm)) * (TILE * TILE) + fine).astype(np.uint64)
     order = np.argsort(key, kind="stable")
     return dict(
         idx=idx.astype(np.int64), iu0=iu0.astype(np.int32), iv0=iv0.astype(np.int32),
@@ -119,6 +120,14 @@ def _weights(g, i0, W, beta):
     """ES weights of the W cells i0..i0+W-1 for coordinate g: (n, W)."""
     x = (i0[:, None] + np.arange(W)[None, :]) - g[:, None]
     return es_kernel(2.0 * x / W, beta)
+
+
+def _mirror(plan, pidx, iu, iv):
+    """Planes below zero (mirror planes, plan.pmirror > 0: w_p = (p + 1/2) dw) are the Hermitian mirror of
+    plane -p-1: cell (iu, iv) -> ((-iu) mod nu, (-iv) mod nv), value conjugated.  Returns the stored
+    (plane, iu, iv) and the mask of conjugated entries."""
+    neg = pidx < 0
+    return (np.where(neg, -pidx - 1, pidx), np.where(neg, np.mod(-iu, plan.nu), iu), np.where(neg, np.mod(-iv, plan.nv), iv), neg)
 
 
 def _vis_phase(plan, b):
@@ -207,9 +216,10 @@ def vis2dirty_np(plan, uvw, freq, vis, wgt=None, mask=None, chunk=20000):
         iv = np.mod(iv0[:, None] + ar, nv)
         for q in range(npl):
             val = (a[sl] * kw[:, q])[:, None, None] * ku[:, :, None] * kv[:, None, :]
-            pidx = np.broadcast_to((ip0 + q)[:, None, None], val.shape)
-            np.add.at(grid, (pidx, np.broadcast_to(iu[:, :, None], val.shape),
-                             np.broadcast_to(iv[:, None, :], val.shape)), val)
+            pidx, iub, ivb, neg = _mirror(plan, np.broadcast_to((ip0 + q)[:, None, None], val.shape),
+                                          np.broadcast_to(iu[:, :, None], val.shape),
+                                          np.broadcast_to(iv[:, None, :], val.shape))
+            np.add.at(grid, (pidx, iub, ivb), np.where(neg, np.conj(val), val))
     corr, nu_, ipx, ipy = _image_factors(plan)
     ix = np.mod(ipx, nu)
     iy = np.mod(ipy, nv)
@@ -259,7 +269,11 @@ def dirty2vis_np(plan, uvw, freq, dirty, mask=None, chunk=20000):
         iv = np.mod(iv0[:, None] + ar, nv)
         acc = np.zeros(iu0.size, dtype=np.complex128)
         for q in range(npl):
-            g = grid[(ip0 + q)[:, None, None], iu[:, :, None], iv[:, None, :]]
+            shp = (iu0.size, W, W)
+            pidx, iub, ivb, neg = _mirror(plan, np.broadcast_to((ip0 + q)[:, None, None], shp),
+                                          np.broadcast_to(iu[:, :, None], shp), np.broadcast_to(iv[:, None, :], shp))
+            g = grid[pidx, iub, ivb]
+            g = np.where(neg, np.conj(g), g)
             acc += kw[:, q] * np.einsum("nij,ni,nj->n", g, ku, kv)
         out[sl] = acc
     out *= np.exp(-2j * np.pi * _vis_phase(plan, b))

@@ -37,7 +37,7 @@ class PlanDesc(C.Structure):
         ("w0", C.c_double), ("dw", C.c_double), ("nshift", C.c_double),
         ("corr_u", C.c_void_p), ("corr_v", C.c_void_p),
         ("gl_x", C.c_void_p), ("gl_w", C.c_void_p),
-        ("n_gl", C.c_int32), ("reserved", C.c_int32),
+        ("n_gl", C.c_int32), ("pmirror", C.c_int32),
     ]
 
 
@@ -59,7 +59,7 @@ SIGNATURES = {
     "pfbg_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(_vp)]),
     "pfbg_plan_destroy": (C.c_int, [_vp]),
     "pfbg_plan_get_info": (C.c_int, [_vp, C.POINTER(PlanInfo)]),
-    "pfbg_plan_set_wrange": (C.c_int, [_vp, _dbl, _i32]),
+    "pfbg_plan_set_wrange": (C.c_int, [_vp, _dbl, _i32, _i32]),
     "pfbg_bind_vis": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32, _vp]),
     "pfbg_bind_weights": (C.c_int, [_vp, _vp, _u32, _vp]),
     "pfbg_bin_dump": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

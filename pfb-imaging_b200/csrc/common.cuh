@@ -17,6 +17,11 @@ struct GParams {
   double beta, pixsize_x, pixsize_y, center_x, center_y;
   double usign, vsign, wsign, w0, dw, nshift;
   int ntile_u, ntile_v;
+  // Mirror planes (pmirror > 0): plane p sits at w_p = (p + 1/2) dw, so plane -p-1 is the Hermitian mirror of
+  // plane p (real image): G_{-p-1}(u,v) = conj G_p(-u,-v).  Samples near w = 0 whose support reaches planes
+  // -pmirror..-1 read / write them at the mirrored cell of plane -q-1, conjugated; those planes are never
+  // stored or transformed.
+  int pmirror;
 };
 
 // ---------------------------------------------------------------------------
@@ -54,8 +59,8 @@ __device__ __forceinline__ VisCoord vis_coord(const GParams& p, const double* __
   if (p.do_wgridding) {
     c.gw = __ddiv_rn(__dsub_rn(c.wt, p.w0), p.dw);
     int ip = (int)floor(__dsub_rn(c.gw, 0.5 * (double)p.W)) + 1;
-    int hi = p.nplanes - p.W;
-    c.ip0 = ip < 0 ? 0 : (ip > hi ? hi : ip);
+    int lo = -p.pmirror, hi = p.nplanes - p.W;
+    c.ip0 = ip < lo ? lo : (ip > hi ? hi : ip);
   } else {
     c.gw = 0.0;
     c.ip0 = 0;
@@ -69,7 +74,17 @@ __device__ __forceinline__ uint64_t bucket_key(const GParams& p, const VisCoord&
   int iuw = wrap(c.iu0, p.nu), ivw = wrap(c.iv0, p.nv);
   uint64_t tile = (uint64_t)(iuw / PFBG_TILE) * (uint64_t)p.ntile_v + (uint64_t)(ivw / PFBG_TILE);
   uint64_t fine = (uint64_t)((iuw % PFBG_TILE) * PFBG_TILE + (ivw % PFBG_TILE));
-  return (tile * (uint64_t)p.nplanes + (uint64_t)c.ip0) * (uint64_t)(PFBG_TILE * PFBG_TILE) + fine;
+  return (tile * (uint64_t)(p.nplanes + p.pmirror) + (uint64_t)(c.ip0 + p.pmirror)) * (uint64_t)(PFBG_TILE * PFBG_TILE) + fine;
+}
+
+// element offset of cell (iu, iv) of plane pl in the stack; planes pl < 0 live at the mirrored cell of plane
+// -pl-1 and are conjugated (cj)
+__device__ __forceinline__ int64_t plane_cell(const GParams& p, int pl, int iu, int iv, bool& cj) {
+  const int64_t plane_sz = (int64_t)p.nu * p.nv;
+  if (pl >= 0) { cj = false; return (int64_t)pl * plane_sz + (int64_t)iu * p.nv + iv; }
+  cj = true;
+  const int mu = iu ? p.nu - iu : 0, mv = iv ? p.nv - iv : 0;
+  return (int64_t)(-pl - 1) * plane_sz + (int64_t)mu * p.nv + mv;
 }
 
 // ES kernel phi(x) = exp(beta (sqrt(1-x^2) - 1)), zero outside |x| <= 1.

@@ -423,6 +423,11 @@ __global__ void k_mark_cells(const Rec* __restrict__ recs, int64_t nact, int W, 
   if (iv2 >= nv) iv2 -= nv;
   uflag[iu >> 5] = 1; uflag[iu2 >> 5] = 1;
   vflag[iv >> 5] = 1; vflag[iv2 >> 5] = 1;
+  if ((recs[k].ip & 0x3fffffff) < 64) {  // first plane < 0 (REC_IP_BIAS): the mirrored cells are touched too
+    const int mu = iu ? nu - iu : 0, mu2 = iu2 ? nu - iu2 : 0, mv = iv ? nv - iv : 0, mv2 = iv2 ? nv - iv2 : 0;
+    uflag[mu >> 5] = 1; uflag[mu2 >> 5] = 1;
+    vflag[mv >> 5] = 1; vflag[mv2 >> 5] = 1;
+  }
 }
 
 // zero the active window of every plane (instead of a memset of the whole stack)

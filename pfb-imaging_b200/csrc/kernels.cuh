@@ -64,7 +64,6 @@ k_grid_direct(GParams p, const double* __restrict__ uvw, const double* __restric
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = p.W, npl = p.do_wgridding ? W : 1;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t plane_sz = (int64_t)p.nu * p.nv;
   for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; k < nact; k += nwarps) {
     uint32_t idx = sorted_idx[k];
     int64_t row = idx / p.nchan;
@@ -91,10 +90,11 @@ k_grid_direct(GParams p, const double* __restrict__ uvw, const double* __restric
       int i = cell / W, j = cell - i * W;
       T wuv = sk[warp][0][i] * sk[warp][1][j];
       int iu = wrap(c.iu0 + i, p.nu), iv = wrap(c.iv0 + j, p.nv);
-      C* g = grid + (int64_t)c.ip0 * plane_sz + (int64_t)iu * p.nv + iv;
       for (int q = 0; q < npl; ++q) {
         T ww = wuv * sk[warp][2][q];
-        atomic_add_c(g + q * plane_sz, are * ww, aim * ww);
+        bool cj;
+        C* g = grid + plane_cell(p, c.ip0 + q, iu, iv, cj);
+        atomic_add_c(g, are * ww, cj ? -aim * ww : aim * ww);
       }
     }
   }
@@ -118,7 +118,6 @@ k_degrid_direct(GParams p, const double* __restrict__ uvw, const double* __restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = p.W, npl = p.do_wgridding ? W : 1;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t plane_sz = (int64_t)p.nu * p.nv;
   for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; k < nact; k += nwarps) {
     uint32_t idx = sorted_idx[k];
     int64_t row = idx / p.nchan;
@@ -139,12 +138,12 @@ k_degrid_direct(GParams p, const double* __restrict__ uvw, const double* __restr
       int i = cell / W, j = cell - i * W;
       T wuv = sk[warp][0][i] * sk[warp][1][j];
       int iu = wrap(c.iu0 + i, p.nu), iv = wrap(c.iv0 + j, p.nv);
-      const C* g = grid + (int64_t)c.ip0 * plane_sz + (int64_t)iu * p.nv + iv;
       for (int q = 0; q < npl; ++q) {
-        C v = g[q * plane_sz];
+        bool cj;
+        C v = grid[plane_cell(p, c.ip0 + q, iu, iv, cj)];
         T ww = wuv * sk[warp][2][q];
         accr += v.x * ww;
-        acci += v.y * ww;
+        acci += (cj ? -v.y : v.y) * ww;
       }
     }
 #pragma unroll

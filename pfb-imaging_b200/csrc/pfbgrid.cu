@@ -191,6 +191,8 @@ extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
   if (d->nu < d->nx + d->W || d->nv < d->ny + d->W) return fail(PFBG_ERR_ARG, "grid smaller than image + support");
   if (d->nplanes < 1 || (d->do_wgridding && d->nplanes < d->W)) return fail(PFBG_ERR_ARG, "nplanes=%d too small for W=%d", d->nplanes, d->W);
   if (!d->do_wgridding && d->nplanes != 1) return fail(PFBG_ERR_ARG, "nplanes must be 1 without w-gridding");
+  if (d->pmirror < 0 || d->pmirror > 32 || (d->pmirror > 0 && (d->nplanes < d->pmirror || d->w0 != 0.5 * d->dw)))
+    return fail(PFBG_ERR_ARG, "mirror planes need 0 <= pmirror <= min(32, nplanes) and w0 == dw/2");
   if (!d->corr_u || !d->corr_v) return fail(PFBG_ERR_ARG, "missing correction vectors");
   if (d->do_wgridding && (!d->gl_x || !d->gl_w || d->n_gl <= 0 || !(d->dw > 0))) return fail(PFBG_ERR_ARG, "missing quadrature / dw for w-gridding");
   int ndev = 0;
@@ -214,6 +216,7 @@ extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
   g.center_x = d->center_x; g.center_y = d->center_y;
   g.usign = d->usign; g.vsign = d->vsign; g.wsign = d->wsign;
   g.w0 = d->w0; g.dw = d->dw; g.nshift = d->nshift;
+  g.pmirror = d->do_wgridding ? d->pmirror : 0;
   g.ntile_u = d->nu / PFBG_TILE; g.ntile_v = d->nv / PFBG_TILE;
   pl->n_gl = d->n_gl;
 
@@ -434,7 +437,7 @@ static void window_from_flags(const std::vector<int>& f, int size, int& lo, int&
 
 // Re-target a plan to another w-range (same image geometry, sigma, W: corr / dw / nshift unchanged).
 // Lets one plan object serve many snapshots (pfb hci): no reallocation unless the stack must grow.
-extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes) {
+extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes, int32_t pmirror) {
   if (!pl) return fail(PFBG_ERR_ARG, "null plan");
   GParams& g = pl->gp;
   if (!g.do_wgridding) {
@@ -442,6 +445,8 @@ extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes) {
     return PFBG_OK;
   }
   if (nplanes < g.W) return fail(PFBG_ERR_ARG, "nplanes=%d too small for W=%d", nplanes, g.W);
+  if (pmirror < 0 || pmirror > 32 || (pmirror > 0 && (nplanes < pmirror || w0 != 0.5 * g.dw)))
+    return fail(PFBG_ERR_ARG, "mirror planes need 0 <= pmirror <= min(32, nplanes) and w0 == dw/2");
   CK(cudaSetDevice(pl->device));
   const size_t need = (size_t)nplanes * g.nu * g.nv * 2 * real_bytes(pl);
   if (need > pl->grid.bytes) {
@@ -456,6 +461,7 @@ extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes) {
   }
   g.w0 = w0;
   g.nplanes = nplanes;
+  g.pmirror = pmirror;
   pl->bound = false;
   return PFBG_OK;
 }
@@ -668,7 +674,7 @@ extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fsc
   }
   const GParams& g = pl->gp;
   // key width
-  uint64_t maxkey = (uint64_t)g.ntile_u * g.ntile_v * (uint64_t)g.nplanes * (PFBG_TILE * PFBG_TILE);
+  uint64_t maxkey = (uint64_t)g.ntile_u * g.ntile_v * (uint64_t)(g.nplanes + g.pmirror) * (PFBG_TILE * PFBG_TILE);
   int bits = 1;
   while ((1ull << bits) <= maxkey) ++bits;  // inactive key = maxkey needs `bits` bits
   DevBuf &keys_a = pl->srt_ka, &keys_b = pl->srt_kb, &vals_a = pl->srt_va, &vals_b = pl->srt_vb, &tmp = pl->srt_tmp;

@@ -27,7 +27,7 @@ template <> struct __align__(16) VisRec<float> {
   uint32_t idx;       // flat (row, chan) index
   float pc, ps;       // e^{+2 pi i (u x0 + v y0 + w nshift)}
   uint16_t iu, iv;    // wrapped first cell
-  int32_t ip;         // first plane; bit 30 = folded sample (visibility conjugated)
+  int32_t ip;         // first plane + REC_IP_BIAS (it can be negative with mirror planes); bit 30 = folded sample
 };
 template <> struct __align__(16) VisRec<double> {
   double x0[3];
@@ -41,6 +41,8 @@ static_assert(sizeof(VisRec<float>) == 32, "VisRec<float> must be 32 bytes");
 static_assert(sizeof(VisRec<double>) == 64, "VisRec<double> must be 64 bytes");
 
 #define REC_CONJ_BIT 0x40000000
+#define REC_IP_BIAS 64
+__device__ __forceinline__ int origin_plane(uint64_t origin) { return (int)(origin >> 32) - REC_IP_BIAS; }
 __device__ __forceinline__ uint64_t pack_origin(uint32_t iu, uint32_t iv, int32_t ip) {
   return ((uint64_t)(uint32_t)(ip & ~REC_CONJ_BIT) << 32) | ((uint64_t)iu << 16) | (uint64_t)iv;
 }
@@ -63,7 +65,7 @@ __global__ void k_make_recs(GParams p, const double* __restrict__ uvw, const dou
   cis_turns(vis_phase_turns(p, c), r.pc, r.ps);
   r.iu = (uint16_t)wrap(c.iu0, p.nu);
   r.iv = (uint16_t)wrap(c.iv0, p.nv);
-  r.ip = c.ip0 | (c.conj ? REC_CONJ_BIT : 0);
+  r.ip = (c.ip0 + REC_IP_BIAS) | (c.conj ? REC_CONJ_BIT : 0);
   recs[k] = r;
 }
 
@@ -150,20 +152,25 @@ __device__ __forceinline__ void run_flush(const GParams& p, typename cplx_of<T>:
   const int W = p.W, npl = p.do_wgridding ? W : 1;
   int iv = (int)(origin & 0xffffu) + j;
   int iu0 = (int)((origin >> 16) & 0xffffu);
-  int ip = (int)(origin >> 32);
+  int ip = origin_plane(origin);
   if (iv >= p.nv) iv -= p.nv;
   const int plane_sz = p.nu * p.nv;  // < 2^31 (nu, nv <= 32768 enforced by the host)
   const bool jok = j < W;
-  if (W == 8 && npl == 8 && iu0 + 8 <= p.nu) {
-    // common case: every lane owns live cells and the 8 rows do not wrap -> one pointer, constant stride
-    typename cplx_of<T>::type* g = grid + (int64_t)(ip + q2) * plane_sz + (int64_t)iu0 * p.nv + iv;
+  if (W == 8 && npl == 8 && iu0 >= 1 && iu0 + 8 <= p.nu) {
+    // common case: every lane owns live cells and the 8 rows do not wrap -> one pointer, constant stride.
+    // Mirror planes (pl < 0) walk the mirrored rows of plane -pl-1 backwards, conjugated.
+    const int mv = iv ? p.nv - iv : 0;
 #pragma unroll
     for (int qq = 0; qq < 2; ++qq) {
-      typename cplx_of<T>::type* gq = g + (int64_t)(4 * qq) * plane_sz;
+      const int pl = ip + q2 + 4 * qq;
+      const bool mir = pl < 0;
+      typename cplx_of<T>::type* gq = grid + (mir ? (int64_t)(-pl - 1) * plane_sz + (int64_t)(p.nu - iu0) * p.nv + mv
+                                                  : (int64_t)pl * plane_sz + (int64_t)iu0 * p.nv + iv);
+      const int step = mir ? -p.nv : p.nv;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        atomic_add_c(gq, acc[i][qq].x, acc[i][qq].y);
-        gq += p.nv;
+        atomic_add_c(gq, acc[i][qq].x, mir ? -acc[i][qq].y : acc[i][qq].y);
+        gq += step;
         acc[i][qq].x = 0;
         acc[i][qq].y = 0;
       }
@@ -174,13 +181,14 @@ __device__ __forceinline__ void run_flush(const GParams& p, typename cplx_of<T>:
   for (int qq = 0; qq < 2; ++qq) {
     int q = q2 + 4 * qq;
     bool ok = jok && q < npl;
-    typename cplx_of<T>::type* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (ok && i < W) {
         int iu = iu0 + i;
         if (iu >= p.nu) iu -= p.nu;
-        atomic_add_c(gq + iu * p.nv, acc[i][qq].x, acc[i][qq].y);
+        bool cj;
+        typename cplx_of<T>::type* g = grid + plane_cell(p, ip + q, iu, iv, cj);
+        atomic_add_c(g, acc[i][qq].x, cj ? -acc[i][qq].y : acc[i][qq].y);
       }
       acc[i][qq].x = 0;
       acc[i][qq].y = 0;
@@ -196,19 +204,25 @@ __device__ __forceinline__ void run_fetch(const GParams& p, const typename cplx_
   const int W = p.W, npl = p.do_wgridding ? W : 1;
   int iv = (int)(origin & 0xffffu) + j;
   int iu0 = (int)((origin >> 16) & 0xffffu);
-  int ip = (int)(origin >> 32);
+  int ip = origin_plane(origin);
   if (iv >= p.nv) iv -= p.nv;
   const int plane_sz = p.nu * p.nv;
   const bool jok = j < W;
-  if (W == 8 && npl == 8 && iu0 + 8 <= p.nu) {
-    const C* g = grid + (int64_t)(ip + q2) * plane_sz + (int64_t)iu0 * p.nv + iv;
+  if (W == 8 && npl == 8 && iu0 >= 1 && iu0 + 8 <= p.nu) {
+    const int mv = iv ? p.nv - iv : 0;
 #pragma unroll
     for (int qq = 0; qq < 2; ++qq) {
-      const C* gq = g + (int64_t)(4 * qq) * plane_sz;
+      const int pl = ip + q2 + 4 * qq;
+      const bool mir = pl < 0;
+      const C* gq = grid + (mir ? (int64_t)(-pl - 1) * plane_sz + (int64_t)(p.nu - iu0) * p.nv + mv
+                                : (int64_t)pl * plane_sz + (int64_t)iu0 * p.nv + iv);
+      const int step = mir ? -p.nv : p.nv;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        gv[i][qq] = *gq;
-        gq += p.nv;
+        C val = *gq;
+        if (mir) val.y = -val.y;
+        gv[i][qq] = val;
+        gq += step;
       }
     }
     return;
@@ -217,14 +231,15 @@ __device__ __forceinline__ void run_fetch(const GParams& p, const typename cplx_
   for (int qq = 0; qq < 2; ++qq) {
     int q = q2 + 4 * qq;
     bool ok = jok && q < npl;
-    const C* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       C val; val.x = 0; val.y = 0;
       if (ok && i < W) {
         int iu = iu0 + i;
         if (iu >= p.nu) iu -= p.nu;
-        val = gq[iu * p.nv];
+        bool cj;
+        val = grid[plane_cell(p, ip + q, iu, iv, cj)];
+        if (cj) val.y = -val.y;
       }
       gv[i][qq] = val;
     }
@@ -476,7 +491,7 @@ __device__ __forceinline__ void wide_flush(const GParams& p, typename cplx_of<T>
   const int W = p.W, npl = p.do_wgridding ? W : 1;
   int iv = (int)(origin & 0xffffu) + j;
   int iu0 = (int)((origin >> 16) & 0xffffu);
-  int ip = (int)(origin >> 32);
+  int ip = origin_plane(origin);
   if (iv >= p.nv) iv -= p.nv;
   const int plane_sz = p.nu * p.nv;
   const bool jok = j < W;
@@ -484,14 +499,15 @@ __device__ __forceinline__ void wide_flush(const GParams& p, typename cplx_of<T>
   for (int qq = 0; qq < NQ; ++qq) {
     const int q = q2 + 2 * qq;
     const bool ok = jok && q < npl;
-    typename cplx_of<T>::type* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
 #pragma unroll
     for (int ii = 0; ii < RPW; ++ii) {
       const int i = row0 + ii;
       if (ok && i < W) {
         int iu = iu0 + i;
         if (iu >= p.nu) iu -= p.nu;
-        atomic_add_c(gq + iu * p.nv, accr[ii][qq], acci[ii][qq]);
+        bool cj;
+        typename cplx_of<T>::type* g = grid + plane_cell(p, ip + q, iu, iv, cj);
+        atomic_add_c(g, accr[ii][qq], cj ? -acci[ii][qq] : acci[ii][qq]);
       }
       accr[ii][qq] = 0;
       acci[ii][qq] = 0;
@@ -657,14 +673,13 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
           cur = org;
           int iv = (int)(org & 0xffffu) + j;
           int iu0 = (int)((org >> 16) & 0xffffu);
-          int ip = (int)(org >> 32);
+          int ip = origin_plane(org);
           if (iv >= p.nv) iv -= p.nv;
           const bool jok = j < W;
 #pragma unroll
           for (int qq = 0; qq < NQ; ++qq) {
             const int q = q2 + 2 * qq;
             const bool ok = jok && q < npl;
-            const C* gq = grid + (int64_t)(ip + q) * plane_sz + iv;
 #pragma unroll
             for (int ii = 0; ii < RPW; ++ii) {
               const int i = row0 + ii;
@@ -672,7 +687,9 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
               if (ok && i < W) {
                 int iu = iu0 + i;
                 if (iu >= p.nu) iu -= p.nu;
-                val = gq[iu * p.nv];
+                bool cj;
+                val = grid[plane_cell(p, ip + q, iu, iv, cj)];
+                if (cj) val.y = -val.y;
               }
               gr[ii][qq] = val.x; gi[ii][qq] = val.y;
             }

@@ -120,6 +120,7 @@ class Plan:
     gl_x: np.ndarray = field(repr=False)  # nodes on [0,1] for psihat_w on device
     gl_w: np.ndarray = field(repr=False)
     est_cost: float = 0.0
+    pmirror: int = 0  # virtual planes below plane 0 served by Hermitian mirroring (then w0 == dw/2)
 
     @property
     def real_bytes(self) -> int:
@@ -131,6 +132,13 @@ class Plan:
             W=self.W, beta=self.beta, sigma=self.sigma, nplanes=self.nplanes,
             w0=self.w0, dw=self.dw, nshift=self.nshift, kernel_err=self.kernel_err,
         )
+
+
+def _mirror_planes(wmax, dw, W):
+    """Planes needed when they sit at (p + 1/2) dw and the ones below zero are mirrored: the highest sample's
+    first plane is floor(wmax/dw - 1/2 - W/2) + 1 (one plane of slack for rounding in the fp64 division)."""
+    top = int(math.floor(wmax / dw - 0.5 - 0.5 * W)) + 1
+    return max(top + W + 1, W, (W + 2) // 2)
 
 
 def w_range(uvw, freq, wsign=1.0):
@@ -193,7 +201,7 @@ def make_plan(
     *, nx, ny, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
     flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
     sigma_min=1.1, sigma_max=2.6, precision="double", wmin=0.0, wmax=0.0, nvis=0,
-    force_sigma=None, force_W=None, safety=None,
+    force_sigma=None, force_W=None, safety=None, mirror=True,
 ) -> Plan:
     """Choose (sigma, W, beta, nu, nv, planes) for one gridder geometry."""
     nx, ny = int(nx), int(ny)
@@ -210,6 +218,8 @@ def make_plan(
     if epsilon < 1e-13:
         raise ValueError("epsilon too small for double precision")
 
+    if wmin < 0.0 or wmax < wmin:  # the kernels fold w < 0 onto w > 0: the planes cover |w|
+        wmin, wmax = (0.0 if wmin * wmax <= 0.0 else min(abs(wmin), abs(wmax))), max(abs(wmin), abs(wmax))
     cx = -center_x if flip_u else center_x
     cy = -center_y if flip_v else center_y
     usign = -1.0 if flip_u else 1.0
@@ -264,6 +274,8 @@ def make_plan(
         if do_wgridding and wmax > wmin:
             dw = 1.0 / (2.0 * s * numax)
             npl = int(math.ceil((wmax - wmin) / dw)) + W
+            if mirror:
+                npl = min(npl, _mirror_planes(wmax, dw, W))
         elif do_wgridding:
             dw = 1.0 / (2.0 * s * numax)
             npl = W
@@ -282,9 +294,19 @@ def make_plan(
         )
     cost, s, W, beta, err, nu, nv, dw, npl, sig_eff = best
 
+    pmirror = 0
     if do_wgridding:
-        # plane p sits at w0 + p*dw; the lowest sample's support starts at plane 0
-        w0 = 0.5 * (wmin + wmax) - 0.5 * (npl - 1) * dw
+        npl_std = (int(math.ceil((wmax - wmin) / dw)) + W) if wmax > wmin else W
+        if mirror and wmax > wmin and _mirror_planes(wmax, dw, W) < npl_std:
+            # |w| reaches down to ~0: put the planes at (p + 1/2) dw and serve the W/2 planes below zero through
+            # the Hermitian mirror of planes 0..W/2-1 instead of storing and transforming them
+            w0 = 0.5 * dw
+            npl = _mirror_planes(wmax, dw, W)
+            pmirror = (W + 2) // 2
+        else:
+            # plane p sits at w0 + p*dw; the lowest sample's support starts at plane 0
+            npl = npl_std
+            w0 = 0.5 * (wmin + wmax) - 0.5 * (npl - 1) * dw
     else:
         w0 = 0.0
 
@@ -297,5 +319,5 @@ def make_plan(
         usign=usign, vsign=vsign, wsign=wsign, do_wgridding=bool(do_wgridding),
         divide_by_n=bool(divide_by_n), epsilon=float(epsilon), kernel_err=float(err),
         corr_u=_correction(nx, nu, W, beta), corr_v=_correction(ny, nv, W, beta),
-        gl_x=gl_x, gl_w=gl_w, est_cost=float(cost),
+        gl_x=gl_x, gl_w=gl_w, est_cost=float(cost), pmirror=int(pmirror),
     )

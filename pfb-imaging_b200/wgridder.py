@@ -52,6 +52,7 @@ class GridderPlan:
             w0=plan.w0, dw=plan.dw, nshift=plan.nshift,
             corr_u=self._keep[0].ctypes.data, corr_v=self._keep[1].ctypes.data,
             gl_x=self._keep[2].ctypes.data, gl_w=self._keep[3].ctypes.data, n_gl=len(self._keep[2]),
+            pmirror=int(getattr(plan, "pmirror", 0)),
         )
         _lib.check(self._lib.pfbg_plan_create(C.byref(d), C.byref(self._h)))
         self.nrow = self.nchan = 0
@@ -285,7 +286,7 @@ def plan_for(uvw, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, c
         free = _POOL.get(key)
         if free:
             gp = free.pop()
-            _lib.check(gp._lib.pfbg_plan_set_wrange(gp._h, p.w0, p.nplanes))
+            _lib.check(gp._lib.pfbg_plan_set_wrange(gp._h, p.w0, p.nplanes, int(p.pmirror)))
             gp.plan = p
         else:
             gp = GridderPlan(p, device=dev)

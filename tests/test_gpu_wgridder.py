@@ -337,8 +337,11 @@ def test_hermitian_fold_of_negative_w(gpu):
                     flip_v=True, divide_by_n=False) as gp:
         wabs = np.abs(p["uvw"][:, 2:3]) * p["freq"][None, :] / 299792458.0
         lo, hi = gp.plan.w0, gp.plan.w0 + (gp.plan.nplanes - 1) * gp.plan.dw
-        assert lo <= wabs.min() and hi >= wabs.max()
-        assert gp.plan.nplanes == int(np.ceil((wabs.max() - wabs.min()) / gp.plan.dw)) + gp.plan.W
+        assert hi >= wabs.max() and gp.plan.nplanes <= int(np.ceil((wabs.max() - wabs.min()) / gp.plan.dw)) + gp.plan.W
+        if gp.plan.pmirror:  # planes at (p + 1/2) dw; those below zero are mirrors of planes 0..pmirror-1
+            assert lo == 0.5 * gp.plan.dw
+        else:
+            assert lo <= wabs.min()
 
 
 def test_full_size_properties_c2_band(gpu):

@@ -81,7 +81,12 @@ def test_bin_indices_invariants():
     assert b["idx"].size == int((p["mask"] != 0).sum())
     x = b["iu0"] + np.arange(plan.W)[:, None] - b["gu"]
     assert (np.abs(x) <= plan.W / 2 + 1e-9).all()
-    assert b["ip0"].min() >= 0 and b["ip0"].max() <= plan.nplanes - plan.W
+    # mirror planes: supports may reach below plane 0 (served by the Hermitian mirror), never clamped
+    assert b["ip0"].min() >= -plan.pmirror and b["ip0"].max() <= plan.nplanes - plan.W
+    xw = b["ip0"] + np.arange(plan.W)[:, None] - b["gw"]
+    assert (np.abs(xw) <= plan.W / 2 + 1e-9).all()
+    std = wg.bin_indices(_plan(p, 1e-5, mirror=False), p["uvw"], p["freq"], p["mask"])
+    assert std["ip0"].min() >= 0
     assert (np.diff(b["key"][b["order"]].astype(np.int64)) >= 0).all()
 
 

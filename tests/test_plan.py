@@ -39,10 +39,18 @@ def test_plan_meets_epsilon(prec, eps):
     assert p.nplanes >= p.W
     if prec == "single":
         assert p.W <= 8
-    # every sample's support fits in the plane stack
-    for w in (-2e4, 2e4):
+    # every sample's support fits in the plane stack (|w| in [0, 2e4] after the Hermitian fold; planes below
+    # zero are served by the mirror of planes 0..pmirror-1)
+    assert p.pmirror > 0 and p.w0 == 0.5 * p.dw and p.pmirror <= p.nplanes
+    for w in (0.0, 1.0, 2e4):
         ip0 = np.floor((w - p.w0) / p.dw - 0.5 * p.W) + 1
-        assert 0 <= ip0 <= p.nplanes - p.W
+        assert -p.pmirror <= ip0 <= p.nplanes - p.W
+    q = make_plan(nx=4096, ny=4096, pixsize_x=5.5e-6, pixsize_y=5.5e-6, epsilon=eps, precision=prec,
+                  wmin=1.9e6, wmax=2e6, nvis=25_000_000, flip_v=True, divide_by_n=False, sigma_max=3.0)
+    assert q.pmirror == 0  # far from w = 0 nothing is mirrored
+    for w in (1.9e6, 2e6):
+        ip0 = np.floor((w - q.w0) / q.dw - 0.5 * q.W) + 1
+        assert 0 <= ip0 <= q.nplanes - q.W
     assert p.vsign == -1.0 and p.usign == 1.0
 
 
