@@ -202,7 +202,7 @@ def run_ours(args, cfg):
                         mask=d["mask"], sigma_min=1.1, sigma_max=3.0, device=local)
         gp.bind_weights(d["wgt"])
         x_d = torch.from_numpy(x).to(dev)
-        bands.append(dict(b=b, d=d, cell=cell, x=x, gp=gp, x_d=x_d, out_d=torch.empty_like(x_d),
+        bands.append(dict(b=b, d=d, cell=cell, x=x, gp=gp, x_d=x_d, out_d=torch.empty_like(x_d), info=gp.info(),
                           wsum=float(d["wgt"].sum(dtype=np.float64)), nvis=d["uvw"].shape[0] * d["freq"].size))
     nvis_local = sum(bd["nvis"] for bd in bands)
     stream = torch.cuda.current_stream().cuda_stream
@@ -307,13 +307,16 @@ def run_ours(args, cfg):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         nchan = cfg["nchan"]
         # SURVEY §8(d) byte model summed over rank 0's bands (plans differ slightly per band; use band-0-of-rank plan)
-        B = sum(algorithmic_bytes(info, bd["nvis"], nchan, p) for bd in bands)
+        B = sum(algorithmic_bytes(bd["info"], bd["nvis"], nchan, p) for bd in bands)
+        # the same model with the plane count a stack WITHOUT mirror planes needs for the same |w| range (what a
+        # ducc0-style gridder transforms): the work this implementation removed still counts there
+        B_std = sum(algorithmic_bytes(dict(bd["info"], nplanes=bd["info"]["nplanes_std"]), bd["nvis"], nchan, p) for bd in bands)
         kernel_phase = {"spread": "k_grid_runs (spreading kernel)", "degrid": "k_degrid_runs (gathering kernel)",
                         "pad_screen_fft": "k_rows_fwd + k_cols_fwd (fused pad/screen/FFT)",
                         "fft_crop_screen": "k_cols_inv + k_rows_inv (fused FFT/screen/crop)"}
         dom = max(kernel_phase, key=lambda k: phases.get(k, 0.0))
         # roofline of the gridding (spreading) kernel, the hand-written kernel SURVEY §8(d) models per sample
-        kb = sum(spread_kernel_bytes(info, bd["nvis"], nchan, p) for bd in bands) / len(bands)
+        kb = sum(spread_kernel_bytes(bd["info"], bd["nvis"], nchan, p) for bd in bands) / len(bands)
         k_ms = phases.get("spread", float("nan")) / len(bands)
         traffic = None
         try:  # measured DRAM bytes per launch from the committed ncu --set full capture of this workload
@@ -327,9 +330,11 @@ def run_ours(args, cfg):
             "achieved": kb / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": kb / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": kb,
-            "note": "run kernels are issue-bound (ncu: DRAM throughput ~5 %, issue slots ~75 %); the plane stack stays L2-resident",
+            "note": "run kernels are issue / FMA-pipe bound (ncu: DRAM throughput ~7 %, issue slots ~56 %, FMA pipe ~50 %); the plane stack stays L2-resident; algorithmic bytes use the plan's own plane count (mirror planes are not counted)",
             "step_algorithmic_bytes_rank0": B, "step_achieved_rank0": B / (my_ms * 1e-3) / 1e9,
             "step_frac": B / (my_ms * 1e-3) / 1e9 / peak, "step_frac_of_nominal_8TBs": B / (my_ms * 1e-3) / 1e9 / 8000.0,
+            "step_frac_unmirrored_planes": B_std / (my_ms * 1e-3) / 1e9 / peak,
+            "planes_per_band": {str(bd["b"]): [bd["info"]["nplanes"], bd["info"]["nplanes_std"]] for bd in bands},
             "dominant_phase": dom, "dominant_phase_kernels": kernel_phase[dom], "phases_ms_rank0": phases,
             "ms_per_band_rank0": per_band,
         }
@@ -351,7 +356,7 @@ def run_ours(args, cfg):
                        "strong_scaling_bound_one_job": round(sum(per_band.values()) / max(per_band.values()), 2),
                        "nvis_total": int(nvis_all.item()),
                        "l2": "inputs larger than L2 (plane stack %.1f GB per band)" % (info["grid_bytes"] / 1e9),
-                       "plan_first_band": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "beta")},
+                       "plan_first_band": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "nplanes_std", "pmirror", "beta")},
                        "parallelism": (f"{nbands} bands of one job LPT-partitioned over {world} GPU(s)" if strong else
                                        f"{world} job(s) of {nbands} band(s), one job per GPU") + ", no data-path collective"},
             "e2e": {"value": e2e_value, "unit": "Mvis/s", "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,

@@ -121,6 +121,7 @@ class Plan:
     gl_w: np.ndarray = field(repr=False)
     est_cost: float = 0.0
     pmirror: int = 0  # virtual planes below plane 0 served by Hermitian mirroring (then w0 == dw/2)
+    nplanes_std: int = 0  # planes a stack without mirroring would need for the same |w| range (reporting only)
 
     @property
     def real_bytes(self) -> int:
@@ -131,6 +132,7 @@ class Plan:
             precision=self.precision, nx=self.nx, ny=self.ny, nu=self.nu, nv=self.nv,
             W=self.W, beta=self.beta, sigma=self.sigma, nplanes=self.nplanes,
             w0=self.w0, dw=self.dw, nshift=self.nshift, kernel_err=self.kernel_err,
+            pmirror=self.pmirror, nplanes_std=self.nplanes_std,
         )
 
 
@@ -320,4 +322,5 @@ def make_plan(
         divide_by_n=bool(divide_by_n), epsilon=float(epsilon), kernel_err=float(err),
         corr_u=_correction(nx, nu, W, beta), corr_v=_correction(ny, nv, W, beta),
         gl_x=gl_x, gl_w=gl_w, est_cost=float(cost), pmirror=int(pmirror),
+        nplanes_std=int(npl_std if do_wgridding else 1),
     )
