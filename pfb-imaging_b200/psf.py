@@ -69,6 +69,11 @@ class PsfConvolver:
             res[...] = tmp
         return res
 
+    def apply_dev(self, x_ptr, out_ptr, beam_ptr=None, eta=None, stream=None):
+        """Same operator on device pointers (asynchronous on `stream`): what the device-resident deconvolution loops call."""
+        _lib.check(self._lib.pfbg_conv_apply(self._h, C.c_void_p(int(x_ptr)), None if beam_ptr is None else C.c_void_p(int(beam_ptr)),
+                                             float(eta) if eta else 0.0, C.c_void_p(int(out_ptr)), _lib.DEVICE_PTRS, stream))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.pfbg_conv_destroy(self._h)
@@ -190,3 +195,35 @@ class HessPSF:
     def close(self):
         for c in self.conv:
             c.close()
+
+
+class PsfGradient:
+    """Gradient of the smooth term of the deconvolution sub-problem, ``grad(x) = hess(x) - dirty`` with the
+    PSF-convolution Hessian (the `grad` callables built in ``core/sara.py:300-340`` / ``deconv`` presets), usable both as
+    the reference's numpy callable and, through ``device_apply``, inside the device-resident loops of
+    ``pfb_imaging_b200.sara`` (no host round trip per iteration)."""
+
+    def __init__(self, hess: HessPSF, dirty):
+        self.hess = hess
+        self.dirty = np.ascontiguousarray(dirty, dtype=np.float64)
+        if self.dirty.shape != (hess.nband, hess.nx, hess.ny):
+            raise ValueError("dirty must have shape (nband, nx, ny)")
+        self._dev = None
+
+    def __call__(self, x):
+        return self.hess.dot(x) - self.dirty
+
+    def device_apply(self, x_t, out_t):
+        import torch
+
+        if self._dev is None:
+            dev = x_t.device
+            self._dev = dict(dirty=torch.from_numpy(self.dirty).to(dev),
+                             beam=[None if b is None else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(dev)
+                                   for b in self.hess.beam])
+        s = torch.cuda.current_stream(x_t.device).cuda_stream
+        for b in range(self.hess.nband):
+            bm = self._dev["beam"][b]
+            self.hess.conv[b].apply_dev(x_t[b].data_ptr(), out_t[b].data_ptr(), None if bm is None else bm.data_ptr(),
+                                        float(self.hess.eta[b]), s)
+        out_t -= self._dev["dirty"]

@@ -281,3 +281,40 @@ def test_l1_reweighting_matches_formula():
     rms = np.array([np.std(tot_u[i][tot_u[i] != 0]) for i in range(2)])
     tot_m = sum(so.psi_dot(model[b], bk, fbs, transposed=True) for b in range(nband))
     np.testing.assert_allclose(w, so.l1reweight(tot_m, 0.7, rms, 2.0), rtol=1e-9)
+
+
+def test_primal_dual_with_device_psf_hessian_gradient():
+    """pfb sara's inner problem: grad(x) = HessPSF(x) - dirty.  The device-resident loop (no host round trips) must
+    equal the same loop driven through the numpy callable."""
+    from pfb_imaging_b200.psf import HessPSF, PsfGradient
+    from pfb_imaging_b200.sara import L21, PrimalDual, PsiNocopyt
+
+    nband, nx, ny = 2, 96, 80
+    nxp, nyp = 144, 120
+    rng = np.random.default_rng(21)
+    psf = np.zeros((nband, nxp, nyp))
+    yy, xx = np.meshgrid(np.arange(nyp) - nyp // 2, np.arange(nxp) - nxp // 2)
+    for b in range(nband):
+        psf[b] = np.exp(-(xx ** 2 + yy ** 2) / (2.0 * (2.0 + b) ** 2))
+    psf /= psf.sum(axis=(1, 2), keepdims=True)
+    abspsf = np.abs(np.fft.rfft2(np.fft.ifftshift(psf, axes=(1, 2)), axes=(1, 2)))
+    truth = np.zeros((nband, nx, ny))
+    truth[:, 40, 30] = 3.0
+    truth[:, 60:66, 50:58] = 1.0
+    hess = HessPSF(nx, ny, abspsf, beam=None, eta=0.01)
+    dirty = hess.dot(truth) + 1e-3 * rng.standard_normal(truth.shape)
+    bases = ["self", "db1", "db2"]
+    sols = []
+    for use_dev in (False, True):
+        psi = PsiNocopyt(nband, nx, ny, bases, 2, 1)
+        reg = L21(psi, bases, nu=len(bases))
+        grad = PsfGradient(hess, dirty)
+        if not use_dev:
+            grad = (lambda g: (lambda x: g(x)))(grad)  # plain numpy callable: no device_apply attribute
+        pd = PrimalDual(tol=1e-14, maxit=20, verbosity=0, positivity=1)
+        pd.setup(reg, 1.0 + 0.01)
+        pd.set_grad(grad)
+        sols.append(pd.solve(np.zeros_like(dirty), 1e-3))
+    np.testing.assert_allclose(sols[1], sols[0], rtol=0, atol=1e-12)
+    assert np.abs(sols[1]).max() > 0.1
+    hess.close()
