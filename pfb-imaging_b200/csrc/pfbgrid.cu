@@ -859,7 +859,7 @@ static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_
     LAUNCHED();
     CK(cudaGetLastError());
   } else if (pl->nactive > 0 && pl->use_runs) {
-    k_degrid_runs<T><<<run_blocks(pl, pl->nactive, DEG_WARPS, 4), DEG_WARPS * 32, 0, s>>>(
+    k_degrid_runs<T><<<run_blocks(pl, pl->nactive, DEG_WARPS, 5), DEG_WARPS * 32, 0, s>>>(
         pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
         (C*)out_sorted, apply_phase);
     LAUNCHED();

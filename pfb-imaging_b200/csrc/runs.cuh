@@ -262,7 +262,7 @@ __device__ __forceinline__ uint32_t run_starts(uint64_t org, uint64_t cur, int l
 // kernel 2: gridding by runs
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(RUN_WARPS * 32)
+__global__ void __launch_bounds__(RUN_WARPS * 32, (sizeof(T) == 4 ? 3 : 1))  // fp32: <= 80 registers, 3 CTAs / SM
 k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
             const typename cplx_of<T>::type* __restrict__ vis, int64_t vis_rs, int64_t vis_cs,
             const T* __restrict__ wgt, typename cplx_of<T>::type* __restrict__ grid, int vis_sorted,
