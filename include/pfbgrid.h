@@ -130,6 +130,15 @@ int pfbg_bin_dump(pfbg_plan* plan, int32_t* iu0, int32_t* iv0, int32_t* ip0, uin
 int pfbg_grid(pfbg_plan* plan, const void* vis, int64_t vis_rs, int64_t vis_cs, const void* wgt,
               void* dirty, uint32_t flags, void* stream);
 
+/*
+ * PSF of an off-centre field (operators/gridder.py:616-629, 877-911; utils/stokes2im.py:483-486):
+ * grids vis[r,c] = exp(sign * 2 pi i f_c/c0 (u x0 + v y0 - w (n0 - 1))), n0 = sqrt(1 - x0^2 - y0^2), with the
+ * unflipped bound u, v, w.  The visibilities are generated on the device (the reference materialises an
+ * (nrow, nchan) complex128 array on the host); sign = +1 at the gridder.py call sites, -1 at stokes2im.py's.
+ */
+int pfbg_grid_psf(pfbg_plan* plan, double x0, double y0, double sign, const void* wgt, void* dirty,
+                  uint32_t flags, void* stream);
+
 /* Kernel 3 (+4, cuFFT): vis (nrow,nchan) contiguous = R dirty; masked samples are zeroed. */
 int pfbg_degrid(pfbg_plan* plan, const void* dirty, void* vis, const void* wgt, uint32_t flags,
                 void* stream);

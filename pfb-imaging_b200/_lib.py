@@ -64,6 +64,7 @@ SIGNATURES = {
     "pfbg_bind_weights": (C.c_int, [_vp, _vp, _u32, _vp]),
     "pfbg_bin_dump": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pfbg_grid": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _u32, _vp]),
+    "pfbg_grid_psf": (C.c_int, [_vp, _dbl, _dbl, _dbl, _vp, _vp, _u32, _vp]),
     "pfbg_degrid": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _vp]),
     "pfbg_hessian": (C.c_int, [_vp, _vp, _vp, _dbl, _dbl, _vp, _u32, _vp]),
     "pfbg_set_profiling": (C.c_int, [_vp, _i32]),

@@ -277,6 +277,24 @@ k_grid2img(GParams p, const typename cplx_of<T>::type* __restrict__ grid, const 
   out[pix] = (T)r;
 }
 
+// PSF visibilities of an off-centre field (operators/gridder.py:616-622, 877-884; utils/stokes2im.py:483-486):
+//   vis[r,c] = exp(sign 2 pi i f_c/c0 (u x0 + v y0 - w (n0 - 1)))      with the UNFLIPPED u, v, w
+// generated on the device from the bound uvw (never materialised or copied from the host).
+template <typename T>
+__global__ void k_psf_ramp(const double* __restrict__ uvw, const double* __restrict__ fscale, int64_t nvis, int nchan,
+                           double x0, double y0, double nm1_0, double sign, typename cplx_of<T>::type* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nvis) return;
+  const int64_t row = k / nchan;
+  const int chan = (int)(k - row * nchan);
+  const double t = sign * fscale[chan] * (uvw[3 * row] * x0 + uvw[3 * row + 1] * y0 - uvw[3 * row + 2] * nm1_0);
+  T c, sn;
+  cis_turns(t, c, sn);
+  typename cplx_of<T>::type o;
+  o.x = c; o.y = sn;
+  out[k] = o;
+}
+
 // small utility kernels -----------------------------------------------------
 template <typename C>
 __global__ void k_zero_vis(C* __restrict__ v, int64_t n) {

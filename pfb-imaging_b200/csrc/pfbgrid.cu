@@ -1028,6 +1028,44 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
   return PFBG_OK;
 }
 
+extern "C" int pfbg_grid_psf(pfbg_plan* pl, double x0, double y0, double sign, const void* wgt, void* dirty,
+                             uint32_t flags, void* stream) {
+  if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
+  if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (x0 * x0 + y0 * y0 >= 1.0) return fail(PFBG_ERR_ARG, "phase centre outside the unit sphere");
+  CK(cudaSetDevice(pl->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = real_bytes(pl);
+  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  pl->n_ev = 0;
+  mark(pl, s);
+  const void* dwgt = wgt;
+  if (wgt && !dev && pl->nvis > 0) CKRC(fetch(pl, pl->wgt_stage, wgt, (size_t)pl->nvis * rb, false, s, &dwgt));
+  if (!dwgt && pl->has_wgt) dwgt = pl->wgt.p;
+  if (pl->nvis > 0) {
+    CKRC(dev_alloc(pl, pl->vis_stage, (size_t)pl->nvis * 2 * rb));
+    const double r2 = x0 * x0 + y0 * y0, nm1_0 = -r2 / (sqrt(1.0 - r2) + 1.0);
+    const unsigned grd = (unsigned)((pl->nvis + 255) / 256);
+    if (pl->precision == PFBG_F32)
+      k_psf_ramp<float><<<grd, 256, 0, s>>>((const double*)pl->uvw.p, (const double*)pl->fscale.p, pl->nvis, pl->gp.nchan, x0, y0, nm1_0, sign, (float2*)pl->vis_stage.p);
+    else
+      k_psf_ramp<double><<<grd, 256, 0, s>>>((const double*)pl->uvw.p, (const double*)pl->fscale.p, pl->nvis, pl->gp.nchan, x0, y0, nm1_0, sign, (double2*)pl->vis_stage.p);
+    LAUNCHED();
+  }
+  mark(pl, s);
+  CKRC(zero_planes(pl, s));
+  CKRC(DISPATCH(run_spread, pl, s, pl->vis_stage.p, (int64_t)pl->gp.nchan, (int64_t)1, dwgt, 0, 1));
+  mark(pl, s);
+  void* dout = dirty;
+  if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
+  CKRC(planes_to_image(pl, s, nullptr, nullptr, 1.0, 0.0, dout));
+  mark(pl, s);
+  if (!dev) CKRC(d2h_staged(pl, dirty, dout, img_bytes, s));
+  mark(pl, s);
+  return PFBG_OK;
+}
+
 extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const void* wgt, uint32_t flags,
                            void* stream) {
   if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");

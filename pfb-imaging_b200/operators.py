@@ -269,22 +269,16 @@ def image_data_products_arrays(uvw, freq, vis, wgt, mask, nx, ny, nx_psf, ny_psf
         out["dirty"] = dirty
     if do_psf:
         nrow, nchan = uvw.shape[0], freq.size
-        if x0 or y0:
-            # gridder.py:616-622 (sign +2j as written there)
-            signu = -1.0 if flip_u else 1.0
-            signv = -1.0 if flip_v else 1.0
-            signx = -1.0 if flip_u else 1.0
-            signy = -1.0 if flip_v else 1.0
-            n = np.sqrt(1 - x0**2 - y0**2)
-            freqfactor = 2j * np.pi * freq[None, :] / 299792458.0
-            psf_vis = np.exp(freqfactor * (signu * uvw[:, 0:1] * x0 * signx + signv * uvw[:, 1:2] * y0 * signy
-                                           - uvw[:, 2:] * (n - 1)))
-        else:
-            psf_vis = np.broadcast_to(np.ones((1,), dtype=np.complex128), (nrow, nchan))
         psf = np.zeros((ncorr, nx_psf, ny_psf), dtype=float)
         with plan_for(uvw, freq, npix_x=nx_psf, npix_y=ny_psf, precision="double", mask=mask, **common) as gp:
             for c in range(ncorr):
-                gp.grid(psf_vis, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c])
+                if x0 or y0:
+                    # gridder.py:616-622 (sign +2j as written there; the flips cancel: signu * signx = 1); the
+                    # phase ramp is generated on the device from the bound uvw instead of an (nrow, nchan) host array
+                    gp.grid_psf(x0, y0, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c], sign=1.0)
+                else:
+                    ones = np.broadcast_to(np.ones((1,), dtype=np.complex128), (nrow, nchan))
+                    gp.grid(ones, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c])
         out["psf"] = psf
         out["psfhat"] = np.fft.rfft2(np.fft.ifftshift(psf, axes=(1, 2)), axes=(1, 2))
     return out
@@ -353,16 +347,14 @@ def grid_partition(part, counts, nx, ny, nx_psf, ny_psf, cell_rad, robustness=No
     with plan_for(uvw, freq, npix_x=nx, npix_y=ny, **common) as gp:
         for c in range(ncorr):
             gp.grid(np.require(vis[c], dtype=np.complex128), wgt=np.require(wgt[c], dtype=np.float64), dirty=dirty[c])
-    if x0 or y0:
-        freqfactor = 2j * np.pi * freq[None, :] / 299792458.0  # sign as written at gridder.py:878
-        psf_vis = np.exp(freqfactor * (signu * uvw[:, 0:1] * x0 * signx + signv * uvw[:, 1:2] * y0 * signy
-                                       - uvw[:, 2:] * (n - 1)))
-    else:
-        psf_vis = np.broadcast_to(np.ones((1,), dtype=np.complex128), (uvw.shape[0], freq.size))
     psf = np.zeros((ncorr, nx_psf, ny_psf), dtype=float)
     with plan_for(uvw, freq, npix_x=nx_psf, npix_y=ny_psf, **common) as gp:
         for c in range(ncorr):
-            gp.grid(psf_vis, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c])
+            if x0 or y0:  # phase ramp generated on the device; sign as written at gridder.py:878
+                gp.grid_psf(x0, y0, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c], sign=1.0)
+            else:
+                ones = np.broadcast_to(np.ones((1,), dtype=np.complex128), (uvw.shape[0], freq.size))
+                gp.grid(ones, wgt=np.require(wgt[c], dtype=np.float64), dirty=psf[c])
     psfhat = np.fft.rfft2(np.fft.ifftshift(psf, axes=(1, 2)), axes=(1, 2))  # r2c, forward, unnormalised (:912)
     out = {"DIRTY": dirty, "PSF": psf, "PSFHAT": psfhat, "BEAM": beam, "WSUM": wsum, "WEIGHT": wgt}
     if fit_psf is not None:

@@ -158,6 +158,19 @@ class GridderPlan:
             out[...] = tmp
         return out
 
+    def grid_psf(self, x0, y0, wgt=None, dirty=None, sign=1.0, stream=None):
+        """PSF of a field centred at (x0, y0): grids exp(sign 2 pi i f/c (u x0 + v y0 - w (n0 - 1))) generated on the
+        device from the bound uvw (operators/gridder.py:616-629; sign=-1 for utils/stokes2im.py:483-486)."""
+        if wgt is not None:
+            wgt = self._check_wgt(wgt)
+        out = self._out_img(dirty, "dirty")
+        tmp = out if out.flags.c_contiguous else np.empty(out.shape, out.dtype)
+        _lib.check(self._lib.pfbg_grid_psf(self._h, float(x0), float(y0), float(sign), _ptr(wgt), _ptr(tmp),
+                                           _lib.HOST_PTRS, stream))
+        if tmp is not out:
+            out[...] = tmp
+        return out
+
     def _out_img(self, arr, name):
         if arr is None:
             return np.empty((self.plan.nx, self.plan.ny), dtype=self.rdt)

@@ -385,3 +385,38 @@ def test_full_size_properties_c2_band(gpu):
     h2 = gp.grid(v, d["wgt"])
     assert rel_l2(h, h2) <= 2e-6
     gp.close()
+
+
+@pytest.mark.parametrize("prec", ["double", "single"])
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_psf_phase_ramp_generated_on_device(gpu, prec, sign):
+    """the off-centre PSF visibilities exp(s 2 pi i f/c (u x0 + v y0 - w (n0-1))) are generated on the
+    device; gridding them must equal gridding the array the reference materialises on the host
+    (operators/gridder.py:616-629 with s=+1, utils/stokes2im.py:483-486 with s=-1)."""
+    p = small_problem(nrow=500, nchan=3, nx=64, ny=80, seed=12)
+    l0, m0 = 0.03, -0.02
+    fu, fv, fw, x0, y0 = ops.wgridder_conventions(l0, m0)
+    rdt, cdt = (np.float32, np.complex64) if prec == "single" else (np.float64, np.complex128)
+    eps = 1e-5 if prec == "single" else 1e-9
+    n0 = np.sqrt(1 - x0 ** 2 - y0 ** 2)
+    ramp = np.exp(sign * 2j * np.pi * p["freq"][None, :] / 299792458.0 *
+                  (p["uvw"][:, 0:1] * x0 + p["uvw"][:, 1:2] * y0 - p["uvw"][:, 2:] * (n0 - 1)))
+    with W.plan_for(p["uvw"], p["freq"], npix_x=64, npix_y=80, pixsize_x=p["cell"], pixsize_y=p["cell"], center_x=x0,
+                    center_y=y0, flip_u=fu, flip_v=fv, flip_w=fw, epsilon=eps, precision=prec, mask=p["mask"],
+                    divide_by_n=False) as gp:
+        wgt = p["wgt"].astype(rdt)
+        a = gp.grid(ramp.astype(cdt), wgt)
+        b = gp.grid_psf(x0, y0, wgt=wgt, sign=sign)
+        assert b.dtype == rdt
+        assert rel_l2(b, a) <= (1e-11 if prec == "double" else 3e-6)
+    if sign < 0 or prec == "single":
+        return
+    # through the reference-level entry point: same PSF as gridding the host-materialised ramp with the sign written
+    # at operators/gridder.py:618 (+2j; see SURVEY §8 a13 for the sign trap)
+    out = ops.image_data_products_arrays(p["uvw"], p["freq"], p["vis"][None], p["wgt"][None], p["mask"], 64, 80, 96, 120,
+                                         p["cell"], p["cell"], l0=l0, m0=m0, epsilon=1e-7, do_dirty=False)
+    with W.plan_for(p["uvw"], p["freq"], npix_x=96, npix_y=120, pixsize_x=p["cell"], pixsize_y=p["cell"], center_x=x0,
+                    center_y=y0, flip_u=fu, flip_v=fv, flip_w=fw, epsilon=1e-7, precision="double", mask=p["mask"],
+                    divide_by_n=False, sigma_min=1.1, sigma_max=3.0) as gp:
+        want = gp.grid(ramp, p["wgt"])
+    assert rel_l2(out["psf"][0], want) <= 1e-10
