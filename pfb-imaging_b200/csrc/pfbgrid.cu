@@ -348,7 +348,9 @@ static int fused_setup_t(pfbg_plan* pl) {
   // measured on B200 (15360^2 x 63 planes): with narrower-than-sector column blocks and one row CTA
   // per SM the fused kernels lose to cuFFT (710 ms vs 520 ms per apply), so large grids stay on cuFFT
   // unless PFBG_FFT=fused asks for them
-  if (pl->col_c != want_c && !(env && strcmp(env, "fused") == 0)) return PFBG_OK;
+  // ... but half-sector blocks still win: measured at 8640^2 (the PSF grid of a 4096^2 field, 12 planes) the fused path
+  // takes 20.6 ms per Hessian apply against cuFFT's 25.9 ms in fp32 (34.6 vs 48.1 ms in fp64) and needs no work area
+  if (pl->col_c * 2 < want_c && !(env && strcmp(env, "fused") == 0)) return PFBG_OK;
   if (fft_smem_bytes<T>(g.nv) > kMaxSmem) return PFBG_OK;
   if (fft_smem_bytes<T>(g.nu * pl->col_c) > kMaxSmem) return PFBG_OK;
   FftDesc du, dv;
