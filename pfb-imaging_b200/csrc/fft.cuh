@@ -305,6 +305,8 @@ __device__ __forceinline__ bool fft_stage_p2_dispatch(cx2<T>* s, const cx2<T>* t
     case 64: fft_stage_p2<T, R, 6, C, DIT>(s, tw, N, tid, nthr); return true;
     case 128: fft_stage_p2<T, R, 7, C, DIT>(s, tw, N, tid, nthr); return true;
     case 256: fft_stage_p2<T, R, 8, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 512: fft_stage_p2<T, R, 9, C, DIT>(s, tw, N, tid, nthr); return true;
+    case 1024: fft_stage_p2<T, R, 10, C, DIT>(s, tw, N, tid, nthr); return true;
     default: return false;
   }
 }
@@ -314,16 +316,27 @@ __device__ __forceinline__ void fft_stage_dispatch(int r, cx2<T>* s, const cx2<T
 #ifndef FFT_NO_P2
   // factorize() puts the odd radices first, so every power-of-two stage has a power-of-two stride:
   // radix 16 with M = 2^r 16^j, and one final stage (radix 2..16) with M = 1
-  if (r == 16) {
-    if (fft_stage_p2_dispatch<T, 16, C, DIT>(s, tw, N, L >> 4, tid, nthr)) return;
-  } else if (L == r) {
+  // (fp32: radix 16 with M = 2^r 16^j; fp64: radix 8 with M = 2^r 8^j — the host never emits radix 16 in fp64,
+  // whose butterfly would need ~250 registers)
+  if constexpr (sizeof(T) == 4) {
+    if (r == 16) {
+      if (fft_stage_p2_dispatch<T, 16, C, DIT>(s, tw, N, L >> 4, tid, nthr)) return;
+    }
+  } else {
+    if (r == 8 && L != r) {
+      if (fft_stage_p2_dispatch<T, 8, C, DIT>(s, tw, N, L >> 3, tid, nthr)) return;
+    }
+  }
+  if (L == r) {
     if (r == 8) { fft_stage_p2<T, 8, 0, C, DIT>(s, tw, N, tid, nthr); return; }
     if (r == 4) { fft_stage_p2<T, 4, 0, C, DIT>(s, tw, N, tid, nthr); return; }
     if (r == 2) { fft_stage_p2<T, 2, 0, C, DIT>(s, tw, N, tid, nthr); return; }
   }
 #endif
+  if constexpr (sizeof(T) == 4) {
+    if (r == 16) { fft_stage<T, 16, C, DIT>(s, tw, N, L, tid, nthr); return; }
+  }
   switch (r) {
-    case 16: fft_stage<T, 16, C, DIT>(s, tw, N, L, tid, nthr); break;
     case 8: fft_stage<T, 8, C, DIT>(s, tw, N, L, tid, nthr); break;
     case 4: fft_stage<T, 4, C, DIT>(s, tw, N, L, tid, nthr); break;
     case 2: fft_stage<T, 2, C, DIT>(s, tw, N, L, tid, nthr); break;

@@ -91,7 +91,7 @@ __device__ __forceinline__ void store_row(cx2<T>* __restrict__ p, const cx2<T> (
 // grid = (plane, image row), plane fastest: the CTAs sharing an image row (x, corr, nu table) are
 // co-resident, so those rows are read from DRAM once instead of once per plane.
 template <typename T>
-__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 1))
+__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 2))
 k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict__ beam, const T* __restrict__ corr,
            typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -309,7 +309,7 @@ k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
 // conjugate w-screen to the ny kept outputs and add their real parts to the fp64 accumulation image
 // (RED.F64; CTAs of one row are adjacent in the grid, so the 32 KB image row stays in L2).
 template <typename T>
-__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 1))
+__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 2))
 k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict__ grid, double* __restrict__ accimg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);

@@ -272,7 +272,9 @@ extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
 // ---------------------------------------------------------------------------
 // fused FFT tables
 // ---------------------------------------------------------------------------
-static bool factorize(int n, FftDesc& d) {
+// maxr: largest power-of-two radix (16 in fp32; 8 in fp64, whose radix-16 butterfly needs ~250 registers and
+// leaves one 8-warp CTA per SM)
+static bool factorize(int n, FftDesc& d, int maxr = 16) {
   d.n = n;
   d.nstage = 0;
   int m = n;
@@ -286,10 +288,11 @@ static bool factorize(int n, FftDesc& d) {
   int a = 0;
   while (m % 2 == 0) { m /= 2; ++a; }
   if (m != 1) return false;
-  while (a >= 4) {
+  const int lg = maxr >= 16 ? 4 : 3;
+  while (a >= lg) {
     if (d.nstage >= FFT_MAX_STAGES) return false;
-    d.radix[d.nstage++] = 16;
-    a -= 4;
+    d.radix[d.nstage++] = 1 << lg;
+    a -= lg;
   }
   if (a > 0) {
     if (d.nstage >= FFT_MAX_STAGES) return false;
@@ -354,7 +357,8 @@ static int fused_setup_t(pfbg_plan* pl) {
   if (fft_smem_bytes<T>(g.nv) > kMaxSmem) return PFBG_OK;
   if (fft_smem_bytes<T>(g.nu * pl->col_c) > kMaxSmem) return PFBG_OK;
   FftDesc du, dv;
-  if (!factorize(g.nu, du) || !factorize(g.nv, dv)) return PFBG_OK;
+  const int maxr = sizeof(T) == 4 ? 16 : 8;
+  if (!factorize(g.nu, du, maxr) || !factorize(g.nv, dv, maxr)) return PFBG_OK;
   std::vector<int> rev, pos;
   CKRC(upload_twiddles<T>(pl, pl->tw_u, g.nu));
   CKRC(upload_twiddles<T>(pl, pl->tw_v, g.nv));
@@ -1314,7 +1318,7 @@ extern "C" int pfbg_counts_to_weights(int32_t precision, int32_t device, void* c
 template <typename T>
 static int debug_fft_t(int n, int batch, const void* in, void* out, int mode, int inverse) {
   FftDesc d;
-  if (!factorize(n, d)) return fail(PFBG_ERR_ARG, "n=%d is not 2^a 3^b 5^c 7^d", n);
+  if (!factorize(n, d, sizeof(T) == 4 ? 16 : 8)) return fail(PFBG_ERR_ARG, "n=%d is not 2^a 3^b 5^c 7^d", n);
   size_t bytes = (size_t)n * sizeof(cx2<T>);
   if (fft_smem_bytes<T>(n) > kMaxSmem) return fail(PFBG_ERR_ARG, "n=%d does not fit shared memory", n);
   std::vector<cx2<T>> tw(n);
@@ -1367,7 +1371,7 @@ template <typename T>
 static int conv_setup_t(pfbg_conv* cv) {
   const ConvTabs& c0 = cv->ct;
   FftDesc du, dv;
-  if (!factorize(c0.nxp, du) || !factorize(c0.nyp, dv))
+  if (!factorize(c0.nxp, du, sizeof(T) == 4 ? 16 : 8) || !factorize(c0.nyp, dv, sizeof(T) == 4 ? 16 : 8))
     return fail(PFBG_ERR_ARG, "padded sizes %d x %d must be 2^a 3^b 5^c 7^d 11^e", c0.nxp, c0.nyp);
   if (fft_smem_bytes<T>(c0.nyp) > kMaxSmem) return fail(PFBG_ERR_ARG, "ny_psf=%d too large for the shared-memory FFT", c0.nyp);
   int cc = (int)(32 / sizeof(cx2<T>));

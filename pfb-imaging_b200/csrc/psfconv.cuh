@@ -21,7 +21,7 @@ struct ConvTabs {
 
 // image rows -> tmp (nx, nyp): FFT along v of the zero-padded row, image placed at columns 0..ny-1
 template <typename T>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 1))
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2))
 k_conv_rows_fwd(ConvTabs ct, const T* __restrict__ x, const T* __restrict__ beam, cx2<T>* __restrict__ tmp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
@@ -74,7 +74,7 @@ k_conv_cols(ConvTabs ct, const cx2<T>* __restrict__ khat, cx2<T>* __restrict__ t
 
 // tmp rows -> image: inverse FFT along v, crop, normalise, beam, ridge
 template <typename T>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 1))
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2))
 k_conv_rows_inv(ConvTabs ct, const cx2<T>* __restrict__ tmp, const T* __restrict__ beam, const T* __restrict__ xin,
                 double scale, double eta, T* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
