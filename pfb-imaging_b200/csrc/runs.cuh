@@ -676,6 +676,26 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
           int ip = origin_plane(org);
           if (iv >= p.nv) iv -= p.nv;
           const bool jok = j < W;
+          if (iu0 >= 1 && iu0 + W <= p.nu) {  // rows do not wrap: constant stride (see wide_flush)
+            const int mv = iv ? p.nv - iv : 0;
+#pragma unroll
+            for (int qq = 0; qq < NQ; ++qq) {
+              const int q = q2 + 2 * qq, pl = ip + q;
+              const bool ok = jok && q < npl, mir = pl < 0;
+              const C* g = grid + (mir ? (int64_t)(-pl - 1) * plane_sz + (int64_t)(p.nu - iu0 - row0) * p.nv + mv
+                                       : (int64_t)pl * plane_sz + (int64_t)(iu0 + row0) * p.nv + iv);
+              const int step = mir ? -p.nv : p.nv;
+#pragma unroll
+              for (int ii = 0; ii < RPW; ++ii) {
+                C val; val.x = 0; val.y = 0;
+                if (ok && row0 + ii < W) {
+                  val = g[ii * step];
+                  if (mir) val.y = -val.y;
+                }
+                gr[ii][qq] = val.x; gi[ii][qq] = val.y;
+              }
+            }
+          } else {
 #pragma unroll
           for (int qq = 0; qq < NQ; ++qq) {
             const int q = q2 + 2 * qq;
@@ -693,6 +713,7 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
               }
               gr[ii][qq] = val.x; gi[ii][qq] = val.y;
             }
+          }
           }
         }
         const T* tp = taps[warp][v];
