@@ -49,6 +49,8 @@ extern "C" {
 #define PFBG_DEVICE_PTRS 1u   /* data pointers are device pointers; call is asynchronous on `stream` */
 #define PFBG_APPLY_WGT 2u     /* degrid: multiply the output by the bound/passed weights */
 #define PFBG_NO_MASK_ZERO 4u  /* degrid: leave masked output samples untouched instead of zeroing */
+#define PFBG_PINNED_IN 16u    /* host-pointer calls: the input image(s) are page-locked (pfbg_host_register): DMA directly */
+#define PFBG_PINNED_OUT 32u   /* host-pointer calls: the output image is page-locked */
 
 typedef struct pfbg_plan pfbg_plan;
 
@@ -151,6 +153,11 @@ int pfbg_degrid(pfbg_plan* plan, const void* dirty, void* vis, const void* wgt, 
  */
 int pfbg_hessian(pfbg_plan* plan, const void* x, const void* beam, double wsum, double eta,
                  void* out, uint32_t flags, void* stream);
+
+/* Page-lock / unlock a caller-owned host range (cudaHostRegister) so that host-pointer calls flagged PFBG_PINNED_*
+ * copy without the pinned staging buffer.  The range must be unregistered before its memory is freed. */
+int pfbg_host_register(void* ptr, uint64_t bytes);
+int pfbg_host_unregister(void* ptr);
 
 /* Seconds spent in the phases of the last grid/degrid/hessian call when profiling is on. */
 int pfbg_set_profiling(pfbg_plan* plan, int32_t on);

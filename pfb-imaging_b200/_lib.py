@@ -18,6 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 PFBG_F32, PFBG_F64 = 0, 1
 HOST_PTRS, DEVICE_PTRS, APPLY_WGT, NO_MASK_ZERO = 0, 1, 2, 4
+PINNED_IN, PINNED_OUT = 16, 32
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -67,6 +68,8 @@ SIGNATURES = {
     "pfbg_grid_psf": (C.c_int, [_vp, _dbl, _dbl, _dbl, _vp, _vp, _u32, _vp]),
     "pfbg_degrid": (C.c_int, [_vp, _vp, _vp, _vp, _u32, _vp]),
     "pfbg_hessian": (C.c_int, [_vp, _vp, _vp, _dbl, _dbl, _vp, _u32, _vp]),
+    "pfbg_host_register": (C.c_int, [_vp, C.c_uint64]),
+    "pfbg_host_unregister": (C.c_int, [_vp]),
     "pfbg_set_profiling": (C.c_int, [_vp, _i32]),
     "pfbg_get_timings": (C.c_int, [_vp, C.POINTER(C.c_float), _i32, C.POINTER(_i32)]),
     "pfbg_launch_count": (_i64, []),

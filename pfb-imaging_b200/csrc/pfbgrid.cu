@@ -594,11 +594,29 @@ static int d2h_staged(pfbg_plan* pl, void* dst, const void* src, size_t bytes, c
   return PFBG_OK;
 }
 
+extern "C" int pfbg_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return fail(PFBG_ERR_ARG, "null range");
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(PFBG_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+  return PFBG_OK;
+}
+extern "C" int pfbg_host_unregister(void* ptr) {
+  if (!ptr) return PFBG_OK;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(PFBG_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+  return PFBG_OK;
+}
+
 static int fetch(pfbg_plan* pl, DevBuf& stage, const void* src, size_t bytes, bool dev, cudaStream_t s,
-                 const void** out, size_t pin_off = 0) {
+                 const void** out, size_t pin_off = 0, bool src_pinned = false) {
   // device pointers are used in place; host pointers are staged on the stream
   if (dev) { *out = src; return PFBG_OK; }
   CKRC(dev_alloc(pl, stage, bytes));
+  if (src_pinned) {  // caller-registered memory: one DMA, no staging copy
+    CK(cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, s));
+    *out = stage.p;
+    return PFBG_OK;
+  }
   CKRC(h2d_staged(pl, stage.p, src, bytes, s, pin_off));
   *out = stage.p;
   return PFBG_OK;
@@ -1121,7 +1139,8 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   pl->n_ev = 0;
   mark(pl, s);
   const void *dx = x, *dbeam = beam;
-  CKRC(fetch(pl, pl->img_in, x, img_bytes, dev, s, &dx));
+  const bool pin_in = flags & PFBG_PINNED_IN, pin_out = flags & PFBG_PINNED_OUT;
+  CKRC(fetch(pl, pl->img_in, x, img_bytes, dev, s, &dx, 0, pin_in));
   if (beam) CKRC(fetch(pl, pl->img_beam, beam, img_bytes, dev, s, &dbeam, (img_bytes + 4095) & ~(size_t)4095));
   CKRC(dev_alloc(pl, pl->mvis, (size_t)(pl->nactive ? pl->nactive : 1) * 2 * rb));
   const void* dwgt = pl->has_wgt ? pl->wgt.p : nullptr;
@@ -1157,7 +1176,10 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
   CKRC(planes_to_image(pl, s, dbeam, eta != 0.0 ? dx : nullptr, wsum > 0.0 ? 1.0 / wsum : 1.0, eta, dout));
   mark(pl, s);
-  if (!dev) CKRC(d2h_staged(pl, out, dout, img_bytes, s));
+  if (!dev && pin_out) {
+    CK(cudaMemcpyAsync(out, dout, img_bytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  } else if (!dev) CKRC(d2h_staged(pl, out, dout, img_bytes, s));
   mark(pl, s);
   return PFBG_OK;
 }

@@ -10,6 +10,7 @@ reused across calls); the free functions build a plan per call like ducc0 does.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -206,8 +207,13 @@ class GridderPlan:
             beam = self._check_img(beam, "beam")
         res = self._out_img(out, "out")
         tmp = res if res.flags.c_contiguous else np.empty(res.shape, res.dtype)
+        flags = _lib.HOST_PTRS
+        if _pinned(x):
+            flags |= _lib.PINNED_IN
+        if out is not None and _pinned(tmp):  # a fresh output array is never seen twice
+            flags |= _lib.PINNED_OUT
         _lib.check(self._lib.pfbg_hessian(self._h, _ptr(x), _ptr(beam), float(wsum) if wsum else 0.0,
-                                          float(eta) if eta else 0.0, _ptr(tmp), _lib.HOST_PTRS, stream))
+                                          float(eta) if eta else 0.0, _ptr(tmp), flags, stream))
         if tmp is not res:
             res[...] = tmp
         return res
@@ -232,6 +238,72 @@ class GridderPlan:
         n = C.c_int32(0)
         _lib.check(self._lib.pfbg_get_timings(self._h, ms, 8, C.byref(n)))
         return [ms[i] for i in range(n.value)]
+
+
+# ---------------------------------------------------------------------------
+# Page-locking of caller arrays that keep coming back (solver work vectors, `xout=` buffers): the second time
+# the same buffer is seen it is registered with CUDA, after which its copies are single DMAs instead of a
+# staged copy through the library's pinned buffer (64 MB image: ~1.3 ms instead of ~3.5 ms per direction).
+# The registration is dropped when the owning ndarray is garbage collected (weakref finaliser, which runs
+# before numpy releases the data) or when the table overflows.
+# ---------------------------------------------------------------------------
+_PIN_SEEN: dict = {}
+_PIN_REG: dict = {}
+_PIN_MAX_BYTES = int(__import__("os").environ.get("PFBG_PIN_MAX_MB", "4096")) << 20
+_PIN_MIN_BYTES = 1 << 20
+
+
+def _pin_owner(a):
+    while isinstance(getattr(a, "base", None), np.ndarray):
+        a = a.base
+    return a if (isinstance(a, np.ndarray) and a.base is None and a.flags.owndata) else None
+
+
+def _unpin(key):
+    ent = _PIN_REG.pop(key, None)
+    if ent is not None:
+        try:
+            _lib.load().pfbg_host_unregister(C.c_void_p(key[0]))
+        except Exception:
+            pass
+
+
+def _pinned(a) -> bool:
+    """True if `a`'s memory is (now) page-locked.  Registers on the second sighting of the same live buffer."""
+    if _PIN_MAX_BYTES <= 0 or a.nbytes < _PIN_MIN_BYTES:
+        return False
+    owner = _pin_owner(a)
+    if owner is None:
+        return False
+    key = (owner.ctypes.data, owner.nbytes)
+    if key in _PIN_REG:  # the finaliser removes the entry before the memory can be re-used
+        return True
+    ref = _PIN_SEEN.get(key)
+    if ref is None or ref() is not owner:  # first sighting of this array object
+        if len(_PIN_SEEN) > 256:
+            _PIN_SEEN.clear()
+        _PIN_SEEN[key] = weakref.ref(owner)
+        return False
+    while _PIN_REG and sum(k[1] for k in _PIN_REG) + owner.nbytes > _PIN_MAX_BYTES:
+        key0 = next(iter(_PIN_REG))
+        fin = _PIN_REG.get(key0)
+        _unpin(key0)
+        if fin is not None:
+            fin.detach()
+    if _lib.load().pfbg_host_register(C.c_void_p(key[0]), owner.nbytes) != 0:
+        _PIN_SEEN.pop(key, None)
+        return False
+    _PIN_REG[key] = weakref.finalize(owner, _unpin, key)
+    _PIN_SEEN.pop(key, None)
+    return True
+
+
+def clear_pinned():
+    for key in list(_PIN_REG):
+        fin = _PIN_REG.get(key)
+        _unpin(key)
+        if fin is not None:
+            fin.detach()
 
 
 # ---------------------------------------------------------------------------

@@ -420,3 +420,29 @@ def test_psf_phase_ramp_generated_on_device(gpu, prec, sign):
                     divide_by_n=False, sigma_min=1.1, sigma_max=3.0) as gp:
         want = gp.grid(ramp, p["wgt"])
     assert rel_l2(out["psf"][0], want) <= 1e-10
+
+
+def test_recurring_host_buffers_are_page_locked_and_results_unchanged(gpu):
+    """Solver-style use: the same x / xout arrays come back every iteration.  From the second call on they are
+    registered with CUDA (direct DMA); results must be identical and the registration must die with the array."""
+    import gc
+
+    p = small_problem(nrow=400, nchan=2, nx=512, ny=512, seed=5)  # 2 MB images: above the pinning threshold
+    W.clear_pinned()
+    with W.plan_for(p["uvw"], p["freq"], npix_x=512, npix_y=512, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=1e-6,
+                    flip_v=True, divide_by_n=False, mask=p["mask"]) as gp:
+        gp.bind_weights(p["wgt"])
+        x = np.random.default_rng(0).standard_normal((512, 512))
+        out = np.empty_like(x)
+        ref = gp.hessian(x).copy()
+        for it in range(3):
+            gp.hessian(x, out=out)
+            # (the order of the fp64 atomic adds differs from call to call; 1/psihat amplifies that round-off)
+            np.testing.assert_allclose(out, ref, rtol=0, atol=1e-8 * np.abs(ref).max())
+        assert len(W._PIN_REG) == 2  # x and out, registered at their second sighting
+        x *= 2.0  # in-place update of a registered buffer is seen by the next call
+        gp.hessian(x, out=out)
+        np.testing.assert_allclose(out, 2.0 * ref, rtol=0, atol=2e-8 * np.abs(ref).max())
+        del x, out
+        gc.collect()
+        assert len(W._PIN_REG) == 0
