@@ -638,6 +638,10 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
   __shared__ T taps[WIDE_WARPS][NB][NT];
   __shared__ __align__(16) T x0s[WIDE_WARPS][NB][4];
   __shared__ uint64_t orgs[WIDE_WARPS][NB];
+  // per-sample partial sums of the 32 lanes: summed lane <-> sample after the batch (skewed, conflict-free) instead
+  // of a 5-level shuffle reduction per sample, whose dependent latency dominated this kernel (ncu: "wait" stalls)
+  extern __shared__ __align__(16) unsigned char wide_part_raw[];  // WIDE_WARPS * NB * 32 complex (dynamic: > 48 KB in fp64)
+  C (*part)[NB][32] = reinterpret_cast<C (*)[NB][32]>(wide_part_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = lane & 15, q2 = lane >> 4;
   const int64_t gwarp = (int64_t)blockIdx.x * WIDE_WARPS + warp;
@@ -666,7 +670,6 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
       __syncwarp();
       wide_taps_warp<T, RPW, NQ>(p, x0s[warp], taps[warp], nb, lane, row0, bscale, xs);
       __syncwarp();
-      T myr = 0, myi = 0;  // lane v keeps the team-partial of sample v
       for (int v = 0; v < nb; ++v) {
         const uint64_t org = orgs[warp][v];
         if (org != cur) {
@@ -727,15 +730,17 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
           sr += pr * wq; si += pi * wq;
         }
         const T tv = tp[RPW + j];
-        sr *= tv; si *= tv;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          sr += __shfl_xor_sync(0xffffffffu, sr, o);
-          si += __shfl_xor_sync(0xffffffffu, si, o);
-        }
-        if (lane == v) { myr = sr; myi = si; }
+        C pv; pv.x = sr * tv; pv.y = si * tv;
+        part[warp][v][lane] = pv;
       }
+      __syncwarp();
       if (lane < nb) {
+        T myr = 0, myi = 0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+          const C pv = part[warp][lane][(lane + l) & 31];
+          myr += pv.x; myi += pv.y;
+        }
         T re = myr, im = myi;
         if (apply_phase) {
           re = myr * r.pc + myi * r.ps;
