@@ -168,8 +168,8 @@ def run_ours(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; rank 0 must print ONE JSON line
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION / WARN) to stdout; rank 0 must print ONE JSON line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
