@@ -137,7 +137,14 @@ static int psi_dot_t(pfbs_psi* p, const T* x, T* alpha, cudaStream_t s) {
       T* ap = (l + 1 < p->nlevel) ? (T*)p->approx[l & 1] : nullptr;
       BandPtr bp{in_stride, astride, (int64_t)p->approx_elems};
       dim3 grd((sy + SW_TY - 1) / SW_TY, (sx + SW_TX - 1) / SW_TX, p->nband);
-      k_dwt_level<T><<<grd, 256, 0, s>>>(in, ld_in, nxin, nyin, ab + (int64_t)lx * p->nymax + ly, p->nymax, sx, sy, ap, p->dec[b], bp);
+      T* blk = ab + (int64_t)lx * p->nymax + ly;
+      switch (p->K[b]) {
+        case 2: k_dwt_level<T, 2><<<grd, 256, 0, s>>>(in, ld_in, nxin, nyin, blk, p->nymax, sx, sy, ap, p->dec[b], bp); break;
+        case 4: k_dwt_level<T, 4><<<grd, 256, 0, s>>>(in, ld_in, nxin, nyin, blk, p->nymax, sx, sy, ap, p->dec[b], bp); break;
+        case 6: k_dwt_level<T, 6><<<grd, 256, 0, s>>>(in, ld_in, nxin, nyin, blk, p->nymax, sx, sy, ap, p->dec[b], bp); break;
+        case 8: k_dwt_level<T, 8><<<grd, 256, 0, s>>>(in, ld_in, nxin, nyin, blk, p->nymax, sx, sy, ap, p->dec[b], bp); break;
+        default: k_dwt_level<T, 10><<<grd, 256, 0, s>>>(in, ld_in, nxin, nyin, blk, p->nymax, sx, sy, ap, p->dec[b], bp); break;
+      }
       pfbg_count_launch();
       in = ap; ld_in = sy; nxin = sx; nyin = sy; in_stride = (int64_t)p->approx_elems;
     }
@@ -175,7 +182,13 @@ static int psi_hdot_t(pfbs_psi* p, const T* alpha, T* x, cudaStream_t s) {
       else { dst = (T*)p->img[l & 1]; ld_dst = p->ny + 2; dst_stride = (int64_t)p->img_elems; acc = 0; }
       BandPtr bp{astride, dst_stride, ll_stride};
       dim3 grd(((nyo + 1) / 2 + SW_TY - 1) / SW_TY, ((nxo + 1) / 2 + SW_TX - 1) / SW_TX, p->nband);
-      k_idwt_level<T><<<grd, 256, 0, s>>>(ll, ld_ll, blk, p->nymax, sx, sy, dst, ld_dst, nxo, nyo, p->rec[b], acc, bp);
+      switch (p->K[b]) {
+        case 2: k_idwt_level<T, 2><<<grd, 256, 0, s>>>(ll, ld_ll, blk, p->nymax, sx, sy, dst, ld_dst, nxo, nyo, p->rec[b], acc, bp); break;
+        case 4: k_idwt_level<T, 4><<<grd, 256, 0, s>>>(ll, ld_ll, blk, p->nymax, sx, sy, dst, ld_dst, nxo, nyo, p->rec[b], acc, bp); break;
+        case 6: k_idwt_level<T, 6><<<grd, 256, 0, s>>>(ll, ld_ll, blk, p->nymax, sx, sy, dst, ld_dst, nxo, nyo, p->rec[b], acc, bp); break;
+        case 8: k_idwt_level<T, 8><<<grd, 256, 0, s>>>(ll, ld_ll, blk, p->nymax, sx, sy, dst, ld_dst, nxo, nyo, p->rec[b], acc, bp); break;
+        default: k_idwt_level<T, 10><<<grd, 256, 0, s>>>(ll, ld_ll, blk, p->nymax, sx, sy, dst, ld_dst, nxo, nyo, p->rec[b], acc, bp); break;
+      }
       pfbg_count_launch();
       ll = dst; ld_ll = ld_dst; ll_stride = dst_stride;
     }

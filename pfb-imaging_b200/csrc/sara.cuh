@@ -24,15 +24,18 @@ struct BandPtr {
 // analysis, one level:  in (nxin, nyin) -> block (2sx, 2sy) = [LL LH; HL HH] (x-first), LL also to `approx`
 //   rows:  r[i, o] = sum_k h[k] in[i, 2o+1-k]        cols:  out[o, :] = sum_k h[k] r[2o+1-k, :]
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(256)
 k_dwt_level(const T* __restrict__ in, int ld_in, int nxin, int nyin, T* __restrict__ out, int ld_out, int sx, int sy,
             T* __restrict__ approx, DwtFilt f, BandPtr bp) {
   constexpr int R = 2 * SW_TX + SW_KMAX - 2, CC = 2 * SW_TY + SW_KMAX - 2;
   __shared__ T sin_[R][CC + 1];
   __shared__ T stmp[R][2 * SW_TY];
-  const int tid = threadIdx.x, K = f.K;
+  const int tid = threadIdx.x;
   const int ox0 = blockIdx.y * SW_TX, oy0 = blockIdx.x * SW_TY;
+  T flo[K], fhi[K];  // filter taps in registers, loops fully unrolled (K is a template parameter)
+#pragma unroll
+  for (int k = 0; k < K; ++k) { flo[k] = (T)f.lo[k]; fhi[k] = (T)f.hi[k]; }
   in += (int64_t)blockIdx.z * bp.in_stride;
   out += (int64_t)blockIdx.z * bp.out_stride;
   if (approx) approx += (int64_t)blockIdx.z * bp.aux_stride;
@@ -49,10 +52,11 @@ k_dwt_level(const T* __restrict__ in, int ld_in, int nxin, int nyin, T* __restri
   for (int idx = tid; idx < nr * SW_TY; idx += 256) {
     const int r = idx / SW_TY, o = idx - r * SW_TY;
     T lo = 0, hi = 0;
+#pragma unroll
     for (int k = 0; k < K; ++k) {
       const T v = sin_[r][2 * o + K - 1 - k];
-      lo += (T)f.lo[k] * v;
-      hi += (T)f.hi[k] * v;
+      lo += flo[k] * v;
+      hi += fhi[k] * v;
     }
     stmp[r][o] = lo;
     stmp[r][SW_TY + o] = hi;
@@ -63,10 +67,11 @@ k_dwt_level(const T* __restrict__ in, int ld_in, int nxin, int nyin, T* __restri
     const int gx = ox0 + o, cc = c < SW_TY ? c : c - SW_TY, gy = oy0 + cc;
     if (gx >= sx || gy >= sy) continue;
     T lo = 0, hi = 0;
+#pragma unroll
     for (int k = 0; k < K; ++k) {
       const T v = stmp[2 * o + K - 1 - k][c];
-      lo += (T)f.lo[k] * v;
-      hi += (T)f.hi[k] * v;
+      lo += flo[k] * v;
+      hi += fhi[k] * v;
     }
     const int ycol = c < SW_TY ? gy : sy + gy;
     out[(int64_t)gx * ld_out + ycol] = lo;
@@ -80,15 +85,19 @@ k_dwt_level(const T* __restrict__ in, int ld_in, int nxin, int nyin, T* __restri
 //   cols: cb[2t+p, c] = sum_m lo[2m+p] X0[t+H-1-m, c] + hi[2m+p] X1[t+H-1-m, c]     (H = K/2)
 //   rows: out[r, 2u+p] = sum_m lo[2m+p] cb[r, u+H-1-m] + hi[2m+p] cb[r, sy+u+H-1-m]
 // ---------------------------------------------------------------------------
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(256)
 k_idwt_level(const T* __restrict__ ll, int ld_ll, const T* __restrict__ blk, int ld_blk, int sx, int sy,
              T* __restrict__ out, int ld_out, int nxo, int nyo, DwtFilt f, int accumulate, BandPtr bp) {
   constexpr int HM = SW_KMAX / 2, RX = SW_TX + HM - 1, RY = SW_TY + HM - 1;
   __shared__ T sc[2][2][RX][RY + 1];       // [x half][y half]
   __shared__ T cb[2 * SW_TX][2][RY + 1];
-  const int tid = threadIdx.x, K = f.K, H = K / 2;
+  constexpr int H = K / 2;
+  const int tid = threadIdx.x;
   const int tx0 = blockIdx.y * SW_TX, ty0 = blockIdx.x * SW_TY;
+  T flo[K], fhi[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { flo[k] = (T)f.lo[k]; fhi[k] = (T)f.hi[k]; }
   ll += (int64_t)blockIdx.z * bp.aux_stride;
   blk += (int64_t)blockIdx.z * bp.in_stride;
   out += (int64_t)blockIdx.z * bp.out_stride;
@@ -111,8 +120,11 @@ k_idwt_level(const T* __restrict__ ll, int ld_ll, const T* __restrict__ blk, int
     const int yh = rem / nry, c = rem - yh * nry;
     const int t = r >> 1, p = r & 1;
     T acc = 0;
-    for (int m = 0; m < H; ++m)
-      acc += (T)f.lo[2 * m + p] * sc[0][yh][t + H - 1 - m][c] + (T)f.hi[2 * m + p] * sc[1][yh][t + H - 1 - m][c];
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+      const T a = sc[0][yh][t + H - 1 - m][c], b = sc[1][yh][t + H - 1 - m][c];
+      acc += (p ? flo[2 * m + 1] : flo[2 * m]) * a + (p ? fhi[2 * m + 1] : fhi[2 * m]) * b;
+    }
     cb[r][yh][c] = acc;
   }
   __syncthreads();
@@ -122,8 +134,11 @@ k_idwt_level(const T* __restrict__ ll, int ld_ll, const T* __restrict__ blk, int
     const int gr = 2 * tx0 + r, gc = 2 * ty0 + cc;
     if (gr >= nxo || gc >= nyo) continue;
     T acc = 0;
-    for (int m = 0; m < H; ++m)
-      acc += (T)f.lo[2 * m + p] * cb[r][0][u + H - 1 - m] + (T)f.hi[2 * m + p] * cb[r][1][u + H - 1 - m];
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+      const T a = cb[r][0][u + H - 1 - m], b = cb[r][1][u + H - 1 - m];
+      acc += (p ? flo[2 * m + 1] : flo[2 * m]) * a + (p ? fhi[2 * m + 1] : fhi[2 * m]) * b;
+    }
     T* o = out + (int64_t)gr * ld_out + gc;
     *o = accumulate ? *o + acc : acc;
   }
