@@ -50,9 +50,11 @@ int pfbs_psi_hdot(pfbs_psi* psi, const void* alpha, void* x, uint32_t flags, voi
  * phase 0: all in one kernel (every band on this device).
  * phase 1: v = vtilde and bsum (ncoef) = sum over the LOCAL bands;   [caller all-reduces bsum across ranks]
  * phase 2: v *= min(1, lam w / |bsum|).
+ * vbar (optional, phases 0 and 2; needs vp): also receives the extrapolated dual 2 v - vp (_nb_extrapolate_dual,
+ * opt/primal_dual.py:16-23) in the same pass.
  */
 int pfbs_dual_update(int32_t precision, int32_t device, const void* vp, void* v, const void* weight, double lam,
-                     double sigma, int32_t nband, int64_t ncoef, void* bsum, int32_t phase, void* stream);
+                     double sigma, int32_t nband, int64_t ncoef, void* bsum, int32_t phase, void* vbar, void* stream);
 /* result = v * max(|sum_band v / sigma| - lam w / sigma, 0) / |sum_band v / sigma| / sigma   (0 where the sum is 0) */
 int pfbs_prox_21m(int32_t precision, int32_t device, const void* v, void* result, const void* weight, double lam,
                   double sigma, int32_t nband, int64_t ncoef, void* stream);

@@ -89,7 +89,7 @@ SIGNATURES = {
     "pfbs_psi_destroy": (C.c_int, [_vp]),
     "pfbs_psi_dot": (C.c_int, [_vp, _vp, _vp, _u32, _vp]),
     "pfbs_psi_hdot": (C.c_int, [_vp, _vp, _vp, _u32, _vp]),
-    "pfbs_dual_update": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _dbl, _i32, _i64, _vp, _i32, _vp]),
+    "pfbs_dual_update": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _dbl, _i32, _i64, _vp, _i32, _vp, _vp]),
     "pfbs_prox_21m": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _dbl, _i32, _i64, _vp]),
     "pfbs_axpby": (C.c_int, [_i32, _i32, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp]),
     "pfbs_extrapolate": (C.c_int, [_i32, _i32, _vp, _vp, _i64, _vp]),

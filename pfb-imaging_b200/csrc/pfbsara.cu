@@ -264,16 +264,18 @@ static unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 extern "C" int pfbs_dual_update(int32_t precision, int32_t device, const void* vp, void* v, const void* weight,
                                 double lam, double sigma, int32_t nband, int64_t ncoef, void* bsum, int32_t phase,
-                                void* stream) {
-  if (!v || !weight || (phase != 2 && !vp) || (phase != 0 && !bsum)) return pfbg_fail(PFBG_ERR_ARG, "null argument");
+                                void* vbar, void* stream) {
+  if (!v || !weight || (phase != 2 && !vp) || (phase != 0 && !bsum) || (vbar && !vp))
+    return pfbg_fail(PFBG_ERR_ARG, "null argument");
+  if (vbar && phase == 1) return pfbg_fail(PFBG_ERR_ARG, "the extrapolated dual is written by phase 0 or 2");
   if (phase < 0 || phase > 2 || nband < 1 || ncoef < 0) return pfbg_fail(PFBG_ERR_ARG, "bad phase / sizes");
   SCK(cudaSetDevice(device));
   cudaStream_t s = (cudaStream_t)stream;
   if (ncoef == 0) return PFBG_OK;
   if (precision == PFBG_F32)
-    k_dual_update<float><<<nblk(ncoef), 256, 0, s>>>((const float*)vp, (float*)v, (const float*)weight, (float)lam, (float)sigma, nband, ncoef, (float*)bsum, phase);
+    k_dual_update<float><<<nblk(ncoef), 256, 0, s>>>((const float*)vp, (float*)v, (const float*)weight, (float)lam, (float)sigma, nband, ncoef, (float*)bsum, phase, (float*)vbar);
   else if (precision == PFBG_F64)
-    k_dual_update<double><<<nblk(ncoef), 256, 0, s>>>((const double*)vp, (double*)v, (const double*)weight, lam, sigma, nband, ncoef, (double*)bsum, phase);
+    k_dual_update<double><<<nblk(ncoef), 256, 0, s>>>((const double*)vp, (double*)v, (const double*)weight, lam, sigma, nband, ncoef, (double*)bsum, phase, (double*)vbar);
   else return pfbg_fail(PFBG_ERR_ARG, "bad precision");
   pfbg_count_launch();
   SCK(cudaGetLastError());

@@ -172,31 +172,34 @@ __global__ void k_transpose(const T* __restrict__ src, T* __restrict__ dst, int 
 }
 
 // l21 dual update / prox ----------------------------------------------------------------------
+// vbar != nullptr: also writes the extrapolated dual 2 v_new - vp (opt/primal_dual.py:16-23) in the same pass, so the
+// loop needs neither the separate extrapolation kernel nor the vp <- v copy (the caller swaps the two buffers)
 template <typename T>
 __global__ void k_dual_update(const T* __restrict__ vp, T* __restrict__ v, const T* __restrict__ w, T lam, T sigma,
-                              int nband, int64_t ncoef, T* __restrict__ bsum, int phase) {
+                              int nband, int64_t ncoef, T* __restrict__ bsum, int phase, T* __restrict__ vbar) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ncoef) return;
-  if (phase == 2) {
-    const T s = fabs(bsum[k]), thr = lam * w[k];
-    if (s > thr) {
-      const T sc = thr / s;
-      for (int b = 0; b < nband; ++b) v[(int64_t)b * ncoef + k] *= sc;
-    }
-    return;
-  }
   T sum = 0;
+  if (phase == 2) {
+    sum = bsum[k];
+  } else {
+    for (int b = 0; b < nband; ++b) {
+      const int64_t o = (int64_t)b * ncoef + k;
+      const T vt = vp[o] + sigma * v[o];
+      v[o] = vt;
+      sum += vt;
+    }
+    if (phase == 1) { bsum[k] = sum; return; }
+  }
+  const T s = fabs(sum), thr = lam * w[k];
+  const bool shrink = s > thr;
+  if (!shrink && !vbar) return;
+  const T sc = shrink ? thr / s : (T)1;
   for (int b = 0; b < nband; ++b) {
     const int64_t o = (int64_t)b * ncoef + k;
-    const T vt = vp[o] + sigma * v[o];
-    v[o] = vt;
-    sum += vt;
-  }
-  if (phase == 1) { bsum[k] = sum; return; }
-  const T s = fabs(sum), thr = lam * w[k];
-  if (s > thr) {
-    const T sc = thr / s;
-    for (int b = 0; b < nband; ++b) v[(int64_t)b * ncoef + k] *= sc;
+    T vn = v[o];
+    if (shrink) { vn *= sc; v[o] = vn; }
+    if (vbar) vbar[o] = (T)2 * vn - vp[o];
   }
 }
 

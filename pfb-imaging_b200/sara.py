@@ -220,9 +220,10 @@ class L21:
         v[...] = vt.cpu().numpy()
         return v
 
-    def dual_update_dev(self, vp_t, v_t, w_t, lam, sigma, reduce=None, bsum_t=None):
+    def dual_update_dev(self, vp_t, v_t, w_t, lam, sigma, reduce=None, bsum_t=None, vbar_t=None):
         """Device tensors.  With `reduce` (an in-place all-reduce of a device tensor over the ranks that hold
-        the other bands) the update runs as: local band sum -> reduce -> scale."""
+        the other bands) the update runs as: local band sum -> reduce -> scale.  `vbar_t` (optional) receives the
+        extrapolated dual 2 v - vp in the same pass."""
         psi = self.psi
         torch = _torch()
         nband, ncoef = v_t.shape[0], int(v_t[0].numel())
@@ -230,15 +231,15 @@ class L21:
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         if reduce is None:
             _lib.check(psi._lib.pfbs_dual_update(psi.prec, psi.device, p(vp_t), p(v_t), p(w_t), float(lam), float(sigma),
-                                                 nband, ncoef, None, 0, s))
+                                                 nband, ncoef, None, 0, p(vbar_t), s))
             return
         if bsum_t is None:
             bsum_t = torch.empty_like(v_t[0])
         _lib.check(psi._lib.pfbs_dual_update(psi.prec, psi.device, p(vp_t), p(v_t), p(w_t), float(lam), float(sigma),
-                                             nband, ncoef, p(bsum_t), 1, s))
+                                             nband, ncoef, p(bsum_t), 1, None, s))
         reduce(bsum_t)
-        _lib.check(psi._lib.pfbs_dual_update(psi.prec, psi.device, None, p(v_t), p(w_t), float(lam), float(sigma),
-                                             nband, ncoef, p(bsum_t), 2, s))
+        _lib.check(psi._lib.pfbs_dual_update(psi.prec, psi.device, p(vp_t), p(v_t), p(w_t), float(lam), float(sigma),
+                                             nband, ncoef, p(bsum_t), 2, p(vbar_t), s))
 
 
 class PrimalDual:
@@ -304,8 +305,11 @@ class PrimalDual:
         xp_t = x_t.clone()
         xout_t = torch.zeros_like(x_t)
         g_t = torch.empty_like(x_t)
-        v_t = self._v
-        vp_t = v_t.clone()
+        # three dual buffers: vp (previous iterate), v (receives Psi^T xp, becomes the new iterate in place) and
+        # vbar (extrapolated 2 v - vp, written by the fused dual update); vp and v swap roles every iteration
+        vp_t = self._v
+        v_t = torch.empty_like(vp_t)
+        vbar_t = torch.empty_like(vp_t)
         w = reg.l1weight
         if psi._transposed:
             w = w.transpose(0, 2, 1)
@@ -319,9 +323,8 @@ class PrimalDual:
         eps, k = 1.0, 0
         for k in range(self.maxit):
             psi.dot_dev(xp_t, v_t, s)
-            reg.dual_update_dev(vp_t, v_t, w_t, lam, self.sigma, self.reduce_tensor, bsum_t)
-            _lib.check(lib.pfbs_extrapolate(prec, dv, p(v_t), p(vp_t), v_t.numel(), s))
-            psi.hdot_dev(vp_t, xout_t, s)
+            reg.dual_update_dev(vp_t, v_t, w_t, lam, self.sigma, self.reduce_tensor, bsum_t, vbar_t)
+            psi.hdot_dev(vbar_t, xout_t, s)
             if dev_grad is not None:
                 dev_grad(xp_t, g_t)
             else:
@@ -344,9 +347,12 @@ class PrimalDual:
                 if self.on_converge is None or self.on_converge(x_t.cpu().numpy(), k, eps):
                     break
             xp_t.copy_(x_t)
-            vp_t.copy_(v_t)
+            vp_t, v_t = v_t, vp_t  # the new iterate becomes the previous one; its buffer is overwritten next
             if not k % self.report_freq and self.verbosity > 1:
                 print(f"PD: at iteration {k} eps = {eps:.3e}")
+        else:
+            vp_t, v_t = v_t, vp_t  # loop ran out after a swap: the latest iterate sits in vp_t
+        self._v = v_t  # warm start of the next solve (on break: v_t holds the latest iterate)
         self.niter, self.eps = k, eps
         if self.verbosity:
             print(f"PD: max iters reached, eps = {eps:.3e}" if k == self.maxit - 1 else f"PD: converged after {k} iterations")
