@@ -684,12 +684,17 @@ extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fsc
   pl->has_wgt = false;
   CKRC(dev_alloc(pl, pl->uvw, (size_t)(nrow > 0 ? nrow : 1) * 3 * sizeof(double)));
   CKRC(dev_alloc(pl, pl->fscale, (size_t)nchan * sizeof(double)));
-  if (nrow > 0) CK(cudaMemcpyAsync(pl->uvw.p, uvw, (size_t)nrow * 3 * sizeof(double), kind, s));
+  // host arrays go through the pinned staging pipeline (threaded copy overlapped with the DMA), not a pageable memcpy
+  if (nrow > 0) {
+    if (dev) CK(cudaMemcpyAsync(pl->uvw.p, uvw, (size_t)nrow * 3 * sizeof(double), kind, s));
+    else CKRC(h2d_staged(pl, pl->uvw.p, uvw, (size_t)nrow * 3 * sizeof(double), s));
+  }
   CK(cudaMemcpyAsync(pl->fscale.p, fscale, (size_t)nchan * sizeof(double), kind, s));
   pl->has_mask = mask != nullptr;
   if (mask && nvis > 0) {
     CKRC(dev_alloc(pl, pl->mask, (size_t)nvis));
-    CK(cudaMemcpyAsync(pl->mask.p, mask, (size_t)nvis, kind, s));
+    if (dev) CK(cudaMemcpyAsync(pl->mask.p, mask, (size_t)nvis, kind, s));
+    else CKRC(h2d_staged(pl, pl->mask.p, mask, (size_t)nvis, s));
   }
   if (nvis == 0) {
     pl->bound = true;
@@ -702,7 +707,9 @@ extern "C" int pfbg_bind_vis(pfbg_plan* pl, const double* uvw, const double* fsc
   int bits = 1;
   while ((1ull << bits) <= maxkey) ++bits;  // inactive key = maxkey needs `bits` bits
   DevBuf &keys_a = pl->srt_ka, &keys_b = pl->srt_kb, &vals_a = pl->srt_va, &vals_b = pl->srt_vb, &tmp = pl->srt_tmp;
-  const bool keep_scratch = nvis <= (int64_t)(4 << 20);  // <= 100 MB of scratch: keep it for the next binding
+  // keep the sort scratch (28 B per sample) for the next binding of this plan: pooled plans of one-shot calls re-bind
+  // all the time (pfb grid: dirty, PSF, residual per band) and cudaMalloc / cudaFree of ~1 GB cost more than the sort
+  const bool keep_scratch = nvis <= (int64_t)(96 << 20);
   auto cleanup = [&]() {
     if (keep_scratch) return;
     dev_free(pl, keys_a); dev_free(pl, keys_b); dev_free(pl, vals_a); dev_free(pl, vals_b); dev_free(pl, tmp);
