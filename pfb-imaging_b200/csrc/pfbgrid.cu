@@ -553,7 +553,7 @@ static int pinned(void*& p, size_t& have, size_t need) {
   return PFBG_OK;
 }
 
-static const size_t kChunk = (size_t)8 << 20;
+static const size_t kChunk = (size_t)32 << 20;  // per-chunk thread spawn amortised; copy of chunk c+1 overlaps the DMA of chunk c
 
 // host -> device through the pinned buffer: CPU copy of chunk c+1 overlaps the DMA of chunk c
 static int h2d_staged(pfbg_plan* pl, void* dst, const void* src, size_t bytes, cudaStream_t s, size_t pin_off = 0) {
