@@ -261,11 +261,13 @@ class PrimalDual:
         self._grad = None
         self._reg = None
         self._v = None
+        self._work = None
         self.niter = 0
         self.eps = 1.0
 
     def setup(self, prox, hessnorm: float) -> None:
         self._reg = prox
+        self._work = None
         self.hessnorm = hessnorm
         nu = prox.nu
         sigma = self._sigma_opt
@@ -301,19 +303,30 @@ class PrimalDual:
         torch = _torch()
         reg, psi = self._reg, self._reg.psi
         lib, prec, dv = psi._lib, psi.prec, psi.device
-        x_t = torch.from_numpy(np.ascontiguousarray(x, dtype=psi.rdt)).to(self._dev)
-        xp_t = x_t.clone()
-        xout_t = torch.zeros_like(x_t)
-        g_t = torch.empty_like(x_t)
+        # work buffers live with the solver: solve() is called once per major cycle and the cubes are GB-sized
+        wk = self._work
+        if wk is None or wk["x"].shape != tuple(np.shape(x)):
+            shp = tuple(np.shape(x))
+            wk = self._work = dict(
+                x=torch.empty(shp, dtype=self._tdt, device=self._dev), xp=torch.empty(shp, dtype=self._tdt, device=self._dev),
+                xout=torch.empty(shp, dtype=self._tdt, device=self._dev), g=torch.empty(shp, dtype=self._tdt, device=self._dev),
+                v=torch.empty_like(self._v), vbar=torch.empty_like(self._v),
+                pin=torch.empty(shp, dtype=self._tdt, pin_memory=True), w=None, w_src=None)
+        x_t, xp_t, xout_t, g_t = wk["x"], wk["xp"], wk["xout"], wk["g"]
+        pin_np = wk["pin"].numpy()
+        np.copyto(pin_np, x, casting="same_kind")
+        x_t.copy_(wk["pin"], non_blocking=True)
+        xp_t.copy_(x_t)
         # three dual buffers: vp (previous iterate), v (receives Psi^T xp, becomes the new iterate in place) and
         # vbar (extrapolated 2 v - vp, written by the fused dual update); vp and v swap roles every iteration
         vp_t = self._v
-        v_t = torch.empty_like(vp_t)
-        vbar_t = torch.empty_like(vp_t)
-        w = reg.l1weight
-        if psi._transposed:
-            w = w.transpose(0, 2, 1)
-        w_t = torch.from_numpy(np.ascontiguousarray(w, dtype=psi.rdt)).to(self._dev)
+        v_t = wk["v"]
+        vbar_t = wk["vbar"]
+        if wk["w_src"] is not reg.l1weight:  # the regulariser replaces the array when it reweights (prox/l21.py:88-91)
+            w = reg.l1weight.transpose(0, 2, 1) if psi._transposed else reg.l1weight
+            wk["w"] = torch.from_numpy(np.ascontiguousarray(w, dtype=psi.rdt)).to(self._dev)
+            wk["w_src"] = reg.l1weight
+        w_t = wk["w"]
         bsum_t = torch.empty_like(v_t[0]) if self.reduce_tensor is not None else None
         s = torch.cuda.current_stream(self._dev).cuda_stream
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
@@ -353,14 +366,15 @@ class PrimalDual:
         else:
             vp_t, v_t = v_t, vp_t  # loop ran out after a swap: the latest iterate sits in vp_t
         self._v = v_t  # warm start of the next solve (on break: v_t holds the latest iterate)
+        wk["v"] = vp_t  # the other dual buffer is free for the next call
         self.niter, self.eps = k, eps
         if self.verbosity:
             print(f"PD: max iters reached, eps = {eps:.3e}" if k == self.maxit - 1 else f"PD: converged after {k} iterations")
-        out = x_t.cpu().numpy()
-        if isinstance(x, np.ndarray) and x.shape == out.shape and x.flags.writeable:
-            x[...] = out
+        wk["pin"].copy_(x_t)  # device -> pinned host (synchronous), then one host copy into the caller's array
+        if isinstance(x, np.ndarray) and x.shape == pin_np.shape and x.flags.writeable:
+            np.copyto(x, pin_np, casting="same_kind")
             return x
-        return out
+        return pin_np.astype(psi.rdt, copy=True)
 
 
 class ForwardBackward:
