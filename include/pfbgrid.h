@@ -51,6 +51,8 @@ extern "C" {
 #define PFBG_NO_MASK_ZERO 4u  /* degrid: leave masked output samples untouched instead of zeroing */
 #define PFBG_PINNED_IN 16u    /* host-pointer calls: the input image(s) are page-locked (pfbg_host_register): DMA directly */
 #define PFBG_PINNED_OUT 32u   /* host-pointer calls: the output image is page-locked */
+#define PFBG_BEAM_CACHED 64u  /* pfbg_hessian, host pointers: `beam` equals the beam of the previous call on this plan
+                               * (the caller vouches for it): use the device copy instead of uploading it again */
 
 typedef struct pfbg_plan pfbg_plan;
 

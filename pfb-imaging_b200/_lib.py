@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 PFBG_F32, PFBG_F64 = 0, 1
 HOST_PTRS, DEVICE_PTRS, APPLY_WGT, NO_MASK_ZERO = 0, 1, 2, 4
-PINNED_IN, PINNED_OUT = 16, 32
+PINNED_IN, PINNED_OUT, BEAM_CACHED = 16, 32, 64
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

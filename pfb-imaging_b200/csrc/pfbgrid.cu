@@ -122,6 +122,7 @@ struct pfbg_plan {
   size_t fft_work = 0;
   int64_t nrow = 0, nvis = 0, nactive = 0;
   bool bound = false, has_mask = false, has_wgt = false;
+  bool beam_on_device = false;  // img_beam holds the beam of the last host-pointer Hessian call
   size_t total_bytes = 0;
   // profiling
   bool profiling = false;
@@ -1156,7 +1157,14 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   const void *dx = x, *dbeam = beam;
   const bool pin_in = flags & PFBG_PINNED_IN, pin_out = flags & PFBG_PINNED_OUT;
   CKRC(fetch(pl, pl->img_in, x, img_bytes, dev, s, &dx, 0, pin_in));
-  if (beam) CKRC(fetch(pl, pl->img_beam, beam, img_bytes, dev, s, &dbeam, (img_bytes + 4095) & ~(size_t)4095));
+  if (beam) {
+    if (!dev && (flags & PFBG_BEAM_CACHED) && pl->beam_on_device && pl->img_beam.bytes >= img_bytes) {
+      dbeam = pl->img_beam.p;  // same beam as the previous call (per-band constant, operators/hessian.py:91-98)
+    } else {
+      CKRC(fetch(pl, pl->img_beam, beam, img_bytes, dev, s, &dbeam, (img_bytes + 4095) & ~(size_t)4095));
+      pl->beam_on_device = !dev;
+    }
+  }
   CKRC(dev_alloc(pl, pl->mvis, (size_t)(pl->nactive ? pl->nactive : 1) * 2 * rb));
   const void* dwgt = pl->has_wgt ? pl->wgt.p : nullptr;
   if (!dev) {

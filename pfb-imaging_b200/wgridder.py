@@ -80,6 +80,7 @@ class GridderPlan:
 
     # -- binding ------------------------------------------------------------
     def bind(self, uvw, freq, mask=None, stream=None):
+        self._beam_fp = None
         uvw = np.ascontiguousarray(uvw, dtype=np.float64)
         freq = np.ascontiguousarray(freq, dtype=np.float64)
         if uvw.ndim != 2 or uvw.shape[1] != 3:
@@ -208,6 +209,13 @@ class GridderPlan:
         res = self._out_img(out, "out")
         tmp = res if res.flags.c_contiguous else np.empty(res.shape, res.dtype)
         flags = _lib.HOST_PTRS
+        if beam is not None:
+            # the beam of a band never changes between applies: upload it once (address + size + a strided checksum
+            # identify it; PFBG_BEAM_CACHE=0 re-uploads every call)
+            fp = (beam.ctypes.data, beam.nbytes, float(beam.ravel()[:: max(1, beam.size // 509)].sum(dtype=np.float64)))
+            if _BEAM_CACHE and fp == getattr(self, "_beam_fp", None):
+                flags |= _lib.BEAM_CACHED
+            self._beam_fp = fp
         if _pinned(x):
             flags |= _lib.PINNED_IN
         if out is not None and _pinned(tmp):  # a fresh output array is never seen twice
@@ -247,6 +255,7 @@ class GridderPlan:
 # The registration is dropped when the owning ndarray is garbage collected (weakref finaliser, which runs
 # before numpy releases the data) or when the table overflows.
 # ---------------------------------------------------------------------------
+_BEAM_CACHE = __import__("os").environ.get("PFBG_BEAM_CACHE", "1") != "0"
 _PIN_SEEN: dict = {}
 _PIN_REG: dict = {}
 _PIN_MAX_BYTES = int(__import__("os").environ.get("PFBG_PIN_MAX_MB", "4096")) << 20

@@ -446,3 +446,25 @@ def test_recurring_host_buffers_are_page_locked_and_results_unchanged(gpu):
         del x, out
         gc.collect()
         assert len(W._PIN_REG) == 0
+
+
+def test_beam_is_cached_on_the_device_between_applies(gpu):
+    """hessian_slice gets the band's beam on every call (operators/hessian.py:15-35); it is uploaded once and re-used
+    while (address, size, strided checksum) stay the same, and re-uploaded when the beam changes."""
+    p = small_problem(nrow=300, nchan=2, nx=128, ny=96, seed=9)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((128, 96))
+    beam = rng.uniform(0.2, 1.0, (128, 96))
+    kw = dict(uvw=p["uvw"], weight=p["wgt"], vis_mask=p["mask"], freq=p["freq"], cell=p["cell"], epsilon=1e-7, wsum=2.0, eta=0.3)
+    ops.clear_plan_cache()
+    a = ops.hessian_slice(x, beam=beam, **kw)
+    b = ops.hessian_slice(x, beam=beam, **kw)       # cached beam
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-9 * np.abs(a).max())
+    beam2 = beam * 0.5
+    c = ops.hessian_slice(x, beam=beam2, **kw)      # new beam: uploaded again
+    ref = 0.25 * (a - 0.3 * x) + 0.3 * x             # beam enters twice, the ridge term not at all
+    np.testing.assert_allclose(c, ref, rtol=0, atol=1e-9 * np.abs(a).max())
+    beam[...] = beam2                                # in-place change of the first array is noticed (checksum)
+    d = ops.hessian_slice(x, beam=beam, **kw)
+    np.testing.assert_allclose(d, ref, rtol=0, atol=1e-9 * np.abs(a).max())
+    ops.clear_plan_cache()
