@@ -71,6 +71,11 @@ int pfbs_primal_step(int32_t precision, int32_t device, void* x, const void* xp,
 int pfbs_norm_diff(int32_t precision, int32_t device, const void* x, const void* xp, int64_t n, double* num_den,
                    void* stream);
 
+/* out2[0] = <a, b>, out2[1] = <c, d> on device arrays (host output; synchronises the stream): the scalar products of
+ * the device-resident conjugate gradients (opt/pcg.py:35-41, 77-85) */
+int pfbs_dot2(int32_t precision, int32_t device, const void* a, const void* b, const void* c, const void* d, int64_t n,
+              double* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,7 @@ SIGNATURES = {
     "pfbs_axpby": (C.c_int, [_i32, _i32, _vp, _dbl, _vp, _dbl, _vp, _i64, _vp]),
     "pfbs_extrapolate": (C.c_int, [_i32, _i32, _vp, _vp, _i64, _vp]),
     "pfbs_primal_step": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _dbl, _i32, _i32, _i64, _vp]),
+    "pfbs_dot2": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i64, C.POINTER(_dbl), _vp]),
     "pfbs_norm_diff": (C.c_int, [_i32, _i32, _vp, _vp, _i64, C.POINTER(_dbl), _vp]),
 }
 

@@ -343,25 +343,54 @@ extern "C" int pfbs_primal_step(int32_t precision, int32_t device, void* x, cons
   return PFBG_OK;
 }
 
+// two doubles of device scratch per device for the reductions (allocated once: no cudaMalloc / cudaFree, which
+// synchronises the device, inside the solver loops)
+static double* reduce_scratch(int device) {
+  static double* buf[64] = {nullptr};
+  if (device < 0 || device >= 64) return nullptr;
+  if (!buf[device] && cudaMalloc(&buf[device], 64) != cudaSuccess) { cudaGetLastError(); buf[device] = nullptr; }
+  return buf[device];
+}
+
+template <typename K>
+static int reduce2(int device, cudaStream_t s, double* out2, K launch) {
+  double* acc = reduce_scratch(device);
+  if (!acc) return pfbg_fail(PFBG_ERR_NOMEM, "no reduction scratch on device %d", device);
+  SCK(cudaMemsetAsync(acc, 0, 16, s));
+  launch(acc);
+  pfbg_count_launch();
+  SCK(cudaGetLastError());
+  SCK(cudaMemcpyAsync(out2, acc, 16, cudaMemcpyDeviceToHost, s));
+  SCK(cudaStreamSynchronize(s));
+  return PFBG_OK;
+}
+
 extern "C" int pfbs_norm_diff(int32_t precision, int32_t device, const void* x, const void* xp, int64_t n,
                               double* num_den, void* stream) {
   if (!x || !xp || !num_den) return pfbg_fail(PFBG_ERR_ARG, "null argument");
+  if (precision != PFBG_F32 && precision != PFBG_F64) return pfbg_fail(PFBG_ERR_ARG, "bad precision");
   SCK(cudaSetDevice(device));
   cudaStream_t s = (cudaStream_t)stream;
   num_den[0] = num_den[1] = 0.0;
   if (n <= 0) return PFBG_OK;
-  double* acc = nullptr;
-  SCK(cudaMalloc(&acc, 16));
-  cudaError_t e = cudaMemsetAsync(acc, 0, 16, s);
-  if (e == cudaSuccess) {
-    const unsigned grd = n < (int64_t)1184 * 256 ? nblk(n) : 1184;  // 148 SMs x 8 CTAs
+  const unsigned grd = n < (int64_t)1184 * 256 ? nblk(n) : 1184;  // 148 SMs x 8 CTAs
+  return reduce2(device, s, num_den, [&](double* acc) {
     if (precision == PFBG_F32) k_norm_diff<float><<<grd, 256, 0, s>>>((const float*)x, (const float*)xp, n, acc);
     else k_norm_diff<double><<<grd, 256, 0, s>>>((const double*)x, (const double*)xp, n, acc);
-    pfbg_count_launch();
-    e = cudaMemcpyAsync(num_den, acc, 16, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  }
-  cudaFree(acc);
-  if (e != cudaSuccess) return pfbg_fail(PFBG_ERR_CUDA, "norm_diff failed: %s", cudaGetErrorString(e));
-  return PFBG_OK;
+  });
+}
+
+extern "C" int pfbs_dot2(int32_t precision, int32_t device, const void* a, const void* b, const void* c, const void* d,
+                         int64_t n, double* out2, void* stream) {
+  if (!a || !b || !c || !d || !out2) return pfbg_fail(PFBG_ERR_ARG, "null argument");
+  if (precision != PFBG_F32 && precision != PFBG_F64) return pfbg_fail(PFBG_ERR_ARG, "bad precision");
+  SCK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  out2[0] = out2[1] = 0.0;
+  if (n <= 0) return PFBG_OK;
+  const unsigned grd = n < (int64_t)1184 * 256 ? nblk(n) : 1184;
+  return reduce2(device, s, out2, [&](double* acc) {
+    if (precision == PFBG_F32) k_dot2<float><<<grd, 256, 0, s>>>((const float*)a, (const float*)b, (const float*)c, (const float*)d, n, acc);
+    else k_dot2<double><<<grd, 256, 0, s>>>((const double*)a, (const double*)b, (const double*)c, (const double*)d, n, acc);
+  });
 }

@@ -267,3 +267,22 @@ __global__ void k_norm_diff(const T* __restrict__ x, const T* __restrict__ xp, i
     atomicAdd(acc + 1, den);
   }
 }
+
+// acc[0] += <a, b>, acc[1] += <c, d> (fp64 accumulation): the scalar products of the device-resident CG / power method
+template <typename T>
+__global__ void k_dot2(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, const T* __restrict__ d,
+                       int64_t n, double* __restrict__ acc) {
+  double s0 = 0, s1 = 0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    s0 += (double)a[k] * (double)b[k];
+    s1 += (double)c[k] * (double)d[k];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(acc, s0);
+    atomicAdd(acc + 1, s1);
+  }
+}

@@ -21,6 +21,8 @@ from __future__ import annotations
 import os
 from collections import OrderedDict
 
+import ctypes as C
+
 import numpy as np
 
 from .wgridder import GridderPlan, dirty2vis, plan_for, vis2dirty
@@ -387,6 +389,22 @@ class BandHessian:
 
     hdot = dot  # self-adjoint
 
+    def dot_dev(self, x_ptr, out_ptr, stream=None):
+        """Same operator on device pointers (asynchronous on `stream`); the beam is uploaded once."""
+        if self.beam is not None and getattr(self, "_beam_t", None) is None:
+            import torch
+
+            self._beam_t = torch.from_numpy(self.beam).to(torch.device("cuda", self.gp.device))
+        bp = None if self.beam is None else C.c_void_p(self._beam_t.data_ptr())
+        self.gp.hessian_dev(x_ptr, bp, self.wsum, self.eta, out_ptr, stream)
+
+    def cg(self, rhs, x0=None, tol=1e-5, maxit=500, minit=1, verbosity=0, report_freq=10):
+        """Solve H x = rhs by conjugate gradients with all vectors on the device (band_worker.py:124-140)."""
+        from .solvers import pcg_device
+
+        return pcg_device(self.dot_dev, np.ascontiguousarray(rhs, dtype=self.gp.rdt), x0=x0, tol=tol, maxit=maxit,
+                          minit=minit, verbosity=verbosity, report_freq=report_freq, device=self.gp.device)
+
     def residual(self, dirty, model):
         """dirty - R^H W R (beam * model)   (band_worker.py:167-180)."""
         xin = np.ascontiguousarray(model if self.beam is None else self.beam * model, dtype=self.gp.rdt)
@@ -429,8 +447,11 @@ class BandPool:
         out = np.zeros_like(rhs)
         for b, op in self.ops.items():
             xb = None if x0 is None else np.array(x0[b], copy=True)
-            out[b] = pcg(op.dot, np.ascontiguousarray(rhs[b]), x0=xb, tol=tol, maxit=maxit, minit=minit,
-                         verbosity=verbosity)
+            if hasattr(op, "cg"):  # device-resident CG of the band operator
+                out[b] = op.cg(rhs[b], x0=xb, tol=tol, maxit=maxit, minit=minit, verbosity=verbosity)
+            else:
+                out[b] = pcg(op.dot, np.ascontiguousarray(rhs[b]), x0=xb, tol=tol, maxit=maxit, minit=minit,
+                             verbosity=verbosity)
         return self._finish(out)
 
     def residual(self, model, dirty, cell_rad=None, epsilon=None, do_wgridding=None, double_accum=None):

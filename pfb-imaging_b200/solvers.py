@@ -98,3 +98,72 @@ def power_method(aop, imsize, b0=None, tol=1e-5, maxit=250, verbosity=1, report_
         print(f"Maximum iterations reached. eps = {eps:.3e}, beta = {beta:.3e}" if k == maxit
               else f"Success, converged after {k} iterations. beta = {beta:.3e}")
     return beta, b
+
+
+def pcg_device(apply_dev, b, x0=None, tol=1e-5, maxit=500, minit=100, verbosity=1, report_freq=10, device=0, reduce=None):
+    """Conjugate gradients with every vector resident on the device (identity preconditioner).
+
+    Same iteration and stopping contract as `pcg` (``opt/pcg.py:202-314``).  `apply_dev(in_ptr, out_ptr, stream)`
+    applies the operator to device arrays (e.g. ``GridderPlan.hessian_dev`` with the band's beam / wsum / eta bound);
+    `b` / `x0` are numpy arrays, the solution comes back as numpy.  Per iteration: one operator apply, three axpby
+    kernels and two fused dot-product kernels; ``eps = ||x - x_prev|| / ||x||`` is formed as ``|alpha| ||p|| / ||x||``
+    so no copy of the previous iterate is kept.  `reduce` sums the scalar pairs over ranks for band-sharded cubes."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    rdt = np.dtype(b.dtype)
+    prec = _lib.PFBG_F32 if rdt == np.float32 else _lib.PFBG_F64
+    dev = torch.device("cuda", device)
+    bt = torch.from_numpy(np.ascontiguousarray(b)).to(dev)
+    x = torch.zeros_like(bt) if x0 is None else torch.from_numpy(np.ascontiguousarray(x0, dtype=rdt)).to(dev)
+    r, p, ap = torch.empty_like(bt), torch.empty_like(bt), torch.empty_like(bt)
+    s = torch.cuda.current_stream(dev).cuda_stream
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    n = bt.numel()
+    out2 = (C.c_double * 2)()
+
+    def axpby(out, a, xx, bb, yy):
+        _lib.check(lib.pfbs_axpby(prec, device, ptr(out), float(a), ptr(xx), float(bb), ptr(yy), n, s))
+
+    def dot2(a, bq, c, d):
+        _lib.check(lib.pfbs_dot2(prec, device, ptr(a), ptr(bq), ptr(c), ptr(d), n, out2, s))
+        loc = np.array([out2[0], out2[1]])
+        return reduce(loc) if reduce is not None else loc
+
+    apply_dev(ptr(x), ptr(r), s)
+    axpby(r, 1.0, r, -1.0, bt)          # r = A x - b
+    rho = dot2(r, r, r, r)[0]
+    if not rho > 0.0:
+        if verbosity:
+            print("Initial residual is zero")
+        return x.cpu().numpy()
+    axpby(p, -1.0, r, 0.0, r)           # p = -r
+    phi0 = rho if np.isfinite(rho) else 1.0
+    k, eps, stalls = 0, 1.0, 0
+    while (eps > tol or k < minit) and k < maxit and stalls < 5:
+        apply_dev(ptr(p), ptr(ap), s)
+        pap, pp = dot2(p, ap, p, p)
+        alpha = rho / pap
+        axpby(x, 1.0, x, alpha, p)
+        axpby(r, 1.0, r, alpha, ap)
+        rho_next, xx = dot2(r, r, x, x)
+        axpby(p, rho_next / rho, p, -1.0, r)
+        rho = rho_next
+        k += 1
+        eps_prev, eps = eps, (abs(alpha) * np.sqrt(pp / xx) if xx > 0 else 0.0)
+        if abs(eps_prev - eps) < 1e-3 * tol:
+            stalls += 1
+        if verbosity > 1 and k % report_freq == 0:
+            print(f"At iteration {k} eps = {eps:.3e}, phi = {rho / phi0:.3e}")
+    if verbosity:
+        if k >= maxit:
+            print(f"Max iters reached. eps = {eps:.3e}")
+        elif stalls >= 5:
+            print(f"Stalled after {k} iterations with eps = {eps:.3e}")
+        else:
+            print(f"Success, converged after {k} iterations")
+    return x.cpu().numpy()

@@ -57,3 +57,26 @@ def test_band_pool_roles(gpu):
     assert np.array_equal(res0, dirty)
     pool.close()
     ops.clear_plan_cache()
+
+
+def test_device_resident_cg_matches_host_cg(gpu):
+    """BandHessian.cg keeps every CG vector on the device; same iterates as solvers.pcg on the numpy operator."""
+    p = small_problem(nrow=2500, nchan=2, nx=48, ny=40, seed=4)
+    wsum = float(p["wgt"][p["mask"] != 0].sum())
+    rng = np.random.default_rng(1)
+    beam = rng.uniform(0.5, 1.0, (48, 40))
+    op = ops.BandHessian(p["uvw"], p["freq"], p["wgt"], p["mask"], 48, 40, p["cell"], beam=beam, epsilon=1e-9, eta=5e-3,
+                         wsum=wsum)
+    model = np.zeros((48, 40))
+    model[10, 12], model[30, 7] = 2.0, -1.0
+    rhs = op.dot(model)
+    for maxit in (7, 150):  # a fixed number of iterations (same iterates) and a converged solve
+        a = solvers.pcg(op.dot, rhs, x0=np.zeros_like(rhs), tol=1e-10, maxit=maxit, minit=1, verbosity=0)
+        b = op.cg(rhs, tol=1e-10, maxit=maxit, minit=1)
+        assert rel_l2(b, a) <= 1e-7
+    assert rel_l2(b, model) <= 1e-3
+    x0 = 0.5 * model
+    c = op.cg(rhs, x0=x0, tol=1e-10, maxit=150, minit=1)
+    assert rel_l2(c, model) <= 1e-3
+    assert not op.cg(np.zeros_like(rhs), tol=1e-10, maxit=5).any()  # zero right-hand side: "initial residual is zero"
+    op.close()
