@@ -468,3 +468,22 @@ def test_beam_is_cached_on_the_device_between_applies(gpu):
     d = ops.hessian_slice(x, beam=beam, **kw)
     np.testing.assert_allclose(d, ref, rtol=0, atol=1e-9 * np.abs(a).max())
     ops.clear_plan_cache()
+
+
+@pytest.mark.parametrize("prec,eps", [("single", 1e-4), ("double", 1e-7)])
+@pytest.mark.parametrize("nx,ny", [(50, 76), (130, 42)])
+def test_image_sizes_off_the_vector_path(gpu, prec, eps, nx, ny):
+    """ny not a multiple of 8: the fused transforms take their scalar fill / drain loops."""
+    p = small_problem(nrow=400, nchan=2, nx=nx, ny=ny, seed=nx)
+    rdt, cdt = (np.float32, np.complex64) if prec == "single" else (np.float64, np.complex128)
+    kw = dict(center_x=0.0, center_y=0.0, flip_u=False, flip_v=True, flip_w=False, do_wgridding=True, divide_by_n=True)
+    with W.plan_for(p["uvw"], p["freq"], npix_x=nx, npix_y=ny, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=eps,
+                    precision=prec, mask=p["mask"], **kw) as gp:
+        act = p["mask"] != 0
+        v = gp.degrid(p["img"].astype(rdt))
+        ref = dft.dft_dirty2vis(p["uvw"], p["freq"], p["img"], p["cell"], p["cell"], **kw)
+        assert rel_l2(v[act], ref[act]) <= eps
+        d = gp.grid(p["vis"].astype(cdt), p["wgt"].astype(rdt))
+        dref = dft.dft_vis2dirty(p["uvw"], p["freq"], p["vis"].astype(cdt), p["wgt"].astype(rdt), p["mask"], nx, ny,
+                                 p["cell"], p["cell"], **kw)
+        assert rel_l2(d, dref) <= eps
