@@ -882,12 +882,9 @@ static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_
     if (out_sorted) CK(cudaMemsetAsync(out_sorted, 0, (size_t)pl->nactive * sizeof(C), s));
     else if (!pl->has_mask || (vis_zeroed == 0)) CK(cudaMemsetAsync(vis_out, 0, (size_t)pl->nvis * sizeof(C), s));
     const size_t psm = (size_t)WIDE_WARPS * 16 * 32 * sizeof(C);  // per-sample lane partials (see k_degrid_runs_wide)
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[sizeof(T) == 8]) {
-      CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 3, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-      CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-      attr_set[sizeof(T) == 8] = true;
-    }
+    // (per device and cheap: set on every launch rather than caching it per process)
+    if (pl->gp.W <= 12) CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 3, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    else CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     if (pl->gp.W <= 12)
       k_degrid_runs_wide<T, 3, 6, 4><<<wide_blocks(pl, pl->nactive, 4), WIDE_WARPS * 32, psm, s>>>(
           pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
