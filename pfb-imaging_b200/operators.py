@@ -405,6 +405,13 @@ class BandHessian:
         return pcg_device(self.dot_dev, np.ascontiguousarray(rhs, dtype=self.gp.rdt), x0=x0, tol=tol, maxit=maxit,
                           minit=minit, verbosity=verbosity, report_freq=report_freq, device=self.gp.device)
 
+    def spectral_norm(self, tol=1e-5, maxit=250, verbosity=0, seed=None):
+        """Largest eigenvalue of the band Hessian by device-resident power iteration (opt/power_method.py:40-92)."""
+        from .solvers import power_method_device
+
+        return power_method_device(self.dot_dev, (self.nx, self.ny), dtype=self.gp.rdt, tol=tol, maxit=maxit,
+                                   verbosity=verbosity, device=self.gp.device, seed=seed)
+
     def residual(self, dirty, model):
         """dirty - R^H W R (beam * model)   (band_worker.py:167-180)."""
         xin = np.ascontiguousarray(model if self.beam is None else self.beam * model, dtype=self.gp.rdt)

@@ -167,3 +167,49 @@ def pcg_device(apply_dev, b, x0=None, tol=1e-5, maxit=500, minit=100, verbosity=
         else:
             print(f"Success, converged after {k} iterations")
     return x.cpu().numpy()
+
+
+def power_method_device(apply_dev, shape, dtype=np.float64, b0=None, tol=1e-5, maxit=250, verbosity=1, report_freq=25,
+                        device=0, reduce=None, seed=None):
+    """Power iteration with the vector resident on the device (``opt/power_method.py:40-92`` contract: stop on the
+    relative change of the Rayleigh quotient).  `apply_dev(in_ptr, out_ptr, stream)` as in `pcg_device`.
+    Returns ``(beta, b)`` with `b` a numpy array."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib
+
+    lib = _lib.load()
+    rdt = np.dtype(dtype)
+    prec = _lib.PFBG_F32 if rdt == np.float32 else _lib.PFBG_F64
+    dev = torch.device("cuda", device)
+    b = np.random.default_rng(seed).standard_normal(shape) if b0 is None else np.asarray(b0)
+    bt = torch.from_numpy(np.ascontiguousarray(b, dtype=rdt)).to(dev)
+    ab = torch.empty_like(bt)
+    s = torch.cuda.current_stream(dev).cuda_stream
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    n = bt.numel()
+    out2 = (C.c_double * 2)()
+
+    def dot2(a, bq, c, d):
+        _lib.check(lib.pfbs_dot2(prec, device, ptr(a), ptr(bq), ptr(c), ptr(d), n, out2, s))
+        loc = np.array([out2[0], out2[1]])
+        return reduce(loc) if reduce is not None else loc
+
+    nrm2 = dot2(bt, bt, bt, bt)[0]
+    _lib.check(lib.pfbs_axpby(prec, device, ptr(bt), 1.0 / np.sqrt(nrm2), ptr(bt), 0.0, ptr(bt), n, s))
+    beta, eps, k = 1.0, 1.0, 0
+    while eps > tol and k < maxit:
+        apply_dev(ptr(bt), ptr(ab), s)
+        num, nrm2 = dot2(bt, ab, ab, ab)  # b is unit norm: the Rayleigh quotient is <b, A b>
+        beta_prev, beta = beta, num
+        _lib.check(lib.pfbs_axpby(prec, device, ptr(bt), 1.0 / np.sqrt(nrm2), ptr(ab), 0.0, ptr(ab), n, s))
+        eps = abs(beta - beta_prev) / abs(beta_prev)
+        k += 1
+        if verbosity > 1 and k % report_freq == 0:
+            print(f"At iteration {k} eps = {eps:.3e}")
+    if verbosity:
+        print(f"Maximum iterations reached. eps = {eps:.3e}, beta = {beta:.3e}" if k == maxit
+              else f"Success, converged after {k} iterations. beta = {beta:.3e}")
+    return beta, bt.cpu().numpy()

@@ -80,3 +80,17 @@ def test_device_resident_cg_matches_host_cg(gpu):
     assert rel_l2(c, model) <= 1e-3
     assert not op.cg(np.zeros_like(rhs), tol=1e-10, maxit=5).any()  # zero right-hand side: "initial residual is zero"
     op.close()
+
+
+def test_device_power_method_matches_host(gpu):
+    p = small_problem(nrow=1500, nchan=2, nx=32, ny=40, seed=6)
+    wsum = float(p["wgt"][p["mask"] != 0].sum())
+    op = ops.BandHessian(p["uvw"], p["freq"], p["wgt"], p["mask"], 32, 40, p["cell"], epsilon=1e-8, eta=1e-2, wsum=wsum)
+    b0 = np.random.default_rng(3).standard_normal((32, 40))
+    beta_h, v_h = solvers.power_method(op.dot, (32, 40), b0=b0, tol=1e-8, maxit=300, verbosity=0)
+    beta_d, v_d = solvers.power_method_device(op.dot_dev, (32, 40), b0=b0, tol=1e-8, maxit=300, verbosity=0)
+    assert abs(beta_d - beta_h) <= 1e-6 * abs(beta_h)
+    assert min(rel_l2(v_d, v_h), rel_l2(v_d, -v_h)) <= 1e-3
+    beta_s, _ = op.spectral_norm(tol=1e-8, maxit=300, seed=0)
+    assert abs(beta_s - beta_h) <= 1e-2 * abs(beta_h)  # other start vector; the stopping rule is on the change of beta
+    op.close()
