@@ -1498,7 +1498,20 @@ extern "C" int pfbg_conv_set_kernel(pfbg_conv* cv, const void* khat, int32_t hal
   const size_t cb = cv->precision == PFBG_F32 ? 8 : 16;
   const cudaMemcpyKind kind = (flags & PFBG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (!half) {
-    CK(cudaMemcpyAsync(cv->khat, khat, (size_t)ct.nxp * ct.nyp * cb, kind, s));
+    // keep the Hermitian part only (all a real image can see; the column stage evaluates half the columns)
+    const size_t fb = (size_t)ct.nxp * ct.nyp * cb;
+    void* df = nullptr;
+    CK(cudaMalloc(&df, fb));
+    cudaError_t e = cudaMemcpyAsync(df, khat, fb, kind, s);
+    if (e == cudaSuccess) {
+      dim3 grd((ct.nyp + 127) / 128, ct.nxp);
+      if (cv->precision == PFBG_F32) k_hermitize<float><<<grd, 128, 0, s>>>(ct.nxp, ct.nyp, (const cx2<float>*)df, (cx2<float>*)cv->khat);
+      else k_hermitize<double><<<grd, 128, 0, s>>>(ct.nxp, ct.nyp, (const cx2<double>*)df, (cx2<double>*)cv->khat);
+      LAUNCHED();
+      e = cudaStreamSynchronize(s);
+    }
+    cudaFree(df);
+    if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "set_kernel failed: %s", cudaGetErrorString(e));
   } else {
     const size_t hb = (size_t)ct.nxp * (ct.nyp / 2 + 1) * cb;
     void* dh = nullptr;
@@ -1527,9 +1540,11 @@ static int conv_apply_t(pfbg_conv* cv, const void* x, const void* beam, double e
   LAUNCHED();
   const int cc = cv->col_c;
   const size_t csm = fft_smem_bytes<T>(ct.nxp * cc);
-  if (cc == 4) k_conv_cols<T, 4><<<ct.nyp / 4, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
-  else if (cc == 2) k_conv_cols<T, 2><<<ct.nyp / 2, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
-  else k_conv_cols<T, 1><<<ct.nyp, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
+  // Hermitian symmetry (real image, real kernel): only the columns l <= nyp/2 are transformed (psfconv.cuh)
+  const int ncol = ct.nyp / 2 + 1;
+  if (cc == 4) k_conv_cols<T, 4><<<(ncol + 3) / 4, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
+  else if (cc == 2) k_conv_cols<T, 2><<<(ncol + 1) / 2, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
+  else k_conv_cols<T, 1><<<ncol, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
   LAUNCHED();
   const double scale = 1.0 / ((double)ct.nxp * (double)ct.nyp);
   k_conv_rows_inv<T><<<ct.nx, rt, fft_smem_bytes<T>(ct.nyp), s>>>(ct, (const cx2<T>*)cv->tmp, (const T*)beam,
