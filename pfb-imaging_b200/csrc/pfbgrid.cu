@@ -1536,7 +1536,7 @@ template <typename T>
 static int conv_apply_t(pfbg_conv* cv, const void* x, const void* beam, double eta, void* out, cudaStream_t s) {
   const ConvTabs& ct = cv->ct;
   const int rt = row_threads(ct.nyp, 256);
-  k_conv_rows_fwd<T><<<ct.nx, rt, fft_smem_bytes<T>(ct.nyp), s>>>(ct, (const T*)x, (const T*)beam, (cx2<T>*)cv->tmp);
+  k_conv_rows_fwd<T><<<(ct.nx + 1) / 2, rt, fft_smem_bytes<T>(ct.nyp), s>>>(ct, (const T*)x, (const T*)beam, (cx2<T>*)cv->tmp);
   LAUNCHED();
   const int cc = cv->col_c;
   const size_t csm = fft_smem_bytes<T>(ct.nxp * cc);
@@ -1547,7 +1547,7 @@ static int conv_apply_t(pfbg_conv* cv, const void* x, const void* beam, double e
   else k_conv_cols<T, 1><<<ncol, 512, csm, s>>>(ct, (const cx2<T>*)cv->khat, (cx2<T>*)cv->tmp);
   LAUNCHED();
   const double scale = 1.0 / ((double)ct.nxp * (double)ct.nyp);
-  k_conv_rows_inv<T><<<ct.nx, rt, fft_smem_bytes<T>(ct.nyp), s>>>(ct, (const cx2<T>*)cv->tmp, (const T*)beam,
+  k_conv_rows_inv<T><<<(ct.nx + 1) / 2, rt, fft_smem_bytes<T>(ct.nyp), s>>>(ct, (const cx2<T>*)cv->tmp, (const T*)beam,
                                                                  eta != 0.0 ? (const T*)x : nullptr, scale, eta, (T*)out);
   LAUNCHED();
   CK(cudaGetLastError());

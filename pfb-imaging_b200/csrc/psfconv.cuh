@@ -19,43 +19,51 @@ struct ConvTabs {
   int nx, ny, nxp, nyp;
 };
 
-// image rows -> tmp (nx, nyp): FFT along v of the zero-padded row, image placed at columns 0..ny-1
+// image rows -> tmp (nx, nyp): FFT along v of the zero-padded rows, image placed at columns 0..ny-1.
+// The rows are real, so TWO of them share one complex transform: z = x_a + i x_b,
+//   X_a[l] = (Z[l] + conj Z[N-l]) / 2,   X_b[l] = (Z[l] - conj Z[N-l]) / (2i),
+// and only the half spectrum l <= nyp/2 is written (column nyp - l of every later stage is the conjugate of column l
+// because x and the kernel are real).  CTA i handles rows 2i and 2i+1.
 template <typename T>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2))
 k_conv_rows_fwd(ConvTabs ct, const T* __restrict__ x, const T* __restrict__ beam, cx2<T>* __restrict__ tmp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x, i = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int ia = 2 * blockIdx.x, ib = ia + 1;
+  const bool has_b = ib < ct.nx;
   for (int n = tid; n < ct.nyp; n += nthr) s[fft_pad<T>(n)] = {(T)0, (T)0};
   __syncthreads();
-  // fill / drain loops keep several independent global accesses in flight (they were latency-bound, like the
-  // plane-transform kernels before the same change)
   constexpr int U = 4;
-  const int64_t row = (int64_t)i * ct.ny;
+  const int64_t ra = (int64_t)ia * ct.ny, rb = (int64_t)ib * ct.ny;
   for (int j0 = tid; j0 < ct.ny; j0 += U * nthr) {
-    T xv[U], bv[U];
+    T va[U], vb[U];
     int pv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = j0 + u * nthr;
       if (j < ct.ny) {
-        xv[u] = x[row + j];
-        bv[u] = beam ? beam[row + j] : (T)1;
+        va[u] = x[ra + j];
+        vb[u] = has_b ? x[rb + j] : (T)0;
+        if (beam) { va[u] *= beam[ra + j]; if (has_b) vb[u] *= beam[rb + j]; }
         pv[u] = ct.pos_v[j];
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (j0 + u * nthr < ct.ny) s[fft_pad<T>(pv[u])] = {xv[u] * bv[u], (T)0};
+      if (j0 + u * nthr < ct.ny) s[fft_pad<T>(pv[u])] = {va[u], vb[u]};
   }
   __syncthreads();
   fft_dit<T, 1>(s, (const cx2<T>*)ct.tw_v, ct.dv, tid, nthr);
-  cx2<T>* dst = tmp + (int64_t)i * ct.nyp;
-  // x (and beam) are real and khat is the transform of a real kernel, so column nyp - l of every later stage is the
-  // complex conjugate of column l: only l <= nyp/2 (rounded up to a column block) is written / transformed
-  const int nkeep = min(ct.nyp, ((ct.nyp / 2 + 1 + 3) / 4) * 4);
-#pragma unroll 4
-  for (int n = tid; n < nkeep; n += nthr) dst[n] = s[fft_pad<T>(n)];
+  cx2<T>* da = tmp + (int64_t)ia * ct.nyp;
+  cx2<T>* db = tmp + (int64_t)ib * ct.nyp;
+  const int nkeep = min(ct.nyp, ((ct.nyp / 2 + 1 + 3) / 4) * 4);  // half spectrum, rounded up to a column block
+#pragma unroll 2
+  for (int l = tid; l < nkeep; l += nthr) {
+    const cx2<T> zl = s[fft_pad<T>(l)], zm = s[fft_pad<T>(l == 0 ? 0 : ct.nyp - l)];
+    da[l] = {(T)0.5 * (zl.x + zm.x), (T)0.5 * (zl.y - zm.y)};
+    if (has_b) db[l] = {(T)0.5 * (zl.y + zm.y), (T)0.5 * (zm.x - zl.x)};
+  }
 }
 
 // column block: forward along u, multiply by khat[k][b], inverse along u, keep rows < nx
@@ -111,32 +119,46 @@ k_conv_cols(ConvTabs ct, const cx2<T>* __restrict__ khat, cx2<T>* __restrict__ t
   }
 }
 
-// tmp rows -> image: inverse FFT along v, crop, normalise, beam, ridge
+// tmp rows -> image: inverse FFT along v, crop, normalise, beam, ridge.  Two rows per transform again: with the half
+// spectra Y_a, Y_b of the two (real) output rows, S[l] = Y_a[l] + i Y_b[l], S[N-l] = conj Y_a[l] + i conj Y_b[l], and
+// the inverse transform of S is y_a + i y_b.  (The inverse is evaluated as conj o forward o conj.)
 template <typename T>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2))
 k_conv_rows_inv(ConvTabs ct, const cx2<T>* __restrict__ tmp, const T* __restrict__ beam, const T* __restrict__ xin,
                 double scale, double eta, T* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x, i = blockIdx.x;
-  const cx2<T>* src = tmp + (int64_t)i * ct.nyp;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int ia = 2 * blockIdx.x, ib = ia + 1;
+  const bool has_b = ib < ct.nx;
+  const cx2<T>* sa = tmp + (int64_t)ia * ct.nyp;
+  const cx2<T>* sb = tmp + (int64_t)ib * ct.nyp;
   const int nh = ct.nyp / 2;
-#pragma unroll 4
-  for (int n = tid; n < ct.nyp; n += nthr) {
-    // columns above nyp/2 are the conjugates of their mirrors (never computed); the inverse transform itself is
-    // conj o forward o conj, so the mirrored half is loaded as is and the computed half conjugated
-    cx2<T> v = src[n <= nh ? n : ct.nyp - n];
-    if (n <= nh) v.y = -v.y;
-    s[fft_pad<T>(n)] = v;
+#pragma unroll 2
+  for (int l = tid; l <= nh; l += nthr) {
+    const cx2<T> ya = sa[l];
+    const cx2<T> yb = has_b ? sb[l] : cx2<T>{(T)0, (T)0};
+    s[fft_pad<T>(l)] = {ya.x - yb.y, -(ya.y + yb.x)};                                   // conj S[l]
+    if (l > 0 && 2 * l < ct.nyp) s[fft_pad<T>(ct.nyp - l)] = {ya.x + yb.y, ya.y - yb.x};  // conj S[N-l]
   }
   __syncthreads();
   fft_dif<T, 1>(s, (const cx2<T>*)ct.tw_v, ct.dv, tid, nthr);
   for (int j = tid; j < ct.ny; j += nthr) {
-    const int64_t pix = (int64_t)i * ct.ny + j;
-    double r = (double)s[fft_pad<T>(ct.pos_v[j])].x * scale;  // real part of conj(.) is the same
-    if (beam) r *= (double)beam[pix];
-    if (xin) r += eta * (double)xin[pix];
-    out[pix] = (T)r;
+    const cx2<T> v = s[fft_pad<T>(ct.pos_v[j])];  // conj of the inverse transform: (y_a, -y_b)
+    {
+      const int64_t pix = (int64_t)ia * ct.ny + j;
+      double r = (double)v.x * scale;
+      if (beam) r *= (double)beam[pix];
+      if (xin) r += eta * (double)xin[pix];
+      out[pix] = (T)r;
+    }
+    if (has_b) {
+      const int64_t pix = (int64_t)ib * ct.ny + j;
+      double r = -(double)v.y * scale;
+      if (beam) r *= (double)beam[pix];
+      if (xin) r += eta * (double)xin[pix];
+      out[pix] = (T)r;
+    }
   }
 }
 

@@ -22,7 +22,8 @@ def ref_hessian_psf(x, abspsf, ny_psf, beam=None, eta=None):
     return out
 
 
-@pytest.mark.parametrize("nx,ny,nxp,nyp", [(64, 48, 96, 80), (100, 100, 140, 154), (128, 128, 176, 176), (32, 32, 32, 32)])
+@pytest.mark.parametrize("nx,ny,nxp,nyp", [(64, 48, 96, 80), (100, 100, 140, 154), (128, 128, 176, 176), (32, 32, 32, 32),
+                                           (51, 37, 72, 60), (33, 64, 64, 90)])  # odd row counts: last row pair is half empty
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 def test_hessian_psf_slice_matches_numpy(gpu, nx, ny, nxp, nyp, dt):
     rng = np.random.default_rng(nx + nyp)
