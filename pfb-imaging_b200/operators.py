@@ -318,11 +318,6 @@ def grid_partition(part, counts, nx, ny, nx_psf, ny_psf, cell_rad, robustness=No
     from .weighting import counts_to_weights
 
     flip_u, flip_v, flip_w, x0, y0 = wgridder_conventions(l0, m0)
-    signu = -1.0 if flip_u else 1.0
-    signv = -1.0 if flip_v else 1.0
-    signx = -1.0 if flip_u else 1.0
-    signy = -1.0 if flip_v else 1.0
-    n = np.sqrt(1 - x0**2 - y0**2)
     uvw = _vals(part, "UVW")
     vis = _vals(part, "VIS")
     wgt = _vals(part, "WEIGHT").copy()
