@@ -59,6 +59,37 @@ def test_band_pool_roles(gpu):
     ops.clear_plan_cache()
 
 
+def test_band_pool_pipelined_matches_band_by_band(gpu, monkeypatch):
+    """hess_dot overlaps the copies of neighbouring bands with the kernels: same numbers as band by band,
+    for pageable and page-locked (second sighting) input cubes, a zero band and a band owned by another rank."""
+    nband, nx, ny = 4, 384, 352  # 1.08 MB per band in fp64: above the page-locking threshold
+    probs = {b: small_problem(nrow=600, nchan=2, nx=nx, ny=ny, seed=20 + b) for b in (0, 1, 3)}  # band 2: not ours
+    bands = {}
+    for b, p in probs.items():
+        wsum = float(p["wgt"][p["mask"] != 0].sum())
+        bands[b] = ops.BandHessian(p["uvw"], p["freq"], p["wgt"], p["mask"], nx, ny, p["cell"], epsilon=1e-8, eta=1e-2,
+                                   wsum=wsum)
+    pool = ops.BandPool(bands, nband=nband)
+    x = np.random.default_rng(5).standard_normal((nband, nx, ny))
+    x[1] = 0.0
+    monkeypatch.setenv("PFBG_POOL_PIPELINE", "0")
+    ref = pool.hess_dot(x)
+    monkeypatch.setenv("PFBG_POOL_PIPELINE", "1")
+    outs = [pool.hess_dot(x) for _ in range(3)]  # pageable, then page-locked input
+    for o in outs:
+        assert o.shape == x.shape and o.dtype == x.dtype
+        assert not o[1].any() and not o[2].any()
+        for b in (0, 3):
+            # sigma = 1.25 / W = 16 at this size: two applies of the SAME path already differ by ~5e-10 (the order of
+            # the grid atomics, amplified by 1 / psihat at the image edge); the bound is epsilon
+            assert rel_l2(o[b], ref[b]) <= 1e-8
+    assert outs[0] is not outs[1] and not np.shares_memory(outs[0], outs[1])  # every call returns its own array
+    y = np.random.default_rng(6).standard_normal((nband, nx, ny)).astype(np.float32)  # wrong dtype: band-by-band path
+    assert rel_l2(pool.hess_dot(y)[0], pool.hess_dot(y.astype(np.float64))[0]) <= 1e-6
+    pool.close()
+    ops.clear_plan_cache()
+
+
 def test_device_resident_cg_matches_host_cg(gpu):
     """BandHessian.cg keeps every CG vector on the device; same iterates as solvers.pcg on the numpy operator."""
     p = small_problem(nrow=2500, nchan=2, nx=48, ny=40, seed=4)
