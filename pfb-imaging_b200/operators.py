@@ -449,7 +449,8 @@ class BandPool:
     def hess_dot(self, x):
         """x: (nband, nx, ny) -> H x (band_worker.py:276-281).  The reference fans the bands out to concurrent
         actors; here the bands of one GPU are pipelined: while band b is being computed, band b+1 is on its way
-        to the device and band b-1 on its way back (three streams), so the PCIe time hides behind the kernels."""
+        to the device and band b-1 on its way back (copy-in, copy-out and two compute streams), so the PCIe time hides
+        behind the kernels and the tail of one band's kernels overlaps the head of the next band's."""
         x = np.asarray(x)
         if self._pipelined_ok(x):
             return self._finish(self._hess_dot_pipelined(x))
@@ -473,6 +474,7 @@ class BandPool:
 
         from .wgridder import _pinned
 
+        NS = 4
         ops_ = list(self.ops.items())
         dev = torch.device("cuda", ops_[0][1].gp.device)
         tdt = torch.from_numpy(np.empty(0, x.dtype)).dtype
@@ -481,14 +483,17 @@ class BandPool:
             with torch.cuda.device(dev):
                 st = self._pipe = {
                     "shape": x.shape[1:], "dtype": tdt,
-                    "s_in": torch.cuda.Stream(dev), "s_cmp": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
-                    # two slots each way: band b+1 arrives / band b-1 leaves while band b is computed
-                    "xd": torch.empty((2,) + x.shape[1:], dtype=tdt, device=dev),
-                    "od": torch.empty((2,) + x.shape[1:], dtype=tdt, device=dev),
+                    "s_in": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                    # slot k computes on its own stream: the tail of one band's kernels overlaps the next band's head
+                    "s_cmp": [torch.cuda.Stream(dev), torch.cuda.Stream(dev)],
+                    # four slots each way (two per compute stream): bands b+1, b+2 arrive / b-1, b-2 leave while
+                    # band b is computed
+                    "xd": torch.empty((NS,) + x.shape[1:], dtype=tdt, device=dev),
+                    "od": torch.empty((NS,) + x.shape[1:], dtype=tdt, device=dev),
                     "xh": None,
-                    "ev_in": [torch.cuda.Event() for _ in range(2)], "ev_cmp": [torch.cuda.Event() for _ in range(2)],
-                    "ev_free_x": [torch.cuda.Event() for _ in range(2)],
-                    "ev_free_o": [torch.cuda.Event() for _ in range(2)],
+                    "ev_in": [torch.cuda.Event() for _ in range(NS)], "ev_cmp": [torch.cuda.Event() for _ in range(NS)],
+                    "ev_free_x": [torch.cuda.Event() for _ in range(NS)],
+                    "ev_free_o": [torch.cuda.Event() for _ in range(NS)],
                 }
         # a fresh result every call, but from torch's caching pinned allocator: the block of a result the caller
         # has dropped is handed out again, so the device -> host copies are single DMAs into page-locked memory
@@ -500,15 +505,16 @@ class BandPool:
                     out[b] = 0
         x_pinned = _pinned(x)  # page-locked at its second sighting (solver work arrays come back)
         if not x_pinned and st["xh"] is None:
-            st["xh"] = torch.empty((2,) + x.shape[1:], dtype=tdt, pin_memory=True)
-        s_in, s_cmp, s_out = st["s_in"], st["s_cmp"], st["s_out"]
+            st["xh"] = torch.empty((NS,) + x.shape[1:], dtype=tdt, pin_memory=True)
+        s_in, s_out = st["s_in"], st["s_out"]
         cur = torch.cuda.current_stream(dev)
-        for s_ in (s_in, s_cmp, s_out):
+        for s_ in (s_in, s_out, *st["s_cmp"]):
             s_.wait_stream(cur)
-        host_ev = [None, None]
-        used = [False, False]
+        host_ev = [None] * NS
+        used = [False] * NS
         for i, (b, op) in enumerate(ops_):
-            k = i & 1
+            k = i % NS
+            s_cmp = st["s_cmp"][k & 1]
             xb = x[b]
             if not _any_nonzero(xb):  # operators/hessian.py:47-48
                 out[b] = 0
@@ -539,7 +545,8 @@ class BandPool:
                 st["ev_free_o"][k].record(s_out)
             used[k] = True
         s_out.synchronize()
-        cur.wait_stream(s_cmp)
+        for s_ in st["s_cmp"]:
+            cur.wait_stream(s_)
         return out
 
     def hess_cg(self, rhs, x0=None, tol=1e-5, maxit=500, minit=1, verbosity=0):

@@ -62,8 +62,8 @@ def test_band_pool_roles(gpu):
 def test_band_pool_pipelined_matches_band_by_band(gpu, monkeypatch):
     """hess_dot overlaps the copies of neighbouring bands with the kernels: same numbers as band by band,
     for pageable and page-locked (second sighting) input cubes, a zero band and a band owned by another rank."""
-    nband, nx, ny = 4, 384, 352  # 1.08 MB per band in fp64: above the page-locking threshold
-    probs = {b: small_problem(nrow=600, nchan=2, nx=nx, ny=ny, seed=20 + b) for b in (0, 1, 3)}  # band 2: not ours
+    nband, nx, ny = 6, 384, 352  # 1.08 MB per band in fp64: above the page-locking threshold
+    probs = {b: small_problem(nrow=600, nchan=2, nx=nx, ny=ny, seed=20 + b) for b in (0, 1, 3, 4, 5)}  # band 2: not ours
     bands = {}
     for b, p in probs.items():
         wsum = float(p["wgt"][p["mask"] != 0].sum())
@@ -79,7 +79,7 @@ def test_band_pool_pipelined_matches_band_by_band(gpu, monkeypatch):
     for o in outs:
         assert o.shape == x.shape and o.dtype == x.dtype
         assert not o[1].any() and not o[2].any()
-        for b in (0, 3):
+        for b in (0, 3, 4, 5):  # bands 4 and 5 run concurrently on the two compute streams
             # sigma = 1.25 / W = 16 at this size: two applies of the SAME path already differ by ~5e-10 (the order of
             # the grid atomics, amplified by 1 / psihat at the image edge); the bound is epsilon
             assert rel_l2(o[b], ref[b]) <= 1e-8
