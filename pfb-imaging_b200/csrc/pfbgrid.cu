@@ -226,7 +226,7 @@ extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
   int rc;
   if ((rc = dev_alloc(pl, pl->corr, (size_t)g.nx * g.ny * rb))) return bail(rc);
   if ((rc = dev_alloc(pl, pl->grid, (size_t)g.nplanes * g.nu * g.nv * 2 * rb))) return bail(rc);
-  if ((rc = dev_alloc(pl, pl->flag, 64))) return bail(rc);
+  if ((rc = dev_alloc(pl, pl->flag, 128))) return bail(rc);
 
   // correction image
   {
@@ -640,10 +640,28 @@ static int fft_exec(pfbg_plan* pl, cudaStream_t s, int dir) {
   return PFBG_OK;
 }
 
+// slice length of the run kernels' work queue: RUN_SLICE when every resident warp gets at least four of them,
+// shorter (a multiple of RUN_SLICE_TAIL) for small bindings so that all warps have work
+static int run_slice(const pfbg_plan* pl, int64_t nact, int warps_per_cta, int ctas_per_sm) {
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
+  const int64_t per_warp = nact / ((int64_t)sm * ctas_per_sm * warps_per_cta * 4);
+  int64_t sl = per_warp / RUN_SLICE_TAIL * RUN_SLICE_TAIL;
+  return (int)(sl < RUN_SLICE_TAIL ? RUN_SLICE_TAIL : (sl > RUN_SLICE ? RUN_SLICE : sl));
+}
+
+// resident CTAs per SM of the run kernels (PFBG_GRID_CTAS / PFBG_DEG_CTAS override the defaults: fewer CTAs leave
+// room for the kernels of another band running on a second stream)
+static int run_ctas(const char* env, int dflt) {
+  const char* e = getenv(env);
+  const int v = e ? atoi(e) : 0;
+  return v >= 1 && v <= dflt ? v : dflt;
+}
+
 static int run_blocks(const pfbg_plan* pl, int64_t nact, int warps_per_cta, int ctas_per_sm) {
   int sm = 148;
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
-  int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  int64_t nslice = (nact + RUN_SLICE_TAIL - 1) / RUN_SLICE_TAIL;
   int64_t want = (nslice + warps_per_cta - 1) / warps_per_cta;
   int64_t cap = (int64_t)sm * ctas_per_sm;  // a multiple of the SM count: one full wave of resident CTAs
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
@@ -652,7 +670,7 @@ static int run_blocks(const pfbg_plan* pl, int64_t nact, int warps_per_cta, int 
 static int wide_blocks(const pfbg_plan* pl, int64_t nact, int team) {
   int sm = 148;
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
-  int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
+  int64_t nslice = (nact + WIDE_SLICE - 1) / WIDE_SLICE;
   int64_t want = (nslice * team + WIDE_WARPS - 1) / WIDE_WARPS;
   int64_t cap = (int64_t)sm * 2;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
@@ -847,20 +865,25 @@ static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs
                       int vis_sorted, int apply_phase) {
   using C = typename cplx_of<T>::type;
   if (pl->nactive > 0 && pl->use_runs && pl->gp.W > 8) {
+    unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 16);  // slice counter of this launch
+    CK(cudaMemsetAsync(queue, 0, 8, s));
     if (pl->gp.W <= 12)
       k_grid_runs_wide<T, 3, 6, 4><<<wide_blocks(pl, pl->nactive, 4), WIDE_WARPS * 32, 0, s>>>(
           pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
-          vis_sorted, apply_phase);
+          vis_sorted, apply_phase, queue);
     else
       k_grid_runs_wide<T, 2, 8, 8><<<wide_blocks(pl, pl->nactive, 8), WIDE_WARPS * 32, 0, s>>>(
           pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
-          vis_sorted, apply_phase);
+          vis_sorted, apply_phase, queue);
     LAUNCHED();
     CK(cudaGetLastError());
   } else if (pl->nactive > 0 && pl->use_runs) {
-    k_grid_runs<T><<<run_blocks(pl, pl->nactive, RUN_WARPS, 3), RUN_WARPS * 32, 0, s>>>(
+    unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 16);  // slice counter of this launch
+    CK(cudaMemsetAsync(queue, 0, 8, s));
+    const int ctas = run_ctas("PFBG_GRID_CTAS", 3);
+    k_grid_runs<T><<<run_blocks(pl, pl->nactive, RUN_WARPS, ctas), RUN_WARPS * 32, 0, s>>>(
         pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
-        vis_sorted, apply_phase);
+        vis_sorted, apply_phase, queue, run_slice(pl, pl->nactive, RUN_WARPS, ctas));
     LAUNCHED();
     CK(cudaGetLastError());
   } else if (pl->nactive > 0) {
@@ -881,6 +904,8 @@ static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_
     // the R warps of a team add their row-partials atomically: start from zero
     if (out_sorted) CK(cudaMemsetAsync(out_sorted, 0, (size_t)pl->nactive * sizeof(C), s));
     else if (!pl->has_mask || (vis_zeroed == 0)) CK(cudaMemsetAsync(vis_out, 0, (size_t)pl->nvis * sizeof(C), s));
+    unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 32);  // one slice counter per row group (<= 8)
+    CK(cudaMemsetAsync(queue, 0, 64, s));
     const size_t psm = (size_t)WIDE_WARPS * 16 * 32 * sizeof(C);  // per-sample lane partials (see k_degrid_runs_wide)
     // (per device and cheap: set on every launch rather than caching it per process)
     if (pl->gp.W <= 12) CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 3, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
@@ -888,17 +913,20 @@ static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_
     if (pl->gp.W <= 12)
       k_degrid_runs_wide<T, 3, 6, 4><<<wide_blocks(pl, pl->nactive, 4), WIDE_WARPS * 32, psm, s>>>(
           pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
-          (C*)out_sorted, apply_phase);
+          (C*)out_sorted, apply_phase, queue);
     else
       k_degrid_runs_wide<T, 2, 8, 8><<<wide_blocks(pl, pl->nactive, 8), WIDE_WARPS * 32, psm, s>>>(
           pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
-          (C*)out_sorted, apply_phase);
+          (C*)out_sorted, apply_phase, queue);
     LAUNCHED();
     CK(cudaGetLastError());
   } else if (pl->nactive > 0 && pl->use_runs) {
-    k_degrid_runs<T><<<run_blocks(pl, pl->nactive, DEG_WARPS, 5), DEG_WARPS * 32, 0, s>>>(
+    unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 24);
+    CK(cudaMemsetAsync(queue, 0, 8, s));
+    const int ctas = run_ctas("PFBG_DEG_CTAS", 5);
+    k_degrid_runs<T><<<run_blocks(pl, pl->nactive, DEG_WARPS, ctas), DEG_WARPS * 32, 0, s>>>(
         pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
-        (C*)out_sorted, apply_phase);
+        (C*)out_sorted, apply_phase, queue, run_slice(pl, pl->nactive, DEG_WARPS, ctas));
     LAUNCHED();
     CK(cudaGetLastError());
   } else if (pl->nactive > 0) {

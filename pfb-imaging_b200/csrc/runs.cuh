@@ -94,7 +94,20 @@ __device__ __forceinline__ double es_scale(double beta) { return beta; }
 
 #define RUN_WARPS 8      /* warps per CTA, gridding */
 #define DEG_WARPS 4      /* warps per CTA, degridding (48 KB static shared memory) */
-#define RUN_SLICE 256
+#ifndef RUN_SLICE
+#define RUN_SLICE 512
+#endif
+#ifndef RUN_SLICE_TAIL
+#define RUN_SLICE_TAIL 64
+#endif
+#ifndef GRID_UNROLL
+#define GRID_UNROLL 2
+#endif
+constexpr int kGridUnroll = GRID_UNROLL;
+#ifndef DEG_UNROLL
+#define DEG_UNROLL 2
+#endif
+constexpr int kDegUnroll = DEG_UNROLL;
 
 template <typename T> struct RunCfg;
 template <> struct RunCfg<float> { static constexpr int NB = 32; };
@@ -251,6 +264,21 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t x, int src) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+// the next slice [kbeg, kend) of the sorted samples for this warp (lane 0 draws it from the launch's counter).
+// The first 7/8 of the samples go out in slices of `big` (RUN_SLICE when there is enough work for every warp, see
+// run_slice() on the host), the rest in slices of RUN_SLICE_TAIL, so the warps finish within a short slice of each
+// other while most runs are not cut by a slice boundary.
+__device__ __forceinline__ bool next_slice(unsigned long long* queue, int lane, int64_t nact, int big, int64_t& kbeg,
+                                           int64_t& kend) {
+  unsigned long long t = 0;
+  if (lane == 0) t = atomicAdd(queue, 1ull);
+  const int64_t sl = (int64_t)shfl_u64(t, 0);
+  const int64_t nbig = (nact - (nact >> 3)) / big;
+  kbeg = sl < nbig ? sl * big : nbig * big + (sl - nbig) * RUN_SLICE_TAIL;
+  kend = min(nact, kbeg + (sl < nbig ? big : RUN_SLICE_TAIL));
+  return kbeg < nact;
+}
+
 // run boundaries of a staged batch as a bit mask: bit v set <=> sample v starts a new run
 __device__ __forceinline__ uint32_t run_starts(uint64_t org, uint64_t cur, int lane, int nb) {
   uint64_t prev = shfl_u64(org, lane > 0 ? lane - 1 : 0);
@@ -266,7 +294,7 @@ __global__ void __launch_bounds__(RUN_WARPS * 32, (sizeof(T) == 4 ? 3 : 1))  // 
 k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
             const typename cplx_of<T>::type* __restrict__ vis, int64_t vis_rs, int64_t vis_cs,
             const T* __restrict__ wgt, typename cplx_of<T>::type* __restrict__ grid, int vis_sorted,
-            int apply_phase) {
+            int apply_phase, unsigned long long* __restrict__ queue, int slice) {
   using C = typename cplx_of<T>::type;
   constexpr int NB = RunCfg<T>::NB;
   __shared__ __align__(16) T taps[RUN_WARPS][NB][24];
@@ -279,14 +307,15 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 #pragma unroll
   for (int i = 0; i < 8; ++i) { acc[i][0].x = acc[i][0].y = 0; acc[i][1].x = acc[i][1].y = 0; }
   uint64_t cur = ~0ull;
-  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
-  const int64_t nwarps = (int64_t)gridDim.x * RUN_WARPS;
-  for (int64_t sl = (int64_t)blockIdx.x * RUN_WARPS + warp; sl < nslice; sl += nwarps) {
-    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+  // slices are handed out in sort order from a device counter: their cost varies with the run length (the dense
+  // core against the outer uv plane), and a fixed stride left the last warps running alone for ~5 % of the kernel
+  for (;;) {
+    int64_t kbeg, kend;
+    if (!next_slice(queue, lane, nact, slice, kbeg, kend)) break;
     // records are fetched one batch ahead (their latency hides behind the FMA stage)
     VisRec<T> rnext;
-    if (sl * RUN_SLICE + lane < kend && lane < NB) rnext = recs[sl * RUN_SLICE + lane];
-    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+    if (kbeg + lane < kend && lane < NB) rnext = recs[kbeg + lane];
+    for (int64_t k0 = kbeg; k0 < kend; k0 += NB) {
       const int nb = (int)min((int64_t)NB, kend - k0);
       const VisRec<T> r = rnext;
       uint64_t org = ~0ull;
@@ -329,7 +358,7 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
         }
         const uint32_t rest = v < 31 ? (starts & (0xffffffffu << (v + 1))) : 0u;
         const int vend = rest ? min(__ffs(rest) - 1, nb) : nb;
-#pragma unroll 2
+#pragma unroll kGridUnroll
         for (; v < vend; ++v) {
           const T* tp = taps[warp][v];
           const T tv = tp[8 + j];
@@ -358,7 +387,8 @@ __global__ void __launch_bounds__(DEG_WARPS * 32)
 k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
               const typename cplx_of<T>::type* __restrict__ grid, const T* __restrict__ wgt,
               typename cplx_of<T>::type* __restrict__ vis_out,
-              typename cplx_of<T>::type* __restrict__ out_sorted, int apply_phase) {
+              typename cplx_of<T>::type* __restrict__ out_sorted, int apply_phase,
+              unsigned long long* __restrict__ queue, int slice) {
   using C = typename cplx_of<T>::type;
   constexpr int NB = RunCfg<T>::NB;
   __shared__ __align__(16) T taps[DEG_WARPS][NB][24];
@@ -371,13 +401,12 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 #pragma unroll
   for (int i = 0; i < 8; ++i) { gv[i][0].x = gv[i][0].y = 0; gv[i][1].x = gv[i][1].y = 0; }
   uint64_t cur = ~0ull;
-  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
-  const int64_t nwarps = (int64_t)gridDim.x * DEG_WARPS;
-  for (int64_t sl = (int64_t)blockIdx.x * DEG_WARPS + warp; sl < nslice; sl += nwarps) {
-    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
+  for (;;) {  // slices from the device counter, see k_grid_runs
+    int64_t kbeg, kend;
+    if (!next_slice(queue, lane, nact, slice, kbeg, kend)) break;
     VisRec<T> rnext;
-    if (sl * RUN_SLICE + lane < kend && lane < NB) rnext = recs[sl * RUN_SLICE + lane];
-    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+    if (kbeg + lane < kend && lane < NB) rnext = recs[kbeg + lane];
+    for (int64_t k0 = kbeg; k0 < kend; k0 += NB) {
       const int nb = (int)min((int64_t)NB, kend - k0);
       const VisRec<T> r = rnext;
       uint64_t org = ~0ull;
@@ -407,7 +436,7 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
         }
         const uint32_t rest = v < 31 ? (starts & (0xffffffffu << (v + 1))) : 0u;
         const int vend = rest ? min(__ffs(rest) - 1, nb) : nb;
-#pragma unroll 2
+#pragma unroll kDegUnroll
         for (; v < vend; ++v) {
           const T* tp = taps[warp][v];
           C a0 = cmul_s(gv[0][0], tp[0]), a1 = cmul_s(gv[0][1], tp[0]);
@@ -455,6 +484,7 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 // FMA stage for its rows.  Named barriers (one id per team) separate the stages.
 // ===========================================================================
 #define WIDE_WARPS 8
+#define WIDE_SLICE 256  /* samples per (statically strided) slice of a team */
 #define WIDE_NB 16   // samples staged per batch
 #define WIDE_NT 48   // tap slots per sample: 16 u, 16 v, 16 w (the first W of each are live)
 
@@ -520,12 +550,13 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32)
 k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
                  const typename cplx_of<T>::type* __restrict__ vis, int64_t vis_rs, int64_t vis_cs,
                  const T* __restrict__ wgt, typename cplx_of<T>::type* __restrict__ grid, int vis_sorted,
-                 int apply_phase) {
+                 int apply_phase, unsigned long long* __restrict__ queue) {
   using C = typename cplx_of<T>::type;
   constexpr int NB = WIDE_NB, NTEAM = WIDE_WARPS / R;
   __shared__ T taps[NTEAM][NB][WIDE_NT];
   __shared__ __align__(16) T x0s[NTEAM][NB][4];
   __shared__ C amp[NTEAM][NB];
+  __shared__ unsigned long long team_slice[NTEAM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / R, r = warp - team * R;
   const int ttid = r * 32 + lane;
@@ -538,11 +569,16 @@ k_grid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 #pragma unroll
     for (int qq = 0; qq < NQ; ++qq) { accr[ii][qq] = 0; acci[ii][qq] = 0; }
   uint64_t cur = ~0ull;
-  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
-  const int64_t nteams = (int64_t)gridDim.x * NTEAM;
-  for (int64_t sl = (int64_t)blockIdx.x * NTEAM + team; sl < nslice; sl += nteams) {
-    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
-    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+  const int64_t nslice = (nact + WIDE_SLICE - 1) / WIDE_SLICE;
+  for (;;) {
+    // the team's next slice, drawn by its first thread from the launch's counter (see k_grid_runs)
+    if (ttid == 0) team_slice[team] = atomicAdd(queue, 1ull);
+    team_sync(team, 32 * R);
+    const int64_t sl = (int64_t)team_slice[team];
+    team_sync(team, 32 * R);  // everybody has read it before the next draw overwrites it
+    if (sl >= nslice) break;
+    const int64_t kend = min(nact, (sl + 1) * WIDE_SLICE);
+    for (int64_t k0 = sl * WIDE_SLICE; k0 < kend; k0 += NB) {
       const int nb = (int)min((int64_t)NB, kend - k0);
       uint64_t org = ~0ull;
       if (lane < nb) {  // every warp reads the records (it needs the run origins); warp 0 stages the rest
@@ -632,7 +668,8 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32)
 k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
                    const typename cplx_of<T>::type* __restrict__ grid, const T* __restrict__ wgt,
                    typename cplx_of<T>::type* __restrict__ vis_out,
-                   typename cplx_of<T>::type* __restrict__ out_sorted, int apply_phase) {
+                   typename cplx_of<T>::type* __restrict__ out_sorted, int apply_phase,
+                   unsigned long long* __restrict__ queue) {
   using C = typename cplx_of<T>::type;
   constexpr int NB = WideCfg<T, RPW, NQ>::NB, NT = WideCfg<T, RPW, NQ>::NT;
   __shared__ T taps[WIDE_WARPS][NB][NT];
@@ -655,11 +692,16 @@ k_degrid_runs_wide(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 #pragma unroll
     for (int qq = 0; qq < NQ; ++qq) { gr[ii][qq] = 0; gi[ii][qq] = 0; }
   uint64_t cur = ~0ull;
-  const int64_t nslice = (nact + RUN_SLICE - 1) / RUN_SLICE;
-  const int64_t nteams = ((int64_t)gridDim.x * WIDE_WARPS) / R;
-  for (int64_t sl = gwarp / R; sl < nslice; sl += nteams) {
-    const int64_t kend = min(nact, (sl + 1) * RUN_SLICE);
-    for (int64_t k0 = sl * RUN_SLICE; k0 < kend; k0 += NB) {
+  const int64_t nslice = (nact + WIDE_SLICE - 1) / WIDE_SLICE;
+  // the warps are independent: every (slice, row group) pair is drawn exactly once from the row group's own counter
+  unsigned long long* myq = queue + (gwarp % R);
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(myq, 1ull);
+    const int64_t sl = (int64_t)shfl_u64(t, 0);
+    if (sl >= nslice) break;
+    const int64_t kend = min(nact, (sl + 1) * WIDE_SLICE);
+    for (int64_t k0 = sl * WIDE_SLICE; k0 < kend; k0 += NB) {
       const int nb = (int)min((int64_t)NB, kend - k0);
       VisRec<T> r;
       if (lane < nb) {
