@@ -881,9 +881,10 @@ static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs
     unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 16);  // slice counter of this launch
     CK(cudaMemsetAsync(queue, 0, 8, s));
     const int ctas = run_ctas("PFBG_GRID_CTAS", 3);
+    const int slice = run_slice(pl, pl->nactive, RUN_WARPS, ctas);
     k_grid_runs<T><<<run_blocks(pl, pl->nactive, RUN_WARPS, ctas), RUN_WARPS * 32, 0, s>>>(
         pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
-        vis_sorted, apply_phase, queue, run_slice(pl, pl->nactive, RUN_WARPS, ctas));
+        vis_sorted, apply_phase, queue, slice);
     LAUNCHED();
     CK(cudaGetLastError());
   } else if (pl->nactive > 0) {
@@ -924,9 +925,10 @@ static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_
     unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 24);
     CK(cudaMemsetAsync(queue, 0, 8, s));
     const int ctas = run_ctas("PFBG_DEG_CTAS", 5);
+    const int slice = run_slice(pl, pl->nactive, DEG_WARPS, ctas);
     k_degrid_runs<T><<<run_blocks(pl, pl->nactive, DEG_WARPS, ctas), DEG_WARPS * 32, 0, s>>>(
         pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
-        (C*)out_sorted, apply_phase, queue, run_slice(pl, pl->nactive, DEG_WARPS, ctas));
+        (C*)out_sorted, apply_phase, queue, slice);
     LAUNCHED();
     CK(cudaGetLastError());
   } else if (pl->nactive > 0) {
