@@ -375,7 +375,7 @@ def run_ours(args, cfg):
             "achieved": kb / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": kb / (k_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "kernel_ms": k_ms, "algorithmic_bytes_per_launch": kb,
-            "note": "run kernels are issue / FMA-pipe bound (ncu: DRAM throughput ~7 %, issue slots ~56 %, FMA pipe ~50 %); the plane stack stays L2-resident; algorithmic bytes use the plan's own plane count (mirror planes are not counted)",
+            "note": "run kernels are issue / FMA-pipe bound (ncu, profiles/r1_ncu_v9_summary.md: DRAM throughput ~8 %, issue slots ~58 %, FMA pipe ~52 %, math_pipe_throttle among the top stalls); the plane stack stays L2-resident; algorithmic bytes use the plan's own plane count (mirror planes are not counted); kernel_ms is the spreading phase of one band run alone (library events), the step runs two bands at a time",
             "step_algorithmic_bytes_rank0": B, "step_achieved_rank0": B / (my_ms * 1e-3) / 1e9,
             "step_frac": B / (my_ms * 1e-3) / 1e9 / peak, "step_frac_of_nominal_8TBs": B / (my_ms * 1e-3) / 1e9 / 8000.0,
             "step_frac_unmirrored_planes": B_std / (my_ms * 1e-3) / 1e9 / peak,

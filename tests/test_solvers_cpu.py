@@ -103,3 +103,37 @@ def test_bench_host_logic():
     info = dict(nplanes=15, nu=6144, nv=6144, nx=4096, ny=4096)
     B = bench.algorithmic_bytes(info, 24998400, 16, 4)
     assert abs(B - (24998400 * (20 + 2 + 3) + 2 * 15 * (6 * 6144 * 6144 * 8 + 3 * 4096 * 4096 * 4))) < 1.0
+
+
+def test_any_nonzero_matches_numpy_any():
+    """The pool's zero-image short circuit (operators/hessian.py:47-48) scans bit patterns in chunks."""
+    from pfb_imaging_b200.operators import _any_nonzero
+
+    rng = np.random.default_rng(0)
+    for dt in (np.float32, np.float64):
+        z = np.zeros((37, 53), dt)
+        assert not _any_nonzero(z) and not _any_nonzero(z, chunk=64)
+        for pos in ((0, 0), (36, 52), (17, 3)):
+            a = z.copy()
+            a[pos] = rng.standard_normal() * 1e-30  # tiny but not zero
+            assert _any_nonzero(a, chunk=100) == bool(a.any())
+        assert _any_nonzero(np.full((3, 5), np.nan, dt))
+    assert not _any_nonzero(np.zeros((0, 4)))
+
+
+def test_band_pool_band_by_band_path_on_plain_operators():
+    """Operators that are not device-pinned BandHessians go band by band; bands of other ranks stay zero."""
+    from pfb_imaging_b200 import operators as ops
+
+    class Scale:
+        def __init__(self, f):
+            self.f = f
+
+        def dot(self, x):
+            return self.f * x
+
+    pool = ops.BandPool({0: Scale(2.0), 2: Scale(-1.0)}, nband=3)
+    x = np.arange(3 * 4 * 5, dtype=np.float64).reshape(3, 4, 5)
+    assert not pool._pipelined_ok(x)
+    y = pool.hess_dot(x)
+    assert np.array_equal(y[0], 2.0 * x[0]) and not y[1].any() and np.array_equal(y[2], -x[2])
