@@ -23,6 +23,8 @@
  *   - _compute_counts / counts_to_weights
  *       (utils/weighting.py:81-140, 143-208)                -> pfbg_counts /
  *                                                              pfbg_counts_to_weights
+ *   - the l2 re-weighting block of image_data_products
+ *       (operators/gridder.py:509-532)                      -> pfbg_l2_reweight
  */
 #ifndef PFBGRID_H
 #define PFBGRID_H
@@ -186,6 +188,20 @@ int pfbg_counts_to_weights(int32_t precision, int32_t device, void* counts, cons
                            int32_t nchan, int32_t ncorr, int32_t nx, int32_t ny, double cell_x,
                            double cell_y, double robust, double usign, double vsign, uint32_t flags,
                            void* stream);
+
+/*
+ * l2 (Student-t) re-weighting of the natural weights from residual visibilities — the block
+ * `if l2_reweight_dof:` of image_data_products (operators/gridder.py:509-532):
+ *     ressq = |resvis|^2 * wgtp;  ovar[c] = sum_{mask>0} ressq[c] / sum(mask);
+ *     wgt[c] *= (dof + 2) / (dof + ressq[c] / ovar[c])          (every sample, flagged ones included)
+ * resvis (ncorr,nrow,nchan) complex of `precision`, wgtp (ncorr,nrow,nchan) real or NULL (= 1),
+ * mask (nrow,nchan) u8 or NULL, wgt (ncorr,nrow,nchan) real, updated in place.  ovar_out (ncorr doubles,
+ * host) receives the per-correlation variance; when any of them is zero nothing is written to wgt and
+ * *applied = 0 (the reference then sets the weights to None).
+ */
+int pfbg_l2_reweight(int32_t precision, int32_t device, const void* resvis, const void* wgtp,
+                     const uint8_t* mask, void* wgt, int64_t nvis, int32_t ncorr, double dof,
+                     double* ovar_out, int32_t* applied, uint32_t flags, void* stream);
 
 /*
  * PSF-convolution Hessian on the device (operators/hessian.py:103-143 hessian_psf_slice,

@@ -88,3 +88,24 @@ def box_sum_counts(counts, npix_super):
     for c in range(counts.shape[0]):
         out[c] = uniform_filter(counts[c], size=size, mode="constant", cval=0.0) * (size * size)
     return out
+
+
+def l2_reweight(residual_vis, wgt, mask, dof, wgtp=None):
+    """Student-t re-weighting of the natural weights from residual visibilities — restates the
+    ``if l2_reweight_dof:`` block of image_data_products
+    (/root/reference/src/pfb_imaging/operators/gridder.py:509-532); pinned by tests/golden/l2_reweight.npz
+    (tests/golden/make_golden_l2.py executes that block itself).
+
+    residual_vis (ncorr,nrow,nchan) complex, wgt (ncorr,nrow,nchan) real (a scaled COPY is returned),
+    mask (nrow,nchan); returns None when the variance is zero (:531-532).  For ncorr > 1 the reference's
+    ``if ovar:`` is ambiguous (numpy raises); this restatement continues when every ovar is non-zero."""
+    p = 1.0 if wgtp is None else np.asarray(wgtp)
+    ressq = (residual_vis * p * residual_vis.conj()).real  # :516
+    sel = np.asarray(mask) > 0
+    ssq = ressq[:, sel].sum(axis=-1)  # :519
+    ovar = ssq / np.asarray(mask).sum()  # :520
+    if not np.all(ovar):  # :521 (NaN counts as true, as in the reference)
+        return None
+    out = np.array(wgt, copy=True)
+    out *= (dof + 2) / (dof + ressq / ovar[:, None, None])  # :527-530
+    return out

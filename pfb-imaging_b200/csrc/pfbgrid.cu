@@ -1384,6 +1384,54 @@ extern "C" int pfbg_counts_to_weights(int32_t precision, int32_t device, void* c
   return PFBG_OK;
 }
 
+extern "C" int pfbg_l2_reweight(int32_t precision, int32_t device, const void* resvis, const void* wgtp,
+                                const uint8_t* mask, void* wgt, int64_t nvis, int32_t ncorr, double dof,
+                                double* ovar_out, int32_t* applied, uint32_t flags, void* stream) {
+  if (!resvis || !wgt || !ovar_out || !applied) return fail(PFBG_ERR_ARG, "null argument");
+  if (nvis < 0 || ncorr <= 0 || ncorr > 16) return fail(PFBG_ERR_ARG, "bad sizes");
+  if (precision != PFBG_F32 && precision != PFBG_F64) return fail(PFBG_ERR_ARG, "bad precision");
+  CK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = precision == PFBG_F32 ? 4 : 8;
+  const size_t wbytes = (size_t)ncorr * nvis * rb;
+  *applied = 0;
+  TmpBufs t;
+  void *drv, *dp = nullptr, *dmask = nullptr, *dwgt, *dsums;
+  CKRC(t.get(&drv, resvis, 2 * wbytes, dev, true, s));
+  if (wgtp) CKRC(t.get(&dp, wgtp, wbytes, dev, true, s));
+  if (mask) CKRC(t.get(&dmask, mask, (size_t)nvis, dev, true, s));
+  CKRC(t.get(&dwgt, wgt, wbytes, dev, true, s));
+  CKRC(t.get(&dsums, nullptr, 17 * 8, false, false, s));
+  CK(cudaMemsetAsync(dsums, 0, 17 * 8, s));
+  dim3 rgrid(592, ncorr);
+  if (nvis > 0) {
+    if (precision == PFBG_F32) k_l2_ssq<float><<<rgrid, 256, 0, s>>>((const float*)drv, (const float*)dp, (const uint8_t*)dmask, nvis, (double*)dsums);
+    else k_l2_ssq<double><<<rgrid, 256, 0, s>>>((const double*)drv, (const double*)dp, (const uint8_t*)dmask, nvis, (double*)dsums);
+    LAUNCHED();
+  }
+  double sums[17];
+  CK(cudaMemcpyAsync(sums, dsums, sizeof sums, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  bool all_nonzero = true;
+  for (int c = 0; c < ncorr; ++c) {
+    ovar_out[c] = sums[c] / sums[ncorr];  // 0/0 -> NaN like numpy; NaN is truthy there too
+    if (ovar_out[c] == 0.0) all_nonzero = false;
+  }
+  if (!all_nonzero) return PFBG_OK;
+  CK(cudaMemcpyAsync(dsums, ovar_out, ncorr * 8, cudaMemcpyHostToDevice, s));
+  if (nvis > 0) {
+    if (precision == PFBG_F32) k_l2_apply<float><<<rgrid, 256, 0, s>>>((const float*)drv, (const float*)dp, (float*)dwgt, nvis, (const double*)dsums, dof, dof + 2.0);
+    else k_l2_apply<double><<<rgrid, 256, 0, s>>>((const double*)drv, (const double*)dp, (double*)dwgt, nvis, (const double*)dsums, dof, dof + 2.0);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (!dev) CK(cudaMemcpyAsync(wgt, dwgt, wbytes, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  *applied = 1;
+  return PFBG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // unit-test hook for the shared-memory FFT engine (fft.cuh)
 // ---------------------------------------------------------------------------

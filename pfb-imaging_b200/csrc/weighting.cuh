@@ -99,3 +99,50 @@ __global__ void k_apply_counts(WParams w, const double* __restrict__ uvw, const 
     if (cv > (T)0) wgt[(int64_t)c * nvis + k] /= cv;
   }
 }
+
+// ---------------------------------------------------------------------------
+// l2 (Student-t) re-weighting from residual visibilities
+// (/root/reference/src/pfb_imaging/operators/gridder.py:509-532):
+//   ressq = |r|^2 * wgtp ;  ovar[c] = sum_{mask>0} ressq[c] / sum(mask) ;  wgt *= (dof + 2) / (dof + ressq / ovar[c])
+// HBM-bound streaming passes: pass 1 reads r (2p) + wgtp (p) + mask (1) per sample, pass 2 reads r, wgtp, wgt and
+// writes wgt.  Vectorisation is left to the 32-lane coalescing (consecutive k -> consecutive addresses).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_l2_ssq(const T* __restrict__ rv, const T* __restrict__ wgtp, const uint8_t* __restrict__ mask,
+                         int64_t nvis, double* __restrict__ sums /* ncorr + 1: ssq[c], mask count */) {
+  int c = blockIdx.y;
+  const T* r = rv + (int64_t)c * nvis * 2;
+  const T* p = wgtp ? wgtp + (int64_t)c * nvis : nullptr;
+  double s = 0;
+  unsigned long long cnt = 0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nvis; k += (int64_t)gridDim.x * blockDim.x) {
+    if (mask && !mask[k]) continue;
+    T re = r[2 * k], im = r[2 * k + 1];
+    T q = p ? (re * p[k]) * re + (im * p[k]) * im : re * re + im * im;
+    s += (double)q;
+    ++cnt;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[c], s);
+    if (c == 0) atomicAdd(&sums[gridDim.y], (double)cnt);
+  }
+}
+
+template <typename T>
+__global__ void k_l2_apply(const T* __restrict__ rv, const T* __restrict__ wgtp, T* __restrict__ wgt, int64_t nvis,
+                           const double* __restrict__ ovar, double dof, double numer) {
+  int c = blockIdx.y;
+  const T* r = rv + (int64_t)c * nvis * 2;
+  const T* p = wgtp ? wgtp + (int64_t)c * nvis : nullptr;
+  T* w = wgt + (int64_t)c * nvis;
+  const double ov = ovar[c];  // ovar, the ratio and the product are float64 in the reference also for float32 data
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nvis; k += (int64_t)gridDim.x * blockDim.x) {
+    T re = r[2 * k], im = r[2 * k + 1];
+    T q = p ? (re * p[k]) * re + (im * p[k]) * im : re * re + im * im;
+    w[k] = (T)((double)w[k] * (numer / (dof + (double)q / ov)));
+  }
+}

@@ -247,30 +247,85 @@ def compute_residual_arrays(uvw, wgt, mask, beam, dirty, freq, flip_u, flip_v, f
 
 def image_data_products_arrays(uvw, freq, vis, wgt, mask, nx, ny, nx_psf, ny_psf, cellx, celly, l0=0.0, m0=0.0,
                                epsilon=1e-7, do_wgridding=True, double_accum=True, do_dirty=True, do_psf=True,
-                               nthreads=1):
-    """Gridder-side products of ``image_data_products`` / ``grid_partition``
-    (operators/gridder.py:578-664, 838-923): WSUM, DIRTY, PSF, PSFHAT.
+                               nthreads=1, model=None, robustness=None, l2_reweight_dof=None, wgtp=None,
+                               do_residual=True, do_noise=False, min_padding=1.7, filter_counts_level=5.0,
+                               npix_super=0, rng=None):
+    """The arrays-level body of ``image_data_products`` (operators/gridder.py:477-757; the zarr / xarray
+    wrapper around it is out of scope): model transfer -> residual visibilities (:477-507), l2 re-weighting
+    (:509-532), imaging weights (:534-575), then WSUM, DIRTY, PSF, PSFHAT, RESIDUAL and NOISE (:583-734).
 
-    vis/wgt are corr-first ``(ncorr,nrow,nchan)``; images come back float64 like the
-    reference (``np.zeros(..., dtype=float)``, gridder.py:588,631)."""
-    from scipy.constants import c as lightspeed  # noqa: F401  (documentary: same constant as the reference)
+    vis/wgt are corr-first ``(ncorr,nrow,nchan)``, ``model`` is ``(ncorr,nx,ny)``; images come back float64
+    like the reference (``np.zeros(..., dtype=float)``, gridder.py:588,631).  ``wgtp`` stands for the prior
+    weights the reference reads from ``dsp`` (:510-514).  The caller's ``wgt`` is not modified; the weights
+    that were used come back as ``out["weight"]``.  ``rng`` seeds the noise realisation (the reference draws
+    it from ``parallel_standard_normal``, :705)."""
+    from . import weighting as _w
 
     flip_u, flip_v, flip_w, x0, y0 = wgridder_conventions(l0, m0)
     ncorr = wgt.shape[0]
+    nrow, nchan = uvw.shape[0], freq.size
     out = {}
-    out["wsum"] = wgt[:, np.asarray(mask).astype(bool)].sum(axis=-1)
     common = dict(pixsize_x=cellx, pixsize_y=celly, center_x=x0, center_y=y0, epsilon=epsilon, flip_u=flip_u,
                   flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=False,
                   sigma_min=1.1, sigma_max=3.0)
-    if do_dirty:
-        dirty = np.zeros((ncorr, nx, ny), dtype=float)
-        with plan_for(uvw, freq, npix_x=nx, npix_y=ny, precision="double", mask=mask, **common) as gp:
+    residual_vis = None
+    if model is None:
+        if l2_reweight_dof:
+            raise ValueError("Requested l2 reweight but no model passed in. Perhaps transfer model from somewhere?")
+    else:
+        # neither weights nor the mask are applied in this direction (:481-503); residual_vis = vis - R model
+        residual_vis = np.empty((ncorr, nrow, nchan), dtype=np.complex128)
+        with plan_for(uvw, freq, npix_x=nx, npix_y=ny, precision="double", mask=None, **common) as gp:
             for c in range(ncorr):
-                gp.grid(np.require(vis[c], dtype=np.complex128), wgt=np.require(wgt[c], dtype=np.float64),
-                        dirty=dirty[c])
-        out["dirty"] = dirty
+                gp.degrid(np.require(model[c], dtype=np.float64), vis=residual_vis[c])
+        np.subtract(vis, residual_vis, out=residual_vis)
+    if l2_reweight_dof or robustness is not None:
+        wgt = np.array(wgt, dtype=np.float64, copy=True)
+    if l2_reweight_dof:
+        if _w.l2_reweight(residual_vis, wgt, mask, l2_reweight_dof, wgtp=wgtp) is None:
+            # the reference sets wgt = None here (:531-532) and then fails on the next subscript
+            raise ValueError("residual visibilities are exactly zero: the l2 re-weighting is undefined")
+    if robustness is not None:
+        nx_pad = int(np.ceil(min_padding * nx))
+        nx_pad += nx_pad % 2
+        ny_pad = int(np.ceil(min_padding * ny))
+        ny_pad += ny_pad % 2
+        usign, vsign = (1.0 if flip_u else -1.0), (1.0 if flip_v else -1.0)
+        counts = _w._compute_counts(uvw, freq, mask, wgt, nx_pad, ny_pad, cellx, celly, uvw.dtype, ngrid=1,
+                                    usign=usign, vsign=vsign)
+        counts = _w.filter_extreme_counts(counts, level=filter_counts_level)
+        counts = _w.box_sum_counts(counts, npix_super)
+        wgt = _w.counts_to_weights(counts, uvw, freq, wgt, mask, nx_pad, ny_pad, cellx, celly, robustness,
+                                   usign=usign, vsign=vsign)
+    out["weight"] = wgt
+    out["wsum"] = wgt[:, np.asarray(mask).astype(bool)].sum(axis=-1)
+    want_res = do_residual and model is not None
+    if do_dirty or want_res or do_noise:
+        with plan_for(uvw, freq, npix_x=nx, npix_y=ny, precision="double", mask=mask, **common) as gp:
+            if do_dirty:
+                dirty = np.zeros((ncorr, nx, ny), dtype=float)
+                for c in range(ncorr):
+                    gp.grid(np.require(vis[c], dtype=np.complex128), wgt=np.require(wgt[c], dtype=np.float64),
+                            dirty=dirty[c])
+                out["dirty"] = dirty
+            if want_res:
+                residual = np.zeros((ncorr, nx, ny), dtype=float)
+                for c in range(ncorr):
+                    gp.grid(residual_vis[c], wgt=np.require(wgt[c], dtype=np.float64), dirty=residual[c])
+                out["model"] = model
+                out["residual"] = residual
+            if do_noise:
+                # noise with covariance W^-1 projected into image space (:700-734)
+                gen = np.random.default_rng(rng)
+                noise = np.zeros((ncorr, nx, ny), dtype=float)
+                for c in range(ncorr):
+                    nvis_ = gen.standard_normal((nrow, nchan)) + 1j * gen.standard_normal((nrow, nchan))
+                    wmask = wgt[c] > 0.0
+                    nvis_[wmask] /= np.sqrt(wgt[c, wmask])
+                    nvis_[~wmask] = 0j
+                    gp.grid(nvis_, wgt=np.require(wgt[c], dtype=np.float64), dirty=noise[c])
+                out["noise"] = noise
     if do_psf:
-        nrow, nchan = uvw.shape[0], freq.size
         psf = np.zeros((ncorr, nx_psf, ny_psf), dtype=float)
         with plan_for(uvw, freq, npix_x=nx_psf, npix_y=ny_psf, precision="double", mask=mask, **common) as gp:
             for c in range(ncorr):

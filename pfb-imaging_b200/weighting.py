@@ -1,7 +1,8 @@
 """Imaging weights on the B200: drop-ins for the numba functions of
 ``/root/reference/src/pfb_imaging/utils/weighting.py`` —
 ``_compute_counts`` (:81-140), ``counts_to_weights`` (:143-208),
-``filter_extreme_counts`` (:212-226), ``box_sum_counts`` (:229-254) — with the
+``filter_extreme_counts`` (:212-226), ``box_sum_counts`` (:229-254), and the l2 re-weighting block of
+``image_data_products`` (``operators/gridder.py:509-532`` -> ``l2_reweight``) — with the
 same positional signatures and in-place behaviour (``counts_to_weights`` mutates
 both ``weight`` and ``counts``).  The histogram / gather run in
 ``libpfbgrid.so`` (``csrc/weighting.cuh``); the median filter and the box sum are
@@ -94,6 +95,47 @@ def counts_to_weights(counts, uvw, freq, weight, mask, nx, ny, cell_size_x, cell
         weight[...] = w
     if c is not counts:
         counts[...] = c
+    return weight
+
+
+def l2_reweight(residual_vis, weight, mask, l2_reweight_dof, wgtp=None):
+    """Student-t re-weighting from residual visibilities: the ``if l2_reweight_dof:`` block of
+    ``image_data_products`` (operators/gridder.py:509-532).  ``weight`` (ncorr,nrow,nchan) is scaled in
+    place by ``(dof + 2) / (dof + |r|^2 wgtp / ovar)`` and returned; ``None`` comes back when the residual
+    variance is exactly zero (:531-532), the weights are then left untouched.
+
+    The reference's ``if ovar:`` only has a truth value for ncorr == 1; for more correlations this
+    routine continues when every per-correlation variance is non-zero."""
+    if not isinstance(weight, np.ndarray) or weight.ndim != 3:
+        raise ValueError("weight must be an ndarray of shape (ncorr, nrow, nchan)")
+    ncorr, nrow, nchan = weight.shape
+    dt = weight.dtype
+    prec = _prec(dt)
+    cdt = np.complex64 if dt == np.float32 else np.complex128
+    rv = np.asarray(residual_vis)
+    if rv.shape != weight.shape or rv.dtype != cdt:
+        raise ValueError(f"residual_vis must be {np.dtype(cdt)} of shape {weight.shape}")
+    rv = np.ascontiguousarray(rv)
+    if wgtp is not None and not np.isscalar(wgtp):
+        wgtp = np.ascontiguousarray(np.broadcast_to(np.asarray(wgtp, dtype=dt), weight.shape))
+    elif wgtp is not None:
+        wgtp = None if float(wgtp) == 1.0 else np.full(weight.shape, wgtp, dtype=dt)
+    if mask is not None:
+        mask = np.asarray(mask)
+        if mask.shape != (nrow, nchan):
+            raise ValueError("mask shape does not match the weights")
+        mask = np.ascontiguousarray(mask if mask.dtype == np.uint8 else mask != 0, dtype=np.uint8)
+    w = weight if weight.flags.c_contiguous else np.ascontiguousarray(weight)
+    ovar = np.zeros(ncorr, dtype=np.float64)
+    applied = C.c_int32(0)
+    lib = _lib.load()
+    _lib.check(lib.pfbg_l2_reweight(prec, current_device(), _p(rv), _p(wgtp), _p(mask), _p(w), nrow * nchan, ncorr,
+                                    float(l2_reweight_dof), _p(ovar), C.cast(C.byref(applied), C.c_void_p),
+                                    _lib.HOST_PTRS, None))
+    if not applied.value:
+        return None
+    if w is not weight:
+        weight[...] = w
     return weight
 
 

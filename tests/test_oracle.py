@@ -134,3 +134,20 @@ def test_uv2xy_identity():
         uvw = np.stack([u, np.full(nx, 1.0), np.zeros(nx)], axis=1)
         ui, vi = ow.uv_cells(uvw, freq, None, nx, 8, cell, 0.01, usign=1.0, vsign=1.0)
         assert np.array_equal(ui[:, 0], i)
+
+
+def test_l2_reweight_restatement_matches_reference_block():
+    """oracle.weighting.l2_reweight against the outputs of the reference's own `if l2_reweight_dof:` block
+    (operators/gridder.py:509-532, executed by tests/golden/make_golden_l2.py): bit-exact."""
+    import os
+
+    from oracle import weighting as ow
+    from pfbg_testutil import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "l2_reweight.npz"))
+    assert int(g["ncase"]) == 8 and bool(g["zero_is_none"])
+    for k in range(int(g["ncase"])):
+        wp = g[f"wgtp_{k}"]
+        got = ow.l2_reweight(g[f"rv_{k}"], g[f"wgt_{k}"], g[f"mask_{k}"], float(g[f"dof_{k}"]), None if wp.size == 0 else wp)
+        assert got.dtype == g[f"out_{k}"].dtype and np.array_equal(got, g[f"out_{k}"])
+    assert ow.l2_reweight(np.zeros((1, 4, 2), complex), np.ones((1, 4, 2)), np.ones((4, 2), np.uint8), 2.0) is None
