@@ -83,6 +83,9 @@ typedef struct pfbg_plan_desc {
                           * plane -p-1 is the Hermitian mirror of plane p (G_{-p-1}(u,v) = conj G_p(-u,-v), the
                           * image being real) and samples near w = 0 use the mirrored cells of planes 0..pmirror-1
                           * instead of planes that would have to be stored and transformed */
+  int32_t fast_screen;   /* fp32 plans only: w-screen phasors from the SFU (sin.approx / cos.approx after the fp64
+                          * range reduction, abs. error ~5e-7) instead of sincospif; for epsilon >= 3e-6 */
+  int32_t reserved;
 } pfbg_plan_desc;
 
 typedef struct pfbg_plan_info {

@@ -38,7 +38,7 @@ class PlanDesc(C.Structure):
         ("w0", C.c_double), ("dw", C.c_double), ("nshift", C.c_double),
         ("corr_u", C.c_void_p), ("corr_v", C.c_void_p),
         ("gl_x", C.c_void_p), ("gl_w", C.c_void_p),
-        ("n_gl", C.c_int32), ("pmirror", C.c_int32),
+        ("n_gl", C.c_int32), ("pmirror", C.c_int32), ("fast_screen", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -22,6 +22,7 @@ struct GParams {
   // -pmirror..-1 read / write them at the mirrored cell of plane -q-1, conjugated; those planes are never
   // stored or transformed.
   int pmirror;
+  int fast_screen;  // fp32: w-screen phasors from the SFU (epsilon >= 3e-6)
 };
 
 // ---------------------------------------------------------------------------
@@ -112,6 +113,20 @@ __device__ __forceinline__ void cis_turns(double t, float& c, float& s) {
 __device__ __forceinline__ void cis_turns(double t, double& c, double& s) {
   t -= rint(t);
   sincospi(2.0 * t, &s, &c);
+}
+
+// w-screen phasor: FAST (fp32 only) takes sin / cos from the SFU after the same fp64 range reduction —
+// |2 pi t| <= pi, where sin.approx / cos.approx are good to ~4e-7 absolute — 5 instructions instead of ~30
+template <bool FAST, typename T>
+__device__ __forceinline__ void cis_screen(double t, T& c, T& s) {
+  if constexpr (FAST && sizeof(T) == 4) {
+    t -= rint(t);
+    const float a = 6.283185307179586f * (float)t;
+    s = __sinf(a);
+    c = __cosf(a);
+  } else {
+    cis_turns(t, c, s);
+  }
 }
 
 // phase (turns) of the centre shift and the n-1 shift for one sample

@@ -90,7 +90,7 @@ __device__ __forceinline__ void store_row(cx2<T>* __restrict__ p, const cx2<T> (
 // --------------------------------------------------------------------------- degrid direction
 // grid = (plane, image row), plane fastest: the CTAs sharing an image row (x, corr, nu table) are
 // co-resident, so those rows are read from DRAM once instead of once per plane.
-template <typename T>
+template <typename T, bool FAST = false>
 __global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 2))
 k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict__ beam, const T* __restrict__ corr,
            typename cplx_of<T>::type* __restrict__ grid) {
@@ -136,7 +136,7 @@ k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict
             cx2<T> v = {val, (T)0};
             if (p.do_wgridding && val != (T)0) {
               T c, sn;
-              cis_turns(wq * nuv[u][e], c, sn);
+              cis_screen<FAST>(wq * nuv[u][e], c, sn);
               v = {val * c, val * sn};
             }
             s[fft_pad<T>(pv[u][e])] = v;
@@ -152,7 +152,7 @@ k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict
       cx2<T> v = {val, (T)0};
       if (p.do_wgridding && val != (T)0) {
         T c, sn;
-        cis_turns(wq * ft.nutab[pix], c, sn);
+        cis_screen<FAST>(wq * ft.nutab[pix], c, sn);
         v = {val * c, val * sn};
       }
       const int jp = j - hy;
@@ -308,7 +308,7 @@ k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
 // One CTA per (plane, image row): read the row (active window only), inverse FFT along v, apply the
 // conjugate w-screen to the ny kept outputs and add their real parts to the fp64 accumulation image
 // (RED.F64; CTAs of one row are adjacent in the grid, so the 32 KB image row stays in L2).
-template <typename T>
+template <typename T, bool FAST = false>
 __global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 2))
 k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict__ grid, double* __restrict__ accimg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -363,7 +363,7 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
             double r;
             if (p.do_wgridding) {
               T c, sn;
-              cis_turns(wq * nuv[u][e], c, sn);
+              cis_screen<FAST>(wq * nuv[u][e], c, sn);
               r = (double)(v.x * c - v.y * sn);  // Re( conj(v) e^{-i theta} )
             } else {
               r = (double)v.x;
@@ -380,7 +380,7 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
       double r;
       if (p.do_wgridding) {
         T c, sn;
-        cis_turns(wq * ft.nutab[row + j], c, sn);
+        cis_screen<FAST>(wq * ft.nutab[row + j], c, sn);
         r = (double)(v.x * c - v.y * sn);
       } else {
         r = (double)v.x;

@@ -218,6 +218,7 @@ extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
   g.usign = d->usign; g.vsign = d->vsign; g.wsign = d->wsign;
   g.w0 = d->w0; g.dw = d->dw; g.nshift = d->nshift;
   g.pmirror = d->do_wgridding ? d->pmirror : 0;
+  g.fast_screen = (d->precision == PFBG_F32 && d->fast_screen) ? 1 : 0;
   g.ntile_u = d->nu / PFBG_TILE; g.ntile_v = d->nv / PFBG_TILE;
   pl->n_gl = d->n_gl;
 
@@ -384,6 +385,12 @@ static int fused_setup_t(pfbg_plan* pl) {
   CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  if constexpr (sizeof(T) == 4) {
+    CK(cudaFuncSetAttribute(k_rows_fwd<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CK(cudaFuncSetAttribute(k_rows_inv<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CK(cudaFuncSetAttribute(k_rows_inv<T, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_rows_fwd<T, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  }
   CKRC(dev_alloc(pl, pl->accimg, (size_t)g.nx * g.ny * sizeof(double)));
   CKRC(dev_alloc(pl, pl->nutab, (size_t)g.nx * g.ny * sizeof(double)));
   k_nu_table<<<dim3((g.ny + 127) / 128, g.nx), 128>>>(g, (double*)pl->nutab.p);
@@ -984,7 +991,11 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
   const int CC = pl->col_c;
   const GParams& g = pl->gp;
   const FusedTabs& ft = pl->ftabs;
-  k_rows_fwd<T><<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+  auto k_rows = &k_rows_fwd<T, false>;
+  if constexpr (sizeof(T) == 4) {
+    if (g.fast_screen) k_rows = &k_rows_fwd<T, true>;
+  }
+  k_rows<<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
       g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, (C*)pl->grid.p);
   LAUNCHED();
   CK(cudaGetLastError());
@@ -1014,7 +1025,11 @@ static int run_fused_inv(pfbg_plan* pl, cudaStream_t s, const void* beam, const 
   CK(cudaGetLastError());
   const int64_t npix = (int64_t)g.nx * g.ny;
   CK(cudaMemsetAsync(pl->accimg.p, 0, (size_t)npix * sizeof(double), s));
-  k_rows_inv<T><<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+  auto k_rows = &k_rows_inv<T, false>;
+  if constexpr (sizeof(T) == 4) {
+    if (g.fast_screen) k_rows = &k_rows_inv<T, true>;
+  }
+  k_rows<<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
       g, ft, (const C*)pl->grid.p, (double*)pl->accimg.p);
   LAUNCHED();
   CK(cudaGetLastError());

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import functools
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -34,6 +35,7 @@ LIGHTSPEED = 299792458.0  # scipy.constants.c, as used at operators/gridder.py:1
 
 TILE = 16  # uv tile edge of the binning kernel (cells)
 N_GL = 64  # Gauss-Legendre nodes for the w-correction evaluated on device
+FAST_SCREEN_EPS = 3e-6  # fp32 plans at or above this accuracy take the w-screen phasors from the SFU
 
 
 def good_size(n: int, primes=(2, 3, 5, 7)) -> int:
@@ -122,6 +124,7 @@ class Plan:
     est_cost: float = 0.0
     pmirror: int = 0  # virtual planes below plane 0 served by Hermitian mirroring (then w0 == dw/2)
     nplanes_std: int = 0  # planes a stack without mirroring would need for the same |w| range (reporting only)
+    fast_screen: int = 0  # fp32, epsilon >= 3e-6: w-screen phasors from the SFU (abs. error ~5e-7)
 
     @property
     def real_bytes(self) -> int:
@@ -132,7 +135,7 @@ class Plan:
             precision=self.precision, nx=self.nx, ny=self.ny, nu=self.nu, nv=self.nv,
             W=self.W, beta=self.beta, sigma=self.sigma, nplanes=self.nplanes,
             w0=self.w0, dw=self.dw, nshift=self.nshift, kernel_err=self.kernel_err,
-            pmirror=self.pmirror, nplanes_std=self.nplanes_std,
+            pmirror=self.pmirror, nplanes_std=self.nplanes_std, fast_screen=self.fast_screen,
         )
 
 
@@ -323,4 +326,6 @@ def make_plan(
         corr_u=_correction(nx, nu, W, beta), corr_v=_correction(ny, nv, W, beta),
         gl_x=gl_x, gl_w=gl_w, est_cost=float(cost), pmirror=int(pmirror),
         nplanes_std=int(npl_std if do_wgridding else 1),
+        fast_screen=int(precision == "single" and do_wgridding and epsilon >= FAST_SCREEN_EPS
+                        and os.environ.get("PFBG_FAST_SCREEN", "1") != "0"),
     )

@@ -54,6 +54,7 @@ class GridderPlan:
             corr_u=self._keep[0].ctypes.data, corr_v=self._keep[1].ctypes.data,
             gl_x=self._keep[2].ctypes.data, gl_w=self._keep[3].ctypes.data, n_gl=len(self._keep[2]),
             pmirror=int(getattr(plan, "pmirror", 0)),
+            fast_screen=int(getattr(plan, "fast_screen", 0)),
         )
         _lib.check(self._lib.pfbg_plan_create(C.byref(d), C.byref(self._h)))
         self.nrow = self.nchan = 0
@@ -327,7 +328,8 @@ _POOL_MAX = int(__import__("os").environ.get("PFBG_PLAN_POOL", "8"))
 
 def _pool_key(p: Plan, device):
     return (device, p.precision, p.nx, p.ny, p.nu, p.nv, p.W, round(p.beta, 12), p.pixsize_x, p.pixsize_y,
-            p.center_x, p.center_y, p.usign, p.vsign, p.wsign, p.do_wgridding, p.divide_by_n, p.dw, p.nshift)
+            p.center_x, p.center_y, p.usign, p.vsign, p.wsign, p.do_wgridding, p.divide_by_n, p.dw, p.nshift,
+            getattr(p, "fast_screen", 0))
 
 
 def clear_plan_pool():

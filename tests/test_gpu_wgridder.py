@@ -487,3 +487,35 @@ def test_image_sizes_off_the_vector_path(gpu, prec, eps, nx, ny):
         dref = dft.dft_vis2dirty(p["uvw"], p["freq"], p["vis"].astype(cdt), p["wgt"].astype(rdt), p["mask"], nx, ny,
                                  p["cell"], p["cell"], **kw)
         assert rel_l2(d, dref) <= eps
+
+
+def test_fast_screen_phasors_stay_inside_the_error_budget(gpu, monkeypatch):
+    """fp32 plans with epsilon >= 3e-6 take the w-screen phasors from the SFU (plan.fast_screen); the switch must
+    cost well under epsilon: both variants against the explicit DFT, and against each other, on a wide field."""
+    p = small_problem(nrow=800, nchan=4, nx=128, ny=96, seed=21, wscale=3.0)
+    kw = dict(flip_v=True, divide_by_n=False)
+    eps = 1e-5
+    ref = dft.dft_dirty2vis(p["uvw"], p["freq"], p["img"], p["cell"], p["cell"], **kw)
+    vis, wgt = p["vis"].astype(np.complex64), p["wgt"].astype(np.float32)
+    dref = dft.dft_vis2dirty(p["uvw"], p["freq"], vis, wgt, p["mask"], 128, 96, p["cell"], p["cell"], **kw)
+    act = p["mask"] != 0
+    res = {}
+    for fast in ("1", "0"):
+        monkeypatch.setenv("PFBG_FAST_SCREEN", fast)
+        W.clear_plan_pool()
+        with W.plan_for(p["uvw"], p["freq"], npix_x=128, npix_y=96, pixsize_x=p["cell"], pixsize_y=p["cell"],
+                        epsilon=eps, precision="single", mask=p["mask"], **kw) as gp:
+            assert gp.plan.fast_screen == int(fast) and gp.plan.nplanes > 1
+            v, d = gp.degrid(p["img"].astype(np.float32)), gp.grid(vis, wgt)
+        assert rel_l2(v[act], ref[act]) <= eps and rel_l2(d, dref) <= eps
+        res[fast] = (v, d)
+    assert rel_l2(res["1"][0][act], res["0"][0][act]) <= 0.2 * eps and rel_l2(res["1"][1], res["0"][1]) <= 0.2 * eps
+    # tighter requests keep the accurate phasors
+    monkeypatch.setenv("PFBG_FAST_SCREEN", "1")
+    W.clear_plan_pool()
+    with W.plan_for(p["uvw"], p["freq"], npix_x=128, npix_y=96, pixsize_x=p["cell"], pixsize_y=p["cell"],
+                    epsilon=1e-6, precision="single", mask=p["mask"], **kw) as gp:
+        assert gp.plan.fast_screen == 0
+    with W.plan_for(p["uvw"], p["freq"], npix_x=128, npix_y=96, pixsize_x=p["cell"], pixsize_y=p["cell"],
+                    epsilon=1e-5, precision="double", mask=p["mask"], **kw) as gp:
+        assert gp.plan.fast_screen == 0
