@@ -35,6 +35,9 @@ __device__ __forceinline__ bool in_window(int n, int lo, int len, int size) {
 }
 
 #define ROWS_MAX_THREADS 256
+#ifndef PFBG_ROWS_INV_INFLIGHT
+#define PFBG_ROWS_INV_INFLIGHT 3
+#endif
 
 // ---- vector access helpers: the load / store loops of these kernels are latency-bound (ncu: 40-55 % of
 // the stall samples were long-scoreboard waits in the fill / drain loops), so every global access moves
@@ -340,12 +343,14 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
   const int64_t row = (int64_t)i * p.ny;
   double* dst = accimg + row;
   if ((p.ny & 7) == 0) {
+    // RU groups of 4 pixels in flight per thread: the nu-table / position loads are L2 round trips
+    constexpr int RU = PFBG_ROWS_INV_INFLIGHT;
     const int ng = p.ny >> 2;
-    for (int g0 = tid; g0 < ng; g0 += 2 * nthr) {
-      double nuv[2][4];
-      int pv[2][4];
+    for (int g0 = tid; g0 < ng; g0 += RU * nthr) {
+      double nuv[RU][4];
+      int pv[RU][4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < RU; ++u) {
         const int g = g0 + u * nthr;
         if (g < ng) {
           const int j = 4 * g, jp = j - hy;
@@ -354,7 +359,7 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < RU; ++u) {
         const int g = g0 + u * nthr;
         if (g < ng) {
 #pragma unroll
