@@ -1417,7 +1417,12 @@ extern "C" int pfbg_l2_reweight(int32_t precision, int32_t device, const void* r
   if (wgtp) CKRC(t.get(&dp, wgtp, wbytes, dev, true, s));
   if (mask) CKRC(t.get(&dmask, mask, (size_t)nvis, dev, true, s));
   CKRC(t.get(&dwgt, wgt, wbytes, dev, true, s));
-  CKRC(t.get(&dsums, nullptr, 17 * 8, false, false, s));
+  {  // 17 doubles of reduction scratch per (host thread, device), kept: no cudaMalloc / cudaFree per call
+    static thread_local void* scratch[64] = {};
+    if (device < 0 || device >= 64) return fail(PFBG_ERR_ARG, "bad device");
+    if (!scratch[device]) CK(cudaMalloc(&scratch[device], 17 * 8));
+    dsums = scratch[device];
+  }
   CK(cudaMemsetAsync(dsums, 0, 17 * 8, s));
   dim3 rgrid(592, ncorr);
   if (nvis > 0) {
