@@ -1,7 +1,7 @@
 // CUDA kernels of the B200 w-gridder (sm_100a).
 //   kernel 1  k_bin            : uv-tile / w-plane bucket key per sample
-//   kernel 2  k_grid_direct    : spread samples onto the plane stack (vector RED)
-//             k_grid_tile      : shared-memory tile accumulation (see grid_tile.cuh)
+//   kernel 2  k_grid_direct    : spread samples onto the plane stack (vector RED; last-resort path, the
+//                                run kernels of runs.cuh are the default)
 //   kernel 3  k_degrid_direct  : gather samples from the plane stack
 //   kernel 4  k_img2grid / k_grid2img / k_corr_init : w-screen, grid correction,
 //             taper (beam), wsum and ridge fused with the pad / crop.

@@ -1,5 +1,5 @@
 // C-ABI implementation (include/pfbgrid.h): plan, binding/sort, cuFFT plumbing
-// and launch sequencing of the sm_100a kernels in kernels.cuh / grid_tile.cuh.
+// and launch sequencing of the sm_100a kernels in kernels.cuh / runs.cuh / fused_fft.cuh.
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <cub/device/device_radix_sort.cuh>
