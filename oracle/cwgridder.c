@@ -172,3 +172,42 @@ void cw_degrid(int64_t n, const int64_t* order, const double* gu, const double* 
     out[2 * k + 1] = im;
   }
 }
+
+/* Sampled explicit DFT (the truth of /root/reference/tests/test_hessian_approx.py:23-67) in OpenMP, for
+ * full-size parity tests: out[p] = Re sum_k a_k exp(+2 pi i (u_k l_p + v_k m_p - w_k nm1_p)), with u, v, w
+ * already in wavelengths and sign-flipped.  oracle/dft.py:dft_vis2dirty is the numpy statement of the same
+ * sum; tests/test_oracle.py pins one against the other. */
+void cw_dft_pixels(int64_t n, const double* u, const double* v, const double* w, const double* a /* 2n */,
+                   int64_t npix, const double* l, const double* m, const double* nm1, double* out) {
+  const double twopi = 6.283185307179586476925286766559;
+  for (int64_t p = 0; p < npix; ++p) {
+    double acc = 0.0;
+    const double lp = l[p], mp = m[p], np_ = nm1[p];
+#pragma omp parallel for reduction(+ : acc) schedule(static)
+    for (int64_t k = 0; k < n; ++k) {
+      double ph = u[k] * lp + v[k] * mp - w[k] * np_;
+      ph -= rint(ph);
+      const double c = cos(twopi * ph), s = sin(twopi * ph);
+      acc += a[2 * k] * c - a[2 * k + 1] * s;
+    }
+    out[p] = acc;
+  }
+}
+
+/* vis[k] = sum_p flux_p exp(-2 pi i (u_k l_p + v_k m_p - w_k nm1_p)) for n sampled (u, v, w). */
+void cw_dft_rows(int64_t n, const double* u, const double* v, const double* w, int64_t npix, const double* l,
+                 const double* m, const double* nm1, const double* flux, double* out /* 2n */) {
+  const double twopi = 6.283185307179586476925286766559;
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < n; ++k) {
+    double re = 0.0, im = 0.0;
+    for (int64_t p = 0; p < npix; ++p) {
+      double ph = u[k] * l[p] + v[k] * m[p] - w[k] * nm1[p];
+      ph -= rint(ph);
+      re += flux[p] * cos(twopi * ph);
+      im -= flux[p] * sin(twopi * ph);
+    }
+    out[2 * k] = re;
+    out[2 * k + 1] = im;
+  }
+}
