@@ -4,8 +4,11 @@
 Contract (see README / DESIGN.md §measurement):
   python bench.py --gpus N --steps K --warmup W            our arm (B200 kernels)
   python bench.py --impl reference --gpus N ...           CPU arm (oracle port; ducc0 unavailable)
-One JSON line on stdout from rank 0.  N>1 is launched with torch.distributed.run (one rank per
-GPU, one imaging band per rank, no data-path collective: weak scaling across bands).
+One JSON line on stdout from rank 0.  N>1 is launched with torch.distributed.run, one rank per GPU.
+Multi-band workloads (c2) are ONE job whose bands are partitioned over the N GPUs (strong scaling:
+longest-processing-time-first assignment, then the plane transforms of the heaviest bands are offloaded
+to the least loaded GPUs over NVLink peer memory, pfb_imaging_b200/split.py); --replicas runs the
+round-1 mode instead (every GPU owns a complete job, weak scaling).
 """
 import argparse
 import json
@@ -92,6 +95,7 @@ def cpu_hessian_sample(cfg, band, row_step, nthreads_note=True):
     from oracle import cwgridder as cw
     from pfb_imaging_b200.plan import make_plan, w_range
 
+    cw.set_threads()  # every host core, whatever OMP_NUM_THREADS torchrun exported
     d, cell, x = make_inputs(cfg, band)
     uvw, freq = d["uvw"], d["freq"]
     wmin, wmax = w_range(uvw, freq)
@@ -125,17 +129,21 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, args.steps)
+    steps = max(1, min(args.steps, 3))  # each step = one Hessian apply of band 0 on the host (seconds of CPU work)
     vals, last = [], None
-    for _ in range(min(steps, 2)):  # each step = one bounded sample (tens of seconds of CPU work)
+    for it in range(min(args.warmup, 1) + steps):
         last = cpu_hessian_sample(cfg, 0, args.cpu_row_step)
-        vals.append(last["value"])
+        if it >= min(args.warmup, 1):
+            vals.append(last["value"])
     v = float(np.mean(vals))
-    sample = (f"every {args.cpu_row_step}th row of band 0 for the per-visibility loops ({last['nvis_sample']} vis, extrapolated "
-              f"to {last['nvis_full']}); plane FFTs/screens at full size; fp64 CPU restatement (ducc0 unavailable)")
+    how = ("all rows" if args.cpu_row_step == 1 else
+           f"every {args.cpu_row_step}th row for the per-visibility loops ({last['nvis_sample']} vis, extrapolated)")
+    sample = (f"band 0 of the workload ({last['nvis_full']} vis), {how}; plane FFTs/screens at full size; fp64 C/OpenMP "
+              f"restatement + scipy.fft on {last['cores']} threads (the port computes in fp64 whatever the workload's "
+              f"dtype; ducc0 itself is not installable here, parity with it is unpinned)")
     line = {
         "impl": "reference", "metric": "Mvis/s per Hessian apply (degrid+grid)", "value": v, "unit": "Mvis/s",
-        "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 * last["t_full"],
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * last["t_full"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["name"], "plan": last["plan"]},
         "cpu_baseline": {"value": v, "unit": "Mvis/s", "cores": last["cores"], "kind": "port", "sample": sample},
@@ -145,22 +153,11 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
-def assign_bands(costs, world):
-    """Longest-processing-time-first partition of the bands over the ranks."""
-    order = sorted(range(len(costs)), key=lambda b: -costs[b])
-    load, owner = [0.0] * world, {}
-    for b in order:
-        r = min(range(world), key=lambda k: load[k])
-        owner[b] = r
-        load[r] += costs[b]
-    return owner
-
-
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
 
-    from pfb_imaging_b200 import _lib, operators as ops, synth, wgridder as W
+    from pfb_imaging_b200 import _lib, operators as ops, split as bsplit, synth, wgridder as W
     from pfb_imaging_b200.plan import make_plan, w_range
 
     rank = int(os.environ.get("RANK", "0"))
@@ -174,27 +171,36 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     p = 4 if cfg["precision"] == "single" else 8
-    nbands = cfg.get("nbands", 1)
-    # Default = weak scaling: every GPU owns one complete job (all `nbands` bands of the config, i.e.
-    # BASELINE.json configs[1] at N=1), so N GPUs image N jobs with no data-path collective.
-    # --strong partitions ONE job's bands over the ranks instead (limited by band heterogeneity:
-    # sum(ms_per_band)/max(ms_per_band), both reported in the JSON line).
-    strong = bool(args.strong) and nbands >= world and nbands > 1
+    job_bands = list(range(cfg.get("nbands", 1)))
+    if args.bands:
+        job_bands = [int(b) for b in args.bands.split(",")]
+    nbands = len(job_bands)
+    # Default for a multi-band workload on N > 1 GPUs: ONE job, its bands partitioned over the ranks (strong scaling,
+    # what north_star specifies).  --replicas: every GPU owns a complete job (weak scaling, the round-1 mode).
+    strong = nbands > 1 and world > 1 and not args.replicas
+
+    def gather_obj(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    owner = None
     if strong:
-        # the job is the whole multi-band config: partition its bands over the ranks (strong scaling)
-        probe, cell0, _ = make_inputs(cfg, 0)
-        costs = []
-        for b in range(nbands):
+        probe, cell0, _ = make_inputs(cfg, job_bands[0])
+        est = []
+        for b in job_bands:
             fr = synth.band_freqs(b, 8, cfg["nchan"])
             wmin, wmax = w_range(probe["uvw"], fr)
             pl = make_plan(nx=cfg["nx"], ny=cfg["nx"], pixsize_x=cell0, pixsize_y=cell0, epsilon=cfg["epsilon"],
                            flip_v=True, divide_by_n=False, sigma_min=1.1, sigma_max=3.0, precision=cfg["precision"],
                            wmin=wmin, wmax=wmax, nvis=probe["uvw"].shape[0] * cfg["nchan"])
-            costs.append(pl.est_cost)
-        owner = assign_bands(costs, world)
-        my_bands = [b for b in range(nbands) if owner[b] == rank]
+            est.append(pl.est_cost)
+        owner = bsplit.lpt_assign(est, world)  # index into job_bands -> rank
+        my_bands = [b for i, b in enumerate(job_bands) if owner[i] == rank]
     else:
-        my_bands = list(range(nbands)) if nbands > 1 else [rank % 8]
+        my_bands = list(job_bands) if nbands > 1 else [rank % 8]
 
     bands = []
     for b in my_bands:
@@ -208,24 +214,6 @@ def run_ours(args, cfg):
                           wsum=float(d["wgt"].sum(dtype=np.float64)), nvis=d["uvw"].shape[0] * d["freq"].size))
     nvis_local = sum(bd["nvis"] for bd in bands)
     stream = torch.cuda.current_stream().cuda_stream
-    # the bands of a job are independent: they alternate between two compute streams, so the tail of one band's
-    # kernels overlaps the head of the next band's (measured: 100.4 -> 89.5 ms for the 8 bands of C2; more than
-    # two streams bring nothing).  Every step forks from / joins the current stream, where the events are recorded.
-    cstreams = [torch.cuda.Stream(dev) for _ in range(2)] if len(bands) > 1 else []
-
-    def step_dev():
-        if not cstreams:
-            for bd in bands:
-                bd["gp"].hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(), stream)
-            return
-        cur = torch.cuda.current_stream()
-        for cs in cstreams:
-            cs.wait_stream(cur)
-        for i, bd in enumerate(bands):
-            bd["gp"].hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(),
-                                 cstreams[i % 2].cuda_stream)
-        for cs in cstreams:
-            cur.wait_stream(cs)
 
     def barrier():
         torch.cuda.synchronize()
@@ -233,10 +221,78 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- per-phase timing of every band on its own (events inside the library, same stream): the input of the
+    # offload schedule and of the roofline section ------------------------------------------------------------
+    names = ["stage_in", "pad_screen_fft", "degrid", "zero_grid", "spread", "fft_crop_screen", "stage_out"]
+    phases = dict.fromkeys(names, 0.0)
+    per_band, band_stats = {}, {}
+    for bd in bands:
+        gp = bd["gp"]
+        for _ in range(2):
+            gp.hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(), stream)
+        gp.set_profiling(True)
+        rec = []
+        for _ in range(3):
+            gp.hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(), stream)
+            torch.cuda.synchronize()
+            rec.append(gp.timings())
+        gp.set_profiling(False)
+        ph = np.median(np.array(rec), axis=0).tolist()
+        bd["phases"] = dict(zip(names, ph))
+        per_band[bd["b"]] = round(float(sum(ph)), 3)
+        band_stats[bd["b"]] = dict(ms=float(sum(ph)), P=int(bd["info"]["nplanes"]),
+                                   t_plane=float(bd["phases"]["pad_screen_fft"] + bd["phases"]["fft_crop_screen"]) /
+                                   int(bd["info"]["nplanes"]))
+        for k, v in zip(names, ph):
+            phases[k] += v
+    all_stats = {}
+    for dct in gather_obj(band_stats):
+        all_stats.update(dct)
+
+    # ---- strong scaling: offload planes of the heaviest bands to the least loaded GPUs -----------------------
+    offloads, model_loads, split = {}, None, None
+    if strong:
+        costs = [all_stats[b]["ms"] for b in job_bands]
+        tpl = [all_stats[b]["t_plane"] for b in job_bands]
+        npl = [all_stats[b]["P"] for b in job_bands]
+        off_idx, model_loads = ({}, None) if args.no_offload else bsplit.plan_offloads(costs, tpl, npl, owner, world)
+        offloads = {job_bands[i]: o for i, o in off_idx.items()}
+        if offloads:
+            split = bsplit.BandSplit({bd["b"]: bd["gp"] for bd in bands}, offloads, rank, local, gather_obj)
+    # helper work runs on its own high-priority stream(s): its CTAs go first whenever an SM frees up, so the owner
+    # of the heavy band never waits for a helper that is busy with its own band
+    hstreams = {b: torch.cuda.Stream(dev, priority=-1) for b in (split.helpers if split else {})}
+    # the bands of a GPU are independent: they alternate between two compute streams, so the tail of one band's
+    # kernels overlaps the head of the next band's (measured: 100.4 -> 89.5 ms for the 8 bands of C2; more than
+    # two streams bring nothing).  Every step forks from / joins the current stream, where the events are recorded.
+    cstreams = [torch.cuda.Stream(dev) for _ in range(2)] if len(bands) > 1 else []
+
+    def step_dev():
+        cur = torch.cuda.current_stream()
+        for hs in hstreams.values():
+            hs.wait_stream(cur)
+        if split:
+            split.serve({b: hs.cuda_stream for b, hs in hstreams.items()})
+        if not cstreams:
+            for bd in bands:
+                bd["gp"].hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(), stream)
+        else:
+            for cs in cstreams:
+                cs.wait_stream(cur)
+            for i, bd in enumerate(bands):
+                bd["gp"].hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(),
+                                     cstreams[i % 2].cuda_stream)
+            for cs in cstreams:
+                cur.wait_stream(cs)
+        for hs in hstreams.values():
+            cur.wait_stream(hs)
+
     # ---- device-resident timing -------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_dev()
     barrier()
+    if split:
+        split.check()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _lib.load().pfbg_launch_count()
@@ -251,6 +307,10 @@ def run_ours(args, cfg):
     launches = _lib.load().pfbg_launch_count() - launches0
     sampler.stop_flag = True
     sampler.join()
+    if split:
+        split.check()
+    ms_ranks = [float(v) / args.steps for v in gather_obj(ms_total)]
+    launches_all = int(sum(gather_obj(int(launches))))
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,24 +319,27 @@ def run_ours(args, cfg):
     if world > 1:
         dist.all_reduce(nvis_all, op=dist.ReduceOp.SUM)
     value = float(nvis_all.item()) / (ms_step * 1e-3) / 1e6
-
-    # ---- per-phase timing (events inside the library, same stream), summed over my bands ---
-    names = ["stage_in", "pad_screen_fft", "degrid", "zero_grid", "spread", "fft_crop_screen", "stage_out"]
-    phases = dict.fromkeys(names, 0.0)
-    per_band = {}
-    for bd in bands:
-        gp = bd["gp"]
-        gp.set_profiling(True)
-        rec = []
-        for _ in range(3):
-            gp.hessian_dev(bd["x_d"].data_ptr(), None, bd["wsum"], 0.0, bd["out_d"].data_ptr(), stream)
-            torch.cuda.synchronize()
-            rec.append(gp.timings())
-        gp.set_profiling(False)
-        ph = np.median(np.array(rec), axis=0).tolist()
-        per_band[bd["b"]] = round(float(sum(ph)), 3)
-        for k, v in zip(names, ph):
-            phases[k] += v
+    helper_phases = {}
+    if split:  # one more (untimed) step with library events on the helper plans: where the helper's time goes
+        for h in split.helpers.values():
+            h.set_profiling(True)
+        step_dev()
+        torch.cuda.synchronize()
+        for b, h in split.helpers.items():
+            tm = h.timings()
+            h.set_profiling(False)
+            if len(tm) >= 5:
+                helper_phases[b] = dict(wait_x=round(tm[0], 3), copy_x_fwd_planes=round(tm[1], 3),
+                                        wait_grid=round(tm[2], 3), inv_planes_partial=round(tm[3], 3))
+        barrier()
+        split.check()
+        barrier()
+        split.close()
+        split = None
+        barrier()
+    helper_all = {}
+    for dct in gather_obj(helper_phases):
+        helper_all.update(dct)
 
     # ---- end to end through the operator call a pfb solver makes (host numpy in/out) ------
     ops._CACHE_SIZE = max(ops._CACHE_SIZE, len(bands))
@@ -324,6 +387,7 @@ def run_ours(args, cfg):
     pool = ops.BandPool(pool_ops, nband=len(bands))
     xcube = np.stack([bd["x"] for bd in bands]) if bands else None
     e2e_pool_value = None
+    t_pool = 0.0
     if bands:
         res = None
         for _ in range(3):  # same hold-one-result pattern as the timed loop (the pinned result blocks get allocated here)
@@ -336,11 +400,41 @@ def run_ours(args, cfg):
         t_pool = (time.perf_counter() - t0) / args.steps
         assert np.isfinite(res[0, :8, :8]).all()
         del res
-        tp = torch.tensor([t_pool], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        e2e_pool_value = float(nvis_all.item()) / float(tp.item()) / 1e6
+    tp = torch.tensor([t_pool], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    e2e_pool_value = float(nvis_all.item()) / float(tp.item()) / 1e6
     pool.close()
+    img_bytes = int(sum(gather_obj(int(sum(bd["x"].nbytes for bd in bands)))))
+
+    # ---- the path pfb's own entry points take by default: fp64, epsilon = 1e-7 (core/grid.py:50), one band ----
+    f64 = None
+    if world == 1 and args.workload == "c2" and not args.no_f64:
+        cfg64 = WORKLOADS["c2d"]
+        d, cell, x = make_inputs(cfg64, 0)
+        gp = W.plan_for(d["uvw"], d["freq"], npix_x=cfg64["nx"], npix_y=cfg64["nx"], pixsize_x=cell, pixsize_y=cell,
+                        epsilon=cfg64["epsilon"], flip_v=True, divide_by_n=False, precision="double", mask=d["mask"],
+                        sigma_min=1.1, sigma_max=3.0, device=local)
+        gp.bind_weights(d["wgt"])
+        x_d = torch.from_numpy(x).to(dev)
+        o_d = torch.empty_like(x_d)
+        ws = float(d["wgt"].sum(dtype=np.float64))
+        for _ in range(3):
+            gp.hessian_dev(x_d.data_ptr(), None, ws, 0.0, o_d.data_ptr(), stream)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            gp.hessian_dev(x_d.data_ptr(), None, ws, 0.0, o_d.data_ptr(), stream)
+        a1.record()
+        torch.cuda.synchronize()
+        ms64 = a0.elapsed_time(a1) / 5
+        i64 = gp.info()
+        f64 = {"workload": cfg64["name"] + " (band 0)", "value": d["uvw"].shape[0] * d["freq"].size / (ms64 * 1e-3) / 1e6,
+               "unit": "Mvis/s", "ms_per_band": ms64, "dtype": "f64",
+               "plan": {k: i64[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "pmirror")}}
+        gp.close()
+        del x_d, o_d
 
     if rank == 0:
         peaks = {}
@@ -386,11 +480,11 @@ def run_ours(args, cfg):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_hessian_sample(cfg, bands[0]["b"], args.cpu_row_step)
+            how = "all rows" if args.cpu_row_step == 1 else f"every {args.cpu_row_step}th row for the per-visibility loops (extrapolated)"
             cpu = {"value": c["value"], "unit": "Mvis/s", "cores": c["cores"], "kind": "port",
-                   "sample": (f"band {bands[0]['b']} only; every {args.cpu_row_step}th row for the per-visibility loops ({c['nvis_sample']} of "
-                              f"{c['nvis_full']} vis, extrapolated), plane FFTs at full size; fp64 C/OpenMP restatement + scipy.fft "
-                              f"(ducc0 unavailable); planes {c['t_planes']:.1f}s, vis(sample) {c['t_vis_sample']:.1f}s")}
-        img_bytes = int(sum(bd["x"].nbytes for bd in bands))
+                   "sample": (f"one Hessian apply of band {bands[0]['b']} ({c['nvis_full']} vis), {how}, plane FFTs at full size; fp64 "
+                              f"C/OpenMP restatement + scipy.fft (ducc0 not installable: parity with it unpinned); planes "
+                              f"{c['t_planes']:.1f}s, vis {c['t_vis_sample']:.1f}s")}
         line = {
             "metric": "Mvis/s per Hessian apply (degrid+grid)", "value": value, "unit": "Mvis/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -398,18 +492,29 @@ def run_ours(args, cfg):
             "data": "synthetic",
             "config": {"workload": cfg["name"], "bands_total": nbands if strong else nbands * world,
                        "bands_on_rank0": [bd["b"] for bd in bands],
-                       "strong_scaling_bound_one_job": round(sum(per_band.values()) / max(per_band.values()), 2),
+                       "ms_per_band": {str(b): round(all_stats[b]["ms"], 3) for b in sorted(all_stats)},
+                       "ms_per_rank": [round(v, 3) for v in ms_ranks],
+                       "band_owner": ({str(b): owner[i] for i, b in enumerate(job_bands)} if strong else None),
+                       "plane_offloads": {str(b): o for b, o in sorted(offloads.items())},
+                       "modelled_ms_per_rank": [round(v, 3) for v in model_loads] if model_loads else None,
+                       "helper_phases_ms": {str(b): v for b, v in sorted(helper_all.items())},
+                       "sum_over_max_of_bands": round(sum(v["ms"] for v in all_stats.values()) /
+                                                      max(v["ms"] for v in all_stats.values()), 2),
                        "nvis_total": int(nvis_all.item()),
                        "l2": "inputs larger than L2 (plane stack %.1f GB per band)" % (info["grid_bytes"] / 1e9),
                        "plan_first_band": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "nplanes_std", "pmirror", "beta")},
                        "streams": "the bands of a GPU alternate between 2 compute streams" if len(bands) > 1 else "one stream",
-                       "parallelism": (f"{nbands} bands of one job LPT-partitioned over {world} GPU(s)" if strong else
-                                       f"{world} job(s) of {nbands} band(s), one job per GPU") + ", no data-path collective"},
+                       "parallelism": (f"{nbands} bands of ONE job partitioned over {world} GPUs (longest-processing-time first); "
+                                       f"plane transforms of {len(offloads)} band(s) offloaded to the least loaded GPUs over NVLink "
+                                       "peer memory (fused into the transform kernels, flags in device memory, no collective)"
+                                       if strong else
+                                       f"{world} job(s) of {nbands} band(s), one job per GPU, no data-path collective")},
             "e2e": {"value": e2e_pool_value, "unit": "Mvis/s", "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
                     "call": "operators.BandPool.hess_dot(x (nband, nx, ny) host numpy) -> new host numpy cube (the reference's BandWorkerPool.hess_dot); bands pinned on the device at construction (like load_band), copies of neighbouring bands overlap the kernels",
                     "hessian_slice_value": e2e_value,
                     "hessian_slice_call": "operators.hessian_slice(x, xout=, uvw=, weight=, vis_mask=, freq=, ...) band after band, host numpy in/out, nothing overlapped"},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches_all, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "f64_default_path": f64,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -423,9 +528,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-row-step", type=int, default=16)
+    ap.add_argument("--cpu-row-step", type=int, default=1, help="CPU arm: per-visibility loops on every n-th row (1 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--strong", action="store_true", help="partition ONE job's bands over the GPUs (strong scaling)")
+    ap.add_argument("--no-f64", action="store_true", help="skip the fp64 / eps=1e-7 single-band measurement")
+    ap.add_argument("--replicas", action="store_true", help="every GPU owns a complete job (weak scaling, the round-1 mode)")
+    ap.add_argument("--strong", action="store_true", help="(default for multi-band workloads) kept for compatibility")
+    ap.add_argument("--no-offload", action="store_true", help="band partition only, no plane offload")
+    ap.add_argument("--bands", default="", help="restrict the job to these bands, e.g. 7,0 (development)")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":

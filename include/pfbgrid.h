@@ -166,6 +166,12 @@ int pfbg_hessian(pfbg_plan* plan, const void* x, const void* beam, double wsum, 
 int pfbg_host_register(void* ptr, uint64_t bytes);
 int pfbg_host_unregister(void* ptr);
 
+/* 64-bit content hash of a host range (multi-threaded, a few ms per 100 MB).  The host-side plan cache of
+ * pfb_imaging_b200.operators validates a cached band binding with it on every call: the reference keeps no state
+ * between hessian_slice calls (operators/hessian.py:15-100), so an in-place edit of weights, flags or beam between
+ * two calls must be seen. */
+int pfbg_host_hash64(const void* ptr, uint64_t bytes, uint64_t* out);
+
 /* Seconds spent in the phases of the last grid/degrid/hessian call when profiling is on. */
 int pfbg_set_profiling(pfbg_plan* plan, int32_t on);
 int pfbg_get_timings(pfbg_plan* plan, float* ms, int32_t n, int32_t* n_written);
@@ -221,6 +227,37 @@ int pfbg_conv_destroy(pfbg_conv* conv);
 int pfbg_conv_set_kernel(pfbg_conv* conv, const void* khat, int32_t half, uint32_t flags, void* stream);
 int pfbg_conv_apply(pfbg_conv* conv, const void* x, const void* beam, double eta, void* out, uint32_t flags,
                     void* stream);
+
+/*
+ * Band split across two GPUs, one process per GPU (the reference runs one actor per band,
+ * operators/band_worker.py:217-246, and sums row partitions by linearity, operators/gridder.py:962-1016,
+ * tests/test_imager_pass2.py:45-63).  When a job has as many bands as GPUs the heaviest band bounds the step, so
+ * its owner hands the plane transforms of the LAST nq w-planes to a helper GPU.  The transfers are fused into the
+ * transform kernels: the helper's forward column pass stores into the owner's peer-mapped plane stack, its inverse
+ * column pass loads the gridded columns from there, and its fp64 partial image reaches the owner by one peer
+ * copy.  Flags in device memory order the two streams; no host round trip, no collective.
+ *
+ * Set-up: owner  pfbg_split_owner_init(plan, nq, blobs[4])      -> ship blobs + plan desc + active window (host side)
+ *         helper pfbg_split_helper_create(desc, nq, window, blobs, &hplan, &mailbox_blob) -> ship mailbox_blob back
+ *         owner  pfbg_split_owner_connect(plan, &mailbox_blob)
+ * Per apply: owner pfbg_hessian(plan, ..., PFBG_DEVICE_PTRS, stream); helper pfbg_split_helper_serve(hplan, stream),
+ * once per owner call and in the same order.  A flag wait gives up after 20 s (pfbg_split_status reports it).
+ */
+#define PFBG_IPC_BLOB_BYTES 96
+typedef struct pfbg_ipc_blob { unsigned char bytes[PFBG_IPC_BLOB_BYTES]; } pfbg_ipc_blob;
+int pfbg_ipc_export(const void* dev_ptr, pfbg_ipc_blob* blob);
+int pfbg_ipc_open(int32_t device, const pfbg_ipc_blob* blob, void** dev_ptr);
+int pfbg_ipc_close_all(void);
+int pfbg_split_owner_init(pfbg_plan* plan, int32_t nq, pfbg_ipc_blob* blobs4);
+int pfbg_split_owner_connect(pfbg_plan* plan, const pfbg_ipc_blob* helper_mailbox);
+/* window4 = {a_lo, a_len, b_lo, b_len}: the owner's active uv window (pfbg_plan_get_window) */
+int pfbg_split_helper_create(const pfbg_plan_desc* desc, int32_t nq, const int32_t* window4,
+                             const pfbg_ipc_blob* owner_blobs4, pfbg_plan** out, pfbg_ipc_blob* mailbox_out);
+int pfbg_split_helper_serve(pfbg_plan* plan, void* stream);
+int pfbg_split_status(pfbg_plan* plan, void* stream, int32_t* timed_out);
+int pfbg_split_end(pfbg_plan* plan);
+/* rows [a_lo, a_lo + a_len) x columns [b_lo, b_lo + b_len) (circular) of the grid any bound sample can touch */
+int pfbg_plan_get_window(const pfbg_plan* plan, int32_t* window4);
 
 /*
  * Unit-test hook for the in-shared-memory FFT engine behind the fused plane transforms:

@@ -40,6 +40,15 @@ int cw_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU baseline sets its thread count explicitly */
+void cw_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* Spread n samples (already in bucket order) onto grid[P][nu][nv] (interleaved re,im). */
 void cw_grid(int64_t n, const int64_t* order, const double* gu, const double* gv, const double* gw,
              const int32_t* iu0, const int32_t* iv0, const int32_t* ip0, const uint64_t* key,

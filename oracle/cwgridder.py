@@ -35,6 +35,12 @@ def nthreads():
     return lib().cw_num_threads()
 
 
+def set_threads(n=None):
+    """Use `n` OpenMP threads (default: every core this process may run on), whatever OMP_NUM_THREADS says."""
+    lib().cw_set_threads(int(n or _ncores()))
+    return nthreads()
+
+
 def _ncores():
     try:
         return len(os.sched_getaffinity(0))

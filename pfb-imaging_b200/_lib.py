@@ -19,6 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 PFBG_F32, PFBG_F64 = 0, 1
 HOST_PTRS, DEVICE_PTRS, APPLY_WGT, NO_MASK_ZERO = 0, 1, 2, 4
 PINNED_IN, PINNED_OUT, BEAM_CACHED = 16, 32, 64
+IPC_BLOB_BYTES = 96
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -84,6 +85,17 @@ SIGNATURES = {
     "pfbg_counts_to_weights": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                          _dbl, _dbl, _dbl, _dbl, _dbl, _u32, _vp]),
     "pfbg_l2_reweight": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _vp, _vp, _u32, _vp]),
+    "pfbg_host_hash64": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "pfbg_ipc_export": (C.c_int, [_vp, _vp]),
+    "pfbg_ipc_open": (C.c_int, [_i32, _vp, C.POINTER(_vp)]),
+    "pfbg_ipc_close_all": (C.c_int, []),
+    "pfbg_split_owner_init": (C.c_int, [_vp, _i32, _vp]),
+    "pfbg_split_owner_connect": (C.c_int, [_vp, _vp]),
+    "pfbg_split_helper_create": (C.c_int, [C.POINTER(PlanDesc), _i32, _vp, _vp, C.POINTER(_vp), _vp]),
+    "pfbg_split_helper_serve": (C.c_int, [_vp, _vp]),
+    "pfbg_split_status": (C.c_int, [_vp, _vp, C.POINTER(_i32)]),
+    "pfbg_split_end": (C.c_int, [_vp]),
+    "pfbg_plan_get_window": (C.c_int, [_vp, _vp]),
     # include/pfbsara.h
     "pfbs_psi_create": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _i32, _i32, C.POINTER(_vp)]),

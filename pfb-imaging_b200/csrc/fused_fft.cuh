@@ -26,6 +26,10 @@ struct FusedTabs {
   const double* nutab;       // (nx,ny) fp64: n - 1 + nshift per pixel (w-screen phase = w_p * nutab, up to 1e3 turns)
   // cells any bound sample can touch: rows [a_lo, a_lo+a_len) and columns [b_lo, b_lo+b_len), circular
   int a_lo, a_len, b_lo, b_len;
+  // plane subset of a launch: CTA plane index + q0 is the logical plane (w_q = w0 + q dw).  Launches over a subset
+  // (band split across GPUs: the owner transforms planes [0, P - nq), a helper GPU the last nq) pass plane-stack
+  // pointers biased so that logical plane q sits at `grid + q * nu * nv` whatever slot it is stored in.
+  int q0;
 };
 
 __device__ __forceinline__ bool in_window(int n, int lo, int len, int size) {
@@ -99,7 +103,7 @@ k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict
            typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x, q = blockIdx.x, i = blockIdx.y;
+  const int tid = threadIdx.x, nthr = blockDim.x, q = blockIdx.x + ft.q0, i = blockIdx.y;
   const int nv = p.nv, hy = p.ny / 2;
   const int ip = i - p.nx / 2;
   const int a = ip < 0 ? ip + p.nu : ip;
@@ -184,14 +188,17 @@ k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict
 // column block of C columns starting at b0; rows of the image band only are read
 template <typename T, int C>
 __global__ void __launch_bounds__(512)
-k_cols_fwd(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid) {
+k_cols_fwd(GParams p, FusedTabs ft, const typename cplx_of<T>::type* grid, typename cplx_of<T>::type* grid_out) {
+  // grid_out == grid for the in-place transform of a local stack; a helper GPU of a split band passes the
+  // owner's peer-mapped stack: the transformed columns then go straight over NVLink (posted stores)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
   constexpr int LGC = C == 1 ? 0 : (C == 2 ? 1 : 2);
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int b0 = (ft.b_lo + blockIdx.x * C) % p.nv, q = blockIdx.y;
+  const int b0 = (ft.b_lo + blockIdx.x * C) % p.nv, q = blockIdx.y + ft.q0;
   const int nu = p.nu, nx = p.nx, hx = p.nx / 2;
-  cx2<T>* g = reinterpret_cast<cx2<T>*>(grid) + (int64_t)q * nu * p.nv + b0;
+  const cx2<T>* g = reinterpret_cast<const cx2<T>*>(grid) + (int64_t)q * nu * p.nv + b0;
+  cx2<T>* go = reinterpret_cast<cx2<T>*>(grid_out) + (int64_t)q * nu * p.nv + b0;
   for (int w = tid; w < (nu - nx) * C; w += nthr) s[fft_pad<T>(hx * C + w)] = {(T)0, (T)0};
   const int nin = nx * C;
   for (int w0 = tid; w0 < nin; w0 += COLS_U * nthr) {
@@ -236,7 +243,7 @@ k_cols_fwd(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
         const int c = w & (C - 1);
         int k = ft.a_lo + (w >> LGC);
         if (k >= nu) k -= nu;
-        g[(int64_t)k * p.nv + c] = s[fft_pad<T>(pos[u] * C + c)];
+        go[(int64_t)k * p.nv + c] = s[fft_pad<T>(pos[u] * C + c)];
       }
     }
   }
@@ -245,14 +252,17 @@ k_cols_fwd(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
 // --------------------------------------------------------------------------- grid direction
 template <typename T, int C>
 __global__ void __launch_bounds__(512)
-k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid) {
+k_cols_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* grid, typename cplx_of<T>::type* grid_out) {
+  // grid may be the peer-mapped stack of the band's owner (helper GPU of a split band: the gridded columns are
+  // read over NVLink, COLS_U loads in flight per thread), grid_out the local stack
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
   constexpr int LGC = C == 1 ? 0 : (C == 2 ? 1 : 2);
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int b0 = (ft.b_lo + blockIdx.x * C) % p.nv, q = blockIdx.y;
+  const int b0 = (ft.b_lo + blockIdx.x * C) % p.nv, q = blockIdx.y + ft.q0;
   const int nu = p.nu, nx = p.nx, hx = p.nx / 2;
-  cx2<T>* g = reinterpret_cast<cx2<T>*>(grid) + (int64_t)q * nu * p.nv + b0;
+  const cx2<T>* g = reinterpret_cast<const cx2<T>*>(grid) + (int64_t)q * nu * p.nv + b0;
+  cx2<T>* go = reinterpret_cast<cx2<T>*>(grid_out) + (int64_t)q * nu * p.nv + b0;
   // rows outside the active window are known to be zero
   for (int w = tid; w < (nu - ft.a_len) * C; w += nthr) {
     int k = ft.a_lo + ft.a_len + (w >> LGC);
@@ -302,7 +312,7 @@ k_cols_inv(GParams p, FusedTabs ft, typename cplx_of<T>::type* __restrict__ grid
         const int k = r < hx ? r : r + (nu - nx);
         cx2<T> v = s[fft_pad<T>(pos[u] * C + c)];
         v.y = -v.y;
-        g[(int64_t)k * p.nv + c] = v;
+        go[(int64_t)k * p.nv + c] = v;
       }
     }
   }
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 2))
 k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict__ grid, double* __restrict__ accimg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);
-  const int tid = threadIdx.x, nthr = blockDim.x, q = blockIdx.x, i = blockIdx.y;
+  const int tid = threadIdx.x, nthr = blockDim.x, q = blockIdx.x + ft.q0, i = blockIdx.y;
   const int nv = p.nv, hy = p.ny / 2;
   const int ip = i - p.nx / 2;
   const int a = ip < 0 ? ip + p.nu : ip;
@@ -395,14 +405,16 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
   }
 }
 
-// out = acc * corr [* beam] * inv_wsum [+ eta * xin]
+// out = (acc [+ acc2]) * corr [* beam] * inv_wsum [+ eta * xin]      (acc2: the planes a helper GPU transformed)
 template <typename T>
-__global__ void k_finish_image(int64_t npix, const double* __restrict__ acc, const T* __restrict__ corr,
-                               const T* __restrict__ beam, const T* __restrict__ xin, double inv_wsum, double eta,
-                               T* __restrict__ out) {
+__global__ void k_finish_image(int64_t npix, const double* __restrict__ acc, const double* __restrict__ acc2,
+                               const T* __restrict__ corr, const T* __restrict__ beam, const T* __restrict__ xin,
+                               double inv_wsum, double eta, T* __restrict__ out) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= npix) return;
-  double r = acc[k] * (double)corr[k];
+  double a = acc[k];
+  if (acc2) a += acc2[k];
+  double r = a * (double)corr[k];
   if (beam) r *= (double)beam[k];
   r *= inv_wsum;
   if (xin) r += eta * (double)xin[k];
@@ -449,4 +461,29 @@ __global__ void k_zero_window(C* __restrict__ grid, int nu, int nv, int a_lo, in
     if (b >= nv) b -= nv;
     row[b] = z;
   }
+}
+
+// ---- band split across GPUs: flags in peer-mapped memory order the kernels of the two processes ------------
+// (one thread each; the waiter polls its OWN memory, the signaller writes over NVLink after a system fence)
+__global__ void k_flag_signal(unsigned long long* flag, unsigned long long value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+__global__ void k_flag_wait(const unsigned long long* flag, unsigned long long want, unsigned long long timeout_ns,
+                            int* timed_out) {
+  unsigned long long t0, t, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= want) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) { *timed_out = 1; break; }  // never hang the GPU: the host reports the time-out
+    __nanosleep(256);
+  }
+}
+// xshare = x [* beam]: what the helper's row transforms start from
+template <typename T>
+__global__ void k_share_image(int64_t npix, const T* __restrict__ x, const T* __restrict__ beam, T* __restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < npix) out[k] = beam ? x[k] * beam[k] : x[k];
 }

@@ -302,6 +302,14 @@ __global__ void k_zero_vis(C* __restrict__ v, int64_t n) {
   if (k < n) { C z; z.x = 0; z.y = 0; v[k] = z; }
 }
 
+// zero the ACTIVE samples only (the wide degridding teams add their row partials atomically; with
+// PFBG_NO_MASK_ZERO the masked samples of the caller's array must stay as they are)
+template <typename C>
+__global__ void k_zero_active(C* __restrict__ v, const uint32_t* __restrict__ sorted_idx, int64_t nact) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nact) { C z; z.x = 0; z.y = 0; v[sorted_idx[k]] = z; }
+}
+
 template <typename T>
 __global__ void k_any_nonzero(const T* __restrict__ x, int64_t n, int* flag) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

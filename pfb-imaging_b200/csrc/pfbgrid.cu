@@ -5,6 +5,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <atomic>
+#include <mutex>
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
@@ -46,6 +47,32 @@ int pfbg_fail(int code, const char* fmt, ...) {
   return code;
 }
 void pfbg_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// Small device scratch blocks (256 B) for the scalar reductions of both translation units: a caller holds a block
+// for the duration of its call, so two host threads (or two streams driven from different threads) on one device
+// never share an accumulator; blocks are recycled, never freed while the process lives (no cudaMalloc / cudaFree
+// inside solver loops).
+static std::mutex g_scratch_mu;
+static std::vector<void*> g_scratch_free[64];
+void* pfbg_scratch_get(int device) {
+  if (device < 0 || device >= 64) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (!g_scratch_free[device].empty()) {
+      void* p = g_scratch_free[device].back();
+      g_scratch_free[device].pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, 256) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pfbg_scratch_put(int device, void* p) {
+  if (!p || device < 0 || device >= 64) return;
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  g_scratch_free[device].push_back(p);
+}
 
 #define CK(call)                                                                           \
   do {                                                                                     \
@@ -124,6 +151,16 @@ struct pfbg_plan {
   bool bound = false, has_mask = false, has_wgt = false;
   bool beam_on_device = false;  // img_beam holds the beam of the last host-pointer Hessian call
   size_t total_bytes = 0;
+  // band split across two GPUs (pfbg_split_*): the plane transforms of the last split_nq planes run on a helper
+  int split_role = 0;             // 0 none, 1 owner, 2 helper
+  int split_nq = 0;
+  int stack_planes = 0;           // planes the local stack holds (helper: split_nq)
+  DevBuf xshare, partial, mailbox, x_local;  // owner: xshare / partial / mailbox are exported; helper: mailbox, x_local
+  void* peer_grid = nullptr;      // helper: the owner's plane stack (peer-mapped)
+  void* peer_xshare = nullptr;    // helper: the owner's x [* beam]
+  void* peer_partial = nullptr;   // helper: the owner's fp64 partial image
+  unsigned long long* peer_mailbox = nullptr;  // the other side's flags
+  unsigned long long split_step = 0;
   // profiling
   bool profiling = false;
   cudaEvent_t ev[8]{};
@@ -166,6 +203,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx, &pl->srt_ka, &pl->srt_kb, &pl->srt_va, &pl->srt_vb, &pl->srt_tmp,
+                   &pl->xshare, &pl->partial, &pl->mailbox, &pl->x_local,
                    &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->pos_u, &pl->cellflags, &pl->accimg, &pl->nutab, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
@@ -182,7 +220,13 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
 template <typename T> static int fused_setup_t(pfbg_plan* pl);
 static int cufft_setup(pfbg_plan* pl);
 
+static int plan_create_impl(const pfbg_plan_desc* d, int stack_planes, pfbg_plan** out);
 extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
+  return plan_create_impl(d, d ? d->nplanes : 0, out);
+}
+
+// stack_planes < nplanes: a transform helper of a split band, which only stores the planes it transforms
+static int plan_create_impl(const pfbg_plan_desc* d, int stack_planes, pfbg_plan** out) {
   if (!d || !out) return fail(PFBG_ERR_ARG, "null argument");
   *out = nullptr;
   if (d->precision != PFBG_F32 && d->precision != PFBG_F64) return fail(PFBG_ERR_ARG, "bad precision");
@@ -226,7 +270,8 @@ extern "C" int pfbg_plan_create(const pfbg_plan_desc* d, pfbg_plan** out) {
   const size_t rb = real_bytes(pl);
   int rc;
   if ((rc = dev_alloc(pl, pl->corr, (size_t)g.nx * g.ny * rb))) return bail(rc);
-  if ((rc = dev_alloc(pl, pl->grid, (size_t)g.nplanes * g.nu * g.nv * 2 * rb))) return bail(rc);
+  pl->stack_planes = stack_planes;
+  if ((rc = dev_alloc(pl, pl->grid, (size_t)stack_planes * g.nu * g.nv * 2 * rb))) return bail(rc);
   if ((rc = dev_alloc(pl, pl->flag, 128))) return bail(rc);
 
   // correction image
@@ -380,6 +425,7 @@ static int fused_setup_t(pfbg_plan* pl) {
   ft.tw_u = pl->tw_u.p; ft.tw_v = pl->tw_v.p;
   ft.rev_u = (const int*)pl->rev_u.p; ft.rev_v = (const int*)pl->rev_v.p; ft.pos_v = (const int*)pl->pos_v.p; ft.pos_u = (const int*)pl->pos_u.p;
   ft.a_lo = 0; ft.a_len = g.nu; ft.b_lo = 0; ft.b_len = g.nv;
+  ft.q0 = 0;
   // opt in to large dynamic shared memory
   CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -463,7 +509,9 @@ extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes, i
   if (pmirror < 0 || pmirror > 32 || (pmirror > 0 && (nplanes < pmirror || w0 != 0.5 * g.dw)))
     return fail(PFBG_ERR_ARG, "mirror planes need 0 <= pmirror <= min(32, nplanes) and w0 == dw/2");
   CK(cudaSetDevice(pl->device));
+  if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split");
   const size_t need = (size_t)nplanes * g.nu * g.nv * 2 * real_bytes(pl);
+  pl->stack_planes = nplanes;
   if (need > pl->grid.bytes) {
     CK(cudaDeviceSynchronize());
     CKRC(dev_alloc(pl, pl->grid, need));
@@ -489,6 +537,12 @@ extern "C" int pfbg_plan_get_info(const pfbg_plan* pl, pfbg_plan_info* info) {
   info->nchan = pl->gp.nchan; info->nplanes = pl->gp.nplanes;
   info->nu = pl->gp.nu; info->nv = pl->gp.nv; info->W = pl->gp.W;
   info->n_work_items = 0;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_plan_get_window(const pfbg_plan* pl, int32_t* w) {
+  if (!pl || !w) return fail(PFBG_ERR_ARG, "null argument");
+  w[0] = pl->ftabs.a_lo; w[1] = pl->ftabs.a_len; w[2] = pl->ftabs.b_lo; w[3] = pl->ftabs.b_len;
   return PFBG_OK;
 }
 
@@ -547,6 +601,50 @@ static void par_memcpy(void* dst, const void* src, size_t n) {
     th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
   }
   for (auto& t : th) t.join();
+}
+
+// 64-bit content hash of a host range on several threads (memory-bandwidth bound: ~150 MB in a few ms).  The
+// operator-level plan cache keys a bound band on the CONTENT of the caller's uvw / mask / weight / beam arrays
+// with it: a single flipped flag or re-weighted sample changes the hash (a sampled checksum would miss it).
+static inline uint64_t mix64(uint64_t h, uint64_t w) {
+  h ^= w;
+  h *= 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+static uint64_t hash_range(const unsigned char* p, size_t n, uint64_t seed) {
+  uint64_t h[4] = {seed ^ 0x243F6A8885A308D3ull, seed ^ 0x13198A2E03707344ull, seed ^ 0xA4093822299F31D0ull, seed ^ 0x082EFA98EC4E6C89ull};
+  size_t i = 0;
+  for (; i + 32 <= n; i += 32) {  // four independent lanes: the multiplies overlap
+    uint64_t w[4];
+    memcpy(w, p + i, 32);
+    h[0] = mix64(h[0], w[0]); h[1] = mix64(h[1], w[1]); h[2] = mix64(h[2], w[2]); h[3] = mix64(h[3], w[3]);
+  }
+  uint64_t tail = 0;
+  if (i < n) memcpy(&tail, p + i, n - i > 8 ? 8 : n - i);
+  for (size_t k = i + 8; k < n; ++k) tail = mix64(tail, p[k]);
+  uint64_t r = mix64(mix64(mix64(mix64(h[0], h[1]), h[2]), h[3]), tail);
+  return mix64(r, (uint64_t)n);
+}
+extern "C" int pfbg_host_hash64(const void* ptr, uint64_t bytes, uint64_t* out) {
+  if (!out || (!ptr && bytes)) return fail(PFBG_ERR_ARG, "null argument");
+  const unsigned char* p = (const unsigned char*)ptr;
+  const size_t n = (size_t)bytes;
+  const int nt = n < ((size_t)4 << 20) ? 1 : host_threads();
+  if (nt == 1) { *out = hash_range(p, n, 0); return PFBG_OK; }
+  std::vector<uint64_t> part(nt, 0);
+  std::vector<std::thread> th;
+  const size_t per = ((n / nt) + 63) & ~(size_t)63;
+  for (int t = 0; t < nt; ++t) {
+    const size_t off = (size_t)t * per;
+    if (off >= n) break;
+    const size_t len = off + per > n ? n - off : per;
+    th.emplace_back([=, &part] { part[t] = hash_range(p + off, len, (uint64_t)t + 1); });
+  }
+  for (auto& t : th) t.join();
+  uint64_t r = 0x6A09E667F3BCC908ull;
+  for (int t = 0; t < nt; ++t) r = mix64(r, part[t]);
+  *out = r;
+  return PFBG_OK;
 }
 
 static int pinned(void*& p, size_t& have, size_t need) {
@@ -911,7 +1009,11 @@ static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_
   if (pl->nactive > 0 && pl->use_runs && pl->gp.W > 8) {
     // the R warps of a team add their row-partials atomically: start from zero
     if (out_sorted) CK(cudaMemsetAsync(out_sorted, 0, (size_t)pl->nactive * sizeof(C), s));
-    else if (!pl->has_mask || (vis_zeroed == 0)) CK(cudaMemsetAsync(vis_out, 0, (size_t)pl->nvis * sizeof(C), s));
+    else if (!pl->has_mask) CK(cudaMemsetAsync(vis_out, 0, (size_t)pl->nvis * sizeof(C), s));
+    else if (vis_zeroed == 0) {  // PFBG_NO_MASK_ZERO: masked samples stay untouched, only the active ones start from zero
+      k_zero_active<C><<<(unsigned)((pl->nactive + 255) / 256), 256, 0, s>>>((C*)vis_out, (const uint32_t*)pl->sorted_idx.p, pl->nactive);
+      LAUNCHED();
+    }
     unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 32);  // one slice counter per row group (<= 8)
     CK(cudaMemsetAsync(queue, 0, 64, s));
     const size_t psm = (size_t)WIDE_WARPS * 16 * 32 * sizeof(C);  // per-sample lane partials (see k_degrid_runs_wide)
@@ -985,56 +1087,88 @@ static int row_threads(int n, int cap) {
   return best;
 }
 
+// Plane subset of the fused transforms: logical planes [q0, q0 + nq).  `stack` is the local plane stack biased so
+// that logical plane q sits at stack + q * nu * nv (a helper of a split band stores plane q0 in slot 0); `remote`
+// (optional) is the peer-mapped stack of the band's owner: the forward column pass then writes there and the
+// inverse column pass reads from there — the transfer over NVLink is fused into the transform kernels.
 template <typename T>
-static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam) {
+static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam, int q0 = 0, int nq = -1,
+                         void* remote = nullptr) {
   using C = typename cplx_of<T>::type;
   const int CC = pl->col_c;
   const GParams& g = pl->gp;
-  const FusedTabs& ft = pl->ftabs;
+  if (nq < 0) nq = g.nplanes - (pl->split_role == 1 ? pl->split_nq : 0);
+  if (nq == 0) return PFBG_OK;
+  FusedTabs ft = pl->ftabs;
+  ft.q0 = q0;
+  const int slot0 = pl->split_role == 2 ? g.nplanes - pl->split_nq : 0;  // logical plane held by slot 0
+  C* stack = (C*)pl->grid.p - (int64_t)slot0 * g.nu * g.nv;
   auto k_rows = &k_rows_fwd<T, false>;
   if constexpr (sizeof(T) == 4) {
     if (g.fast_screen) k_rows = &k_rows_fwd<T, true>;
   }
-  k_rows<<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
-      g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, (C*)pl->grid.p);
+  k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+      g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, stack);
   LAUNCHED();
   CK(cudaGetLastError());
-  const dim3 cgrid(ft.b_len / CC, g.nplanes);
+  const dim3 cgrid(ft.b_len / CC, nq);
   const size_t csm = fft_smem_bytes<T>(g.nu * CC);
-  if (CC == 4) k_cols_fwd<T, 4><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
-  else if (CC == 2) k_cols_fwd<T, 2><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
-  else k_cols_fwd<T, 1><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
+  C* dst = remote ? (C*)remote : stack;
+  if (CC == 4) k_cols_fwd<T, 4><<<cgrid, 512, csm, s>>>(g, ft, stack, dst);
+  else if (CC == 2) k_cols_fwd<T, 2><<<cgrid, 512, csm, s>>>(g, ft, stack, dst);
+  else k_cols_fwd<T, 1><<<cgrid, 512, csm, s>>>(g, ft, stack, dst);
   LAUNCHED();
   CK(cudaGetLastError());
   return PFBG_OK;
 }
 
+// inverse transforms of planes [q0, q0 + nq) accumulated into accimg (zeroed first)
 template <typename T>
-static int run_fused_inv(pfbg_plan* pl, cudaStream_t s, const void* beam, const void* xin, double inv_wsum, double eta,
-                         void* out) {
+static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, const void* remote) {
   using C = typename cplx_of<T>::type;
   const int CC = pl->col_c;
   const GParams& g = pl->gp;
-  const FusedTabs& ft = pl->ftabs;
-  const dim3 cgrid(ft.b_len / CC, g.nplanes);
-  const size_t csm = fft_smem_bytes<T>(g.nu * CC);
-  if (CC == 4) k_cols_inv<T, 4><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
-  else if (CC == 2) k_cols_inv<T, 2><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
-  else k_cols_inv<T, 1><<<cgrid, 512, csm, s>>>(g, ft, (C*)pl->grid.p);
-  LAUNCHED();
-  CK(cudaGetLastError());
+  FusedTabs ft = pl->ftabs;
+  ft.q0 = q0;
+  const int slot0 = pl->split_role == 2 ? g.nplanes - pl->split_nq : 0;
+  C* stack = (C*)pl->grid.p - (int64_t)slot0 * g.nu * g.nv;
   const int64_t npix = (int64_t)g.nx * g.ny;
   CK(cudaMemsetAsync(pl->accimg.p, 0, (size_t)npix * sizeof(double), s));
+  if (nq == 0) return PFBG_OK;
+  const dim3 cgrid(ft.b_len / CC, nq);
+  const size_t csm = fft_smem_bytes<T>(g.nu * CC);
+  const C* src = remote ? (const C*)remote : stack;
+  if (CC == 4) k_cols_inv<T, 4><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
+  else if (CC == 2) k_cols_inv<T, 2><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
+  else k_cols_inv<T, 1><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
+  LAUNCHED();
+  CK(cudaGetLastError());
   auto k_rows = &k_rows_inv<T, false>;
   if constexpr (sizeof(T) == 4) {
     if (g.fast_screen) k_rows = &k_rows_inv<T, true>;
   }
-  k_rows<<<dim3(g.nplanes, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
-      g, ft, (const C*)pl->grid.p, (double*)pl->accimg.p);
+  k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+      g, ft, stack, (double*)pl->accimg.p);
   LAUNCHED();
   CK(cudaGetLastError());
-  k_finish_image<T><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(npix, (const double*)pl->accimg.p, (const T*)pl->corr.p,
-                                                                (const T*)beam, (const T*)xin, inv_wsum, eta, (T*)out);
+  return PFBG_OK;
+}
+
+static int split_wait(pfbg_plan* pl, cudaStream_t s, int slot);
+static int split_signal(pfbg_plan* pl, cudaStream_t s, int slot);
+
+template <typename T>
+static int run_fused_inv(pfbg_plan* pl, cudaStream_t s, const void* beam, const void* xin, double inv_wsum, double eta,
+                         void* out) {
+  const GParams& g = pl->gp;
+  const bool owner = pl->split_role == 1;
+  CKRC(run_fused_inv_acc<T>(pl, s, 0, g.nplanes - (owner ? pl->split_nq : 0), nullptr));
+  const int64_t npix = (int64_t)g.nx * g.ny;
+  if (owner) CKRC(split_wait(pl, s, 1));  // the helper's partial image (its planes) has arrived
+  k_finish_image<T><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(npix, (const double*)pl->accimg.p,
+                                                                owner ? (const double*)pl->partial.p : nullptr,
+                                                                (const T*)pl->corr.p, (const T*)beam, (const T*)xin,
+                                                                inv_wsum, eta, (T*)out);
   LAUNCHED();
   CK(cudaGetLastError());
   return PFBG_OK;
@@ -1078,6 +1212,7 @@ static int zero_planes(pfbg_plan* pl, cudaStream_t s) {
 extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t vis_cs, const void* wgt,
                          void* dirty, uint32_t flags, void* stream) {
   if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
+  if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split: only pfbg_hessian / pfbg_split_helper_serve");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
   if (!vis && pl->nvis > 0) return fail(PFBG_ERR_ARG, "null vis");
   CK(cudaSetDevice(pl->device));
@@ -1113,6 +1248,7 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
 extern "C" int pfbg_grid_psf(pfbg_plan* pl, double x0, double y0, double sign, const void* wgt, void* dirty,
                              uint32_t flags, void* stream) {
   if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
+  if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split: only pfbg_hessian / pfbg_split_helper_serve");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
   if (x0 * x0 + y0 * y0 >= 1.0) return fail(PFBG_ERR_ARG, "phase centre outside the unit sphere");
   CK(cudaSetDevice(pl->device));
@@ -1151,6 +1287,7 @@ extern "C" int pfbg_grid_psf(pfbg_plan* pl, double x0, double y0, double sign, c
 extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const void* wgt, uint32_t flags,
                            void* stream) {
   if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
+  if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split: only pfbg_hessian / pfbg_split_helper_serve");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
   if (!vis && pl->nvis > 0) return fail(PFBG_ERR_ARG, "null vis");
   CK(cudaSetDevice(pl->device));
@@ -1173,7 +1310,12 @@ extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const vo
   CKRC(image_to_planes(pl, s, dimg, nullptr));
   mark(pl, s);
   void* dvis = vis;
-  if (!dev && pl->nvis > 0) { CKRC(dev_alloc(pl, pl->vis_stage, vis_bytes)); dvis = pl->vis_stage.p; }
+  if (!dev && pl->nvis > 0) {
+    CKRC(dev_alloc(pl, pl->vis_stage, vis_bytes));
+    dvis = pl->vis_stage.p;
+    // PFBG_NO_MASK_ZERO with host pointers: the masked samples of the caller's array make the round trip unchanged
+    if (pl->has_mask && (flags & PFBG_NO_MASK_ZERO)) CKRC(h2d_staged(pl, dvis, vis, vis_bytes, s));
+  }
   if (pl->nvis > 0) {
     const int zeroed = (pl->has_mask && !(flags & PFBG_NO_MASK_ZERO)) ? 1 : 0;
     if (zeroed) CK(cudaMemsetAsync(dvis, 0, vis_bytes, s));
@@ -1189,6 +1331,8 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
                             uint32_t flags, void* stream) {
   if (!pl || !x || !out) return fail(PFBG_ERR_ARG, "null argument");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (pl->split_role == 2) return fail(PFBG_ERR_STATE, "split helper plans only serve (pfbg_split_helper_serve)");
+  if (pl->split_role == 1 && !(flags & PFBG_DEVICE_PTRS)) return fail(PFBG_ERR_STATE, "split plans take device pointers");
   CK(cudaSetDevice(pl->device));
   cudaStream_t s = (cudaStream_t)stream;
   const bool dev = flags & PFBG_DEVICE_PTRS;
@@ -1226,9 +1370,21 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
       return PFBG_OK;
     }
   }
+  const bool owner = pl->split_role == 1;
+  if (owner) {  // publish x [* beam] to the helper GPU that transforms the last split_nq planes
+    const int64_t npix = (int64_t)pl->gp.nx * pl->gp.ny;
+    ++pl->split_step;
+    if (pl->precision == PFBG_F32)
+      k_share_image<float><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(npix, (const float*)dx, (const float*)dbeam, (float*)pl->xshare.p);
+    else
+      k_share_image<double><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(npix, (const double*)dx, (const double*)dbeam, (double*)pl->xshare.p);
+    LAUNCHED();
+    CKRC(split_signal(pl, s, 0));  // X_READY
+  }
   mark(pl, s);
   // R (beam * x): pad + screen, FFT, gather (phase factors cancel against the adjoint)
   CKRC(image_to_planes(pl, s, dx, dbeam));
+  if (owner) CKRC(split_wait(pl, s, 0));  // FWD_ARRIVED: the helper's planes are in the stack
   mark(pl, s);
   CKRC(DISPATCH(run_gather, pl, s, nullptr, nullptr, pl->mvis.p, 0));
   mark(pl, s);
@@ -1236,6 +1392,7 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   CKRC(zero_planes(pl, s));
   mark(pl, s);
   CKRC(DISPATCH(run_spread, pl, s, pl->mvis.p, 0, 0, dwgt, 1, 0));
+  if (owner) CKRC(split_signal(pl, s, 1));  // GRID_DONE: the helper may fetch its planes
   mark(pl, s);
   void* dout = out;
   if (!dev) { CKRC(dev_alloc(pl, pl->img_out, img_bytes)); dout = pl->img_out.p; }
@@ -1246,6 +1403,282 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
     CK(cudaStreamSynchronize(s));
   } else if (!dev) CKRC(d2h_staged(pl, out, dout, img_bytes, s));
   mark(pl, s);
+  return PFBG_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Band split across two GPUs (one process per GPU; SURVEY §8e, BASELINE north_star "bands are partitioned across
+// the 8 GPUs"): when a job has as many bands as GPUs the heaviest band bounds the step (band 7 of C2 costs 1.7x
+// band 0: more w-planes, a larger active uv window).  The plane transforms are the divisible half of a Hessian
+// apply, so the owner of a heavy band hands the LAST nq planes to a helper GPU:
+//   forward : helper reads x [* beam] from the owner, runs k_rows_fwd + k_cols_fwd on its planes; the column pass
+//             stores the transformed columns straight into the owner's plane stack (peer-mapped, NVLink);
+//   inverse : the helper's k_cols_inv loads the gridded columns of its planes from the owner's stack over NVLink,
+//             k_rows_inv accumulates them into a local fp64 image, which one peer copy hands to the owner, whose
+//             epilogue adds it to its own accumulator.
+// The two processes never talk on the host after set-up: four flags in device memory (each polled by its owner,
+// written by the peer after a system-scope fence) order the kernels of the two streams.
+//   helper mailbox: [0] X_READY (owner -> helper), [1] GRID_DONE;  owner mailbox: [0] FWD_ARRIVED, [1] PARTIAL_ARRIVED
+// Buffers cross the process boundary as CUDA IPC handles (pfbg_ipc_blob); within one process (tests) the raw
+// pointer is used.
+// ---------------------------------------------------------------------------
+#include <unistd.h>
+#include <map>
+#include <mutex>
+
+struct IpcBlob {
+  cudaIpcMemHandle_t h;   // 64 bytes
+  uint64_t offset;        // of the pointer inside the allocation the handle names
+  uint64_t raw;           // the pointer itself (valid inside the exporting process)
+  int64_t pid;
+  int32_t device;
+  int32_t pad;
+};
+static_assert(sizeof(IpcBlob) == PFBG_IPC_BLOB_BYTES, "pfbg_ipc_blob size");
+
+static std::mutex g_ipc_mu;
+static std::map<std::string, void*> g_ipc_open;  // handle bytes -> mapped base (a handle opens once per process)
+
+static int ipc_export(const void* ptr, IpcBlob* b) {
+  memset(b, 0, sizeof *b);
+  // cudaMalloc may carve small allocations out of a larger block: the handle names the block
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn get_range = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return (range_fn)f;
+  }();
+  unsigned long long base = (unsigned long long)(uintptr_t)ptr;
+  size_t size = 0;
+  if (get_range && get_range(&base, &size, (unsigned long long)(uintptr_t)ptr) != 0) base = (unsigned long long)(uintptr_t)ptr;
+  CK(cudaIpcGetMemHandle(&b->h, (void*)(uintptr_t)base));
+  b->offset = (uint64_t)((uintptr_t)ptr - (uintptr_t)base);
+  b->raw = (uint64_t)(uintptr_t)ptr;
+  b->pid = (int64_t)getpid();
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  b->device = dev;
+  return PFBG_OK;
+}
+
+static int ipc_open(const IpcBlob* b, int my_device, void** out) {
+  *out = nullptr;
+  if (b->pid == (int64_t)getpid()) {  // same process: the pointer is valid as it is
+    if (b->device != my_device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, my_device, b->device));
+      if (!can) return fail(PFBG_ERR_STATE, "device %d cannot access device %d", my_device, b->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(PFBG_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    *out = (void*)(uintptr_t)b->raw;
+    return PFBG_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  const std::string key((const char*)&b->h, sizeof b->h);
+  auto it = g_ipc_open.find(key);
+  void* base = nullptr;
+  if (it != g_ipc_open.end()) base = it->second;
+  else {
+    cudaError_t e = cudaIpcOpenMemHandle(&base, b->h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PFBG_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e)); }
+    g_ipc_open[key] = base;
+  }
+  *out = (char*)base + b->offset;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_ipc_export(const void* dev_ptr, pfbg_ipc_blob* blob) {
+  if (!dev_ptr || !blob) return fail(PFBG_ERR_ARG, "null argument");
+  return ipc_export(dev_ptr, (IpcBlob*)blob);
+}
+extern "C" int pfbg_ipc_open(int32_t device, const pfbg_ipc_blob* blob, void** dev_ptr) {
+  if (!blob || !dev_ptr) return fail(PFBG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(device));
+  return ipc_open((const IpcBlob*)blob, device, dev_ptr);
+}
+extern "C" int pfbg_ipc_close_all(void) {
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  for (auto& kv : g_ipc_open) cudaIpcCloseMemHandle(kv.second);
+  g_ipc_open.clear();
+  cudaGetLastError();
+  return PFBG_OK;
+}
+
+static const size_t kMailboxBytes = (size_t)2 << 20;  // its own allocation block
+static const unsigned long long kSplitTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+// CUDA loads kernels lazily and the first launch of a kernel synchronises the context: a launch issued while a flag
+// wait spins on the same device would not start before the wait gives up.  Every kernel a split apply uses is
+// therefore launched once at set-up, before any wait can spin.
+static int split_warm_flags(pfbg_plan* pl) {
+  unsigned long long* scratch = (unsigned long long*)pl->mailbox.p + 32;  // beyond the live slots and the time-out word
+  k_flag_signal<<<1, 1>>>(scratch, 0ull);
+  k_flag_wait<<<1, 1>>>(scratch, 0ull, 1000ull, (int*)(scratch + 1));
+  if (pl->precision == PFBG_F32) k_share_image<float><<<1, 32>>>(0, nullptr, nullptr, nullptr);
+  else k_share_image<double><<<1, 32>>>(0, nullptr, nullptr, nullptr);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return PFBG_OK;
+}
+
+static int split_signal(pfbg_plan* pl, cudaStream_t s, int slot) {
+  k_flag_signal<<<1, 1, 0, s>>>(pl->peer_mailbox + slot, pl->split_step);
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+static int split_wait(pfbg_plan* pl, cudaStream_t s, int slot) {
+  k_flag_wait<<<1, 1, 0, s>>>((const unsigned long long*)pl->mailbox.p + slot, pl->split_step, kSplitTimeoutNs,
+                              (int*)((char*)pl->mailbox.p + 64));
+  LAUNCHED();
+  CK(cudaGetLastError());
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_split_owner_init(pfbg_plan* pl, int32_t nq, pfbg_ipc_blob* blobs4) {
+  if (!pl || !blobs4) return fail(PFBG_ERR_ARG, "null argument");
+  if (!pl->fused) return fail(PFBG_ERR_STATE, "band split needs the fused plane transforms");
+  if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is already part of a band split");
+  if (nq < 1 || nq >= pl->gp.nplanes) return fail(PFBG_ERR_ARG, "nq=%d outside [1, nplanes)", nq);
+  CK(cudaSetDevice(pl->device));
+  const size_t npix = (size_t)pl->gp.nx * pl->gp.ny;
+  CKRC(dev_alloc(pl, pl->xshare, npix * real_bytes(pl)));
+  CKRC(dev_alloc(pl, pl->partial, npix * sizeof(double)));
+  CKRC(dev_alloc(pl, pl->mailbox, kMailboxBytes));
+  CK(cudaMemset(pl->mailbox.p, 0, 4096));
+  CK(cudaMemset(pl->partial.p, 0, npix * sizeof(double)));
+  IpcBlob* b = (IpcBlob*)blobs4;
+  CKRC(ipc_export(pl->grid.p, &b[0]));
+  CKRC(ipc_export(pl->xshare.p, &b[1]));
+  CKRC(ipc_export(pl->partial.p, &b[2]));
+  CKRC(ipc_export(pl->mailbox.p, &b[3]));
+  pl->split_nq = nq;
+  pl->split_step = 0;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_split_owner_connect(pfbg_plan* pl, const pfbg_ipc_blob* helper_mailbox) {
+  if (!pl || !helper_mailbox) return fail(PFBG_ERR_ARG, "null argument");
+  if (pl->split_nq < 1 || pl->split_role) return fail(PFBG_ERR_STATE, "pfbg_split_owner_init first");
+  CK(cudaSetDevice(pl->device));
+  void* p = nullptr;
+  CKRC(ipc_open((const IpcBlob*)helper_mailbox, pl->device, &p));
+  pl->peer_mailbox = (unsigned long long*)p;
+  CKRC(split_warm_flags(pl));
+  if (pl->bound) {  // one whole (unsplit) apply on the shared image: loads every kernel of the path
+    CK(cudaMemset(pl->xshare.p, 0, (size_t)pl->gp.nx * pl->gp.ny * real_bytes(pl)));
+    CKRC(pfbg_hessian(pl, pl->xshare.p, nullptr, 0.0, 0.0, pl->xshare.p, PFBG_DEVICE_PTRS, nullptr));
+    CK(cudaDeviceSynchronize());
+  }
+  pl->split_role = 1;
+  return PFBG_OK;
+}
+
+extern "C" int pfbg_split_helper_create(const pfbg_plan_desc* d, int32_t nq, const int32_t* window4,
+                                        const pfbg_ipc_blob* owner_blobs4, pfbg_plan** out,
+                                        pfbg_ipc_blob* mailbox_out) {
+  if (!d || !window4 || !owner_blobs4 || !out || !mailbox_out) return fail(PFBG_ERR_ARG, "null argument");
+  if (nq < 1 || nq >= d->nplanes) return fail(PFBG_ERR_ARG, "nq=%d outside [1, nplanes)", nq);
+  pfbg_plan* pl = nullptr;
+  CKRC(plan_create_impl(d, nq, &pl));
+  auto bail = [&](int rc) { pfbg_plan_destroy(pl); return rc; };
+  if (!pl->fused) { fail(PFBG_ERR_STATE, "band split needs the fused plane transforms"); return bail(PFBG_ERR_STATE); }
+  FusedTabs& ft = pl->ftabs;
+  ft.a_lo = window4[0]; ft.a_len = window4[1]; ft.b_lo = window4[2]; ft.b_len = window4[3];
+  if (ft.a_lo < 0 || ft.a_len < 1 || ft.a_lo + 0 >= pl->gp.nu || ft.a_len > pl->gp.nu || ft.b_lo < 0 || ft.b_len < 1 ||
+      ft.b_lo >= pl->gp.nv || ft.b_len > pl->gp.nv || (ft.b_len % pl->col_c)) {
+    fail(PFBG_ERR_ARG, "bad active window");
+    return bail(PFBG_ERR_ARG);
+  }
+  int rc;
+  const size_t npix = (size_t)pl->gp.nx * pl->gp.ny;
+  if ((rc = dev_alloc(pl, pl->x_local, npix * real_bytes(pl))) || (rc = dev_alloc(pl, pl->mailbox, kMailboxBytes))) return bail(rc);
+  if (cudaMemset(pl->mailbox.p, 0, 4096) != cudaSuccess) { fail(PFBG_ERR_CUDA, "memset failed"); return bail(PFBG_ERR_CUDA); }
+  const IpcBlob* b = (const IpcBlob*)owner_blobs4;
+  void* p[4] = {};
+  for (int i = 0; i < 4; ++i)
+    if ((rc = ipc_open(&b[i], pl->device, &p[i]))) return bail(rc);
+  pl->peer_grid = p[0]; pl->peer_xshare = p[1]; pl->peer_partial = p[2]; pl->peer_mailbox = (unsigned long long*)p[3];
+  if ((rc = ipc_export(pl->mailbox.p, (IpcBlob*)mailbox_out))) return bail(rc);
+  pl->split_role = 2;
+  pl->split_nq = nq;
+  pl->split_step = 0;
+  pl->bound = false;
+  // dry run on the local stack (see split_warm_flags): transforms of the helper's planes, the peer copy of the image
+  if ((rc = split_warm_flags(pl))) return bail(rc);
+  {
+    const int q0 = pl->gp.nplanes - nq;
+    cudaError_t e = cudaMemcpy(pl->x_local.p, pl->peer_xshare, npix * real_bytes(pl), cudaMemcpyDefault);
+    if (e != cudaSuccess) { fail(PFBG_ERR_CUDA, "peer copy from the owner failed: %s", cudaGetErrorString(e)); return bail(PFBG_ERR_CUDA); }
+    cudaMemset(pl->x_local.p, 0, npix * real_bytes(pl));
+    rc = pl->precision == PFBG_F32 ? run_fused_fwd<float>(pl, 0, pl->x_local.p, nullptr, q0, nq, nullptr)
+                                   : run_fused_fwd<double>(pl, 0, pl->x_local.p, nullptr, q0, nq, nullptr);
+    if (!rc) rc = pl->precision == PFBG_F32 ? run_fused_inv_acc<float>(pl, 0, q0, nq, nullptr)
+                                            : run_fused_inv_acc<double>(pl, 0, q0, nq, nullptr);
+    if (rc) return bail(rc);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { fail(PFBG_ERR_CUDA, "helper dry run failed: %s", cudaGetErrorString(e)); return bail(PFBG_ERR_CUDA); }
+  }
+  *out = pl;
+  return PFBG_OK;
+}
+
+// One Hessian apply worth of helper work, enqueued on `stream` (asynchronous; it waits on the owner's flags on the
+// device).  Must be called once per pfbg_hessian call of the owner, in the same order.
+extern "C" int pfbg_split_helper_serve(pfbg_plan* pl, void* stream) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  if (pl->split_role != 2) return fail(PFBG_ERR_STATE, "not a split helper");
+  CK(cudaSetDevice(pl->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const GParams& g = pl->gp;
+  const int nq = pl->split_nq, q0 = g.nplanes - nq;
+  const size_t npix = (size_t)g.nx * g.ny;
+  ++pl->split_step;
+  pl->n_ev = 0;
+  mark(pl, s);
+  CKRC(split_wait(pl, s, 0));  // X_READY
+  mark(pl, s);
+  CK(cudaMemcpyAsync(pl->x_local.p, pl->peer_xshare, npix * real_bytes(pl), cudaMemcpyDefault, s));
+  if (pl->precision == PFBG_F32) CKRC(run_fused_fwd<float>(pl, s, pl->x_local.p, nullptr, q0, nq, pl->peer_grid));
+  else CKRC(run_fused_fwd<double>(pl, s, pl->x_local.p, nullptr, q0, nq, pl->peer_grid));
+  CKRC(split_signal(pl, s, 0));  // FWD_ARRIVED
+  mark(pl, s);
+  CKRC(split_wait(pl, s, 1));  // GRID_DONE
+  mark(pl, s);
+  if (pl->precision == PFBG_F32) CKRC(run_fused_inv_acc<float>(pl, s, q0, nq, pl->peer_grid));
+  else CKRC(run_fused_inv_acc<double>(pl, s, q0, nq, pl->peer_grid));
+  CK(cudaMemcpyAsync(pl->peer_partial, pl->accimg.p, npix * sizeof(double), cudaMemcpyDefault, s));
+  CKRC(split_signal(pl, s, 1));  // PARTIAL_ARRIVED
+  mark(pl, s);
+  return PFBG_OK;
+}
+
+// Synchronises `stream` and reports whether any flag wait of this plan gave up (peer gone / calls out of step).
+extern "C" int pfbg_split_status(pfbg_plan* pl, void* stream, int32_t* timed_out) {
+  if (!pl || !timed_out) return fail(PFBG_ERR_ARG, "null argument");
+  *timed_out = 0;
+  if (!pl->split_role && pl->split_nq == 0) return PFBG_OK;
+  CK(cudaSetDevice(pl->device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  int t = 0;
+  CK(cudaMemcpy(&t, (char*)pl->mailbox.p + 64, 4, cudaMemcpyDeviceToHost));
+  *timed_out = t;
+  return PFBG_OK;
+}
+
+// Leave the split: the owner transforms all its planes again.  Both sides must be idle (synchronise first).
+extern "C" int pfbg_split_end(pfbg_plan* pl) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  CK(cudaSetDevice(pl->device));
+  CK(cudaDeviceSynchronize());
+  if (pl->split_role == 2) return fail(PFBG_ERR_STATE, "destroy a helper plan instead");
+  pl->split_role = 0;
+  pl->split_nq = 0;
+  pl->peer_mailbox = nullptr;
   return PFBG_OK;
 }
 
@@ -1417,12 +1850,13 @@ extern "C" int pfbg_l2_reweight(int32_t precision, int32_t device, const void* r
   if (wgtp) CKRC(t.get(&dp, wgtp, wbytes, dev, true, s));
   if (mask) CKRC(t.get(&dmask, mask, (size_t)nvis, dev, true, s));
   CKRC(t.get(&dwgt, wgt, wbytes, dev, true, s));
-  {  // 17 doubles of reduction scratch per (host thread, device), kept: no cudaMalloc / cudaFree per call
-    static thread_local void* scratch[64] = {};
-    if (device < 0 || device >= 64) return fail(PFBG_ERR_ARG, "bad device");
-    if (!scratch[device]) CK(cudaMalloc(&scratch[device], 17 * 8));
-    dsums = scratch[device];
-  }
+  // 17 doubles of reduction scratch, held for this call (pfbg_scratch_get: recycled blocks, no cudaMalloc per call)
+  struct Hold {
+    int dev; void* p;
+    ~Hold() { pfbg_scratch_put(dev, p); }
+  } hold{device, pfbg_scratch_get(device)};
+  if (!hold.p) return fail(PFBG_ERR_NOMEM, "no reduction scratch on device %d", device);
+  dsums = hold.p;
   CK(cudaMemsetAsync(dsums, 0, 17 * 8, s));
   dim3 rgrid(592, ncorr);
   if (nvis > 0) {

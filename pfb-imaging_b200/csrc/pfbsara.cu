@@ -343,18 +343,19 @@ extern "C" int pfbs_primal_step(int32_t precision, int32_t device, void* x, cons
   return PFBG_OK;
 }
 
-// two doubles of device scratch per device for the reductions (allocated once: no cudaMalloc / cudaFree, which
-// synchronises the device, inside the solver loops)
-static double* reduce_scratch(int device) {
-  static double* buf[64] = {nullptr};
-  if (device < 0 || device >= 64) return nullptr;
-  if (!buf[device] && cudaMalloc(&buf[device], 64) != cudaSuccess) { cudaGetLastError(); buf[device] = nullptr; }
-  return buf[device];
-}
+// two doubles of device scratch for the reductions, held for the duration of the call (pfbgrid.cu: recycled blocks,
+// one per concurrent caller, so host threads / streams on one device never share an accumulator; no cudaMalloc /
+// cudaFree, which synchronises the device, inside the solver loops)
+void* pfbg_scratch_get(int device);
+void pfbg_scratch_put(int device, void* p);
 
 template <typename K>
 static int reduce2(int device, cudaStream_t s, double* out2, K launch) {
-  double* acc = reduce_scratch(device);
+  struct Hold {
+    int dev; void* p;
+    ~Hold() { pfbg_scratch_put(dev, p); }
+  } hold{device, pfbg_scratch_get(device)};
+  double* acc = (double*)hold.p;
   if (!acc) return pfbg_fail(PFBG_ERR_NOMEM, "no reduction scratch on device %d", device);
   SCK(cudaMemsetAsync(acc, 0, 16, s));
   launch(acc);

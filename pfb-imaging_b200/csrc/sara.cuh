@@ -233,15 +233,16 @@ __global__ void k_axpby(T* out, T a, const T* x, T b, const T* y, int64_t n) {
   if (k < n) out[k] = a * x[k] + b * y[k];
 }
 
+// x, xp and xout may be one and the same array (ForwardBackward's in-place positivity pass calls this with
+// tau = 0): no __restrict__ here, and tau == 0 leaves xp untouched even where xout is inf / NaN
 template <typename T>
-__global__ void k_primal_step(T* __restrict__ x, const T* __restrict__ xp, const T* __restrict__ xout, T tau,
-                              int positivity, int nband, int64_t npix) {
+__global__ void k_primal_step(T* x, const T* xp, const T* xout, T tau, int positivity, int nband, int64_t npix) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= npix) return;
   bool kill = false;
   for (int b = 0; b < nband; ++b) {
     const int64_t o = (int64_t)b * npix + k;
-    T v = xp[o] - tau * xout[o];
+    T v = tau != (T)0 ? xp[o] - tau * xout[o] : xp[o];
     if (positivity == 1 && v < (T)0) v = 0;
     if (positivity == 2 && v <= (T)0) kill = true;
     x[o] = v;

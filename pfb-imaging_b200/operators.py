@@ -13,7 +13,11 @@ A small LRU of bound plans plays the role of the per-band pinned state of
 ``_BandWorkerImpl`` (operators/band_worker.py:61-106): repeated calls with the
 same ``uvw/freq/mask/weight`` arrays (pcg, power method) skip upload, binning
 and sort.  Entries hold references to the caller's arrays and re-validate a
-sampled checksum on every hit, so in-place edits are detected.
+64-bit hash of their FULL content on every hit (``pfbg_host_hash64``: threaded,
+a few ms per 100 MB), so any in-place edit — one more flagged sample, a
+re-weighted row — re-binds the band; the reference keeps no state between calls.
+``PFBG_CACHE_CHECK=sample`` restores the strided checksum of round 1 (~20 us;
+misses sparse edits) for callers that never edit their arrays in place.
 """
 
 from __future__ import annotations
@@ -53,12 +57,21 @@ def _sig(a):
     return (a.ctypes.data, a.shape, a.strides, a.dtype.str)
 
 
+_CACHE_CHECK = os.environ.get("PFBG_CACHE_CHECK", "full")
+
+
 def _sample(a):
+    """Content fingerprint of a caller array: full 64-bit hash (default) or the strided checksum."""
     if a is None:
-        return 0.0
-    f = np.asarray(a).reshape(-1) if np.asarray(a).flags.c_contiguous else np.asarray(a).ravel()
-    if f.size == 0:
-        return 0.0
+        return 0
+    a = np.asarray(a)
+    if a.size == 0:
+        return 0
+    if _CACHE_CHECK != "sample":
+        from .wgridder import content_hash
+
+        return content_hash(a)
+    f = a.reshape(-1) if a.flags.c_contiguous else a.ravel()
     step = max(1, f.size // 2048)
     s = f[::step]
     return float(np.abs(s).sum(dtype=np.float64)) + float(np.abs(f[-1])) * 3.0 + float(np.abs(f[0])) * 7.0

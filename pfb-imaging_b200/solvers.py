@@ -107,7 +107,9 @@ def pcg_device(apply_dev, b, x0=None, tol=1e-5, maxit=500, minit=100, verbosity=
     applies the operator to device arrays (e.g. ``GridderPlan.hessian_dev`` with the band's beam / wsum / eta bound);
     `b` / `x0` are numpy arrays, the solution comes back as numpy.  Per iteration: one operator apply, three axpby
     kernels and two fused dot-product kernels; ``eps = ||x - x_prev|| / ||x||`` is formed as ``|alpha| ||p|| / ||x||``
-    so no copy of the previous iterate is kept.  `reduce` sums the scalar pairs over ranks for band-sharded cubes."""
+    so no copy of the previous iterate is kept.  `reduce` sums the scalar pairs over ranks for band-sharded cubes.
+    Like the reference's solvers (``opt/pcg.py:106-112``) a given `x0` of the operator's dtype is bound as the
+    iterate: it receives the solution and IS the returned array."""
     import ctypes as C
 
     import torch
@@ -126,6 +128,13 @@ def pcg_device(apply_dev, b, x0=None, tol=1e-5, maxit=500, minit=100, verbosity=
     n = bt.numel()
     out2 = (C.c_double * 2)()
 
+    def result():
+        res = x.cpu().numpy()
+        if isinstance(x0, np.ndarray) and x0.dtype == rdt and x0.shape == res.shape and x0.flags.writeable:
+            x0[...] = res
+            return x0
+        return res
+
     def axpby(out, a, xx, bb, yy):
         _lib.check(lib.pfbs_axpby(prec, device, ptr(out), float(a), ptr(xx), float(bb), ptr(yy), n, s))
 
@@ -140,7 +149,7 @@ def pcg_device(apply_dev, b, x0=None, tol=1e-5, maxit=500, minit=100, verbosity=
     if not rho > 0.0:
         if verbosity:
             print("Initial residual is zero")
-        return x.cpu().numpy()
+        return result()
     axpby(p, -1.0, r, 0.0, r)           # p = -r
     phi0 = rho if np.isfinite(rho) else 1.0
     k, eps, stalls = 0, 1.0, 0
@@ -166,7 +175,7 @@ def pcg_device(apply_dev, b, x0=None, tol=1e-5, maxit=500, minit=100, verbosity=
             print(f"Stalled after {k} iterations with eps = {eps:.3e}")
         else:
             print(f"Success, converged after {k} iterations")
-    return x.cpu().numpy()
+    return result()
 
 
 def power_method_device(apply_dev, shape, dtype=np.float64, b0=None, tol=1e-5, maxit=250, verbosity=1, report_freq=25,

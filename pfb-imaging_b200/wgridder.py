@@ -26,10 +26,40 @@ def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+def content_hash(a) -> int:
+    """64-bit hash of the full content of a numpy array (threaded, in libpfbgrid.so; host memory only)."""
+    a = np.asarray(a)
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    h = C.c_uint64(0)
+    _lib.check(_lib.load().pfbg_host_hash64(C.c_void_p(a.ctypes.data), a.nbytes, C.byref(h)))
+    return int(h.value)
+
+
 def current_device() -> int:
     import os
 
     return int(os.environ.get("PFBG_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def _plan_desc(plan: Plan, device: int):
+    """The C struct of a host-side plan (+ the arrays it points to, which the caller keeps alive)."""
+    keep = (np.ascontiguousarray(plan.corr_u, dtype=np.float64),
+            np.ascontiguousarray(plan.corr_v, dtype=np.float64),
+            np.ascontiguousarray(plan.gl_x, dtype=np.float64),
+            np.ascontiguousarray(plan.gl_w, dtype=np.float64))
+    d = _lib.PlanDesc(
+        precision=_PREC[plan.precision], device=device, nx=plan.nx, ny=plan.ny, nu=plan.nu, nv=plan.nv,
+        W=plan.W, nplanes=plan.nplanes, do_wgridding=int(plan.do_wgridding), divide_by_n=int(plan.divide_by_n),
+        beta=plan.beta, pixsize_x=plan.pixsize_x, pixsize_y=plan.pixsize_y,
+        center_x=plan.center_x, center_y=plan.center_y, usign=plan.usign, vsign=plan.vsign, wsign=plan.wsign,
+        w0=plan.w0, dw=plan.dw, nshift=plan.nshift,
+        corr_u=keep[0].ctypes.data, corr_v=keep[1].ctypes.data,
+        gl_x=keep[2].ctypes.data, gl_w=keep[3].ctypes.data, n_gl=len(keep[2]),
+        pmirror=int(getattr(plan, "pmirror", 0)),
+        fast_screen=int(getattr(plan, "fast_screen", 0)),
+    )
+    return d, keep
 
 
 class GridderPlan:
@@ -41,21 +71,7 @@ class GridderPlan:
         self.device = current_device() if device is None else int(device)
         self._h = C.c_void_p()
         self._lib = _lib.load()
-        self._keep = (np.ascontiguousarray(plan.corr_u, dtype=np.float64),
-                      np.ascontiguousarray(plan.corr_v, dtype=np.float64),
-                      np.ascontiguousarray(plan.gl_x, dtype=np.float64),
-                      np.ascontiguousarray(plan.gl_w, dtype=np.float64))
-        d = _lib.PlanDesc(
-            precision=_PREC[plan.precision], device=self.device, nx=plan.nx, ny=plan.ny, nu=plan.nu, nv=plan.nv,
-            W=plan.W, nplanes=plan.nplanes, do_wgridding=int(plan.do_wgridding), divide_by_n=int(plan.divide_by_n),
-            beta=plan.beta, pixsize_x=plan.pixsize_x, pixsize_y=plan.pixsize_y,
-            center_x=plan.center_x, center_y=plan.center_y, usign=plan.usign, vsign=plan.vsign, wsign=plan.wsign,
-            w0=plan.w0, dw=plan.dw, nshift=plan.nshift,
-            corr_u=self._keep[0].ctypes.data, corr_v=self._keep[1].ctypes.data,
-            gl_x=self._keep[2].ctypes.data, gl_w=self._keep[3].ctypes.data, n_gl=len(self._keep[2]),
-            pmirror=int(getattr(plan, "pmirror", 0)),
-            fast_screen=int(getattr(plan, "fast_screen", 0)),
-        )
+        d, self._keep = _plan_desc(plan, self.device)
         _lib.check(self._lib.pfbg_plan_create(C.byref(d), C.byref(self._h)))
         self.nrow = self.nchan = 0
         self.rdt = _RDT[plan.precision]
@@ -211,9 +227,9 @@ class GridderPlan:
         tmp = res if res.flags.c_contiguous else np.empty(res.shape, res.dtype)
         flags = _lib.HOST_PTRS
         if beam is not None:
-            # the beam of a band never changes between applies: upload it once (address + size + a strided checksum
-            # identify it; PFBG_BEAM_CACHE=0 re-uploads every call)
-            fp = (beam.ctypes.data, beam.nbytes, float(beam.ravel()[:: max(1, beam.size // 509)].sum(dtype=np.float64)))
+            # the beam of a band never changes between applies: upload it once (address + size + a hash of its full
+            # content identify it, so an in-place patch of a few pixels is seen; PFBG_BEAM_CACHE=0 re-uploads every call)
+            fp = (beam.ctypes.data, beam.nbytes, content_hash(beam))
             if _BEAM_CACHE and fp == getattr(self, "_beam_fp", None):
                 flags |= _lib.BEAM_CACHED
             self._beam_fp = fp
@@ -239,6 +255,32 @@ class GridderPlan:
     def degrid_dev(self, dirty_ptr, vis_ptr, stream=None):
         _lib.check(self._lib.pfbg_degrid(self._h, dirty_ptr, vis_ptr, None, _lib.DEVICE_PTRS, stream))
 
+    # -- band split across two GPUs (include/pfbgrid.h "Band split"; pfb_imaging_b200.split drives it) ---------
+    def window(self):
+        """(a_lo, a_len, b_lo, b_len): grid rows / columns any bound sample can touch."""
+        w = (C.c_int32 * 4)()
+        _lib.check(self._lib.pfbg_plan_get_window(self._h, w))
+        return tuple(int(v) for v in w)
+
+    def split_owner_init(self, nq: int) -> bytes:
+        """Hand the transforms of the last `nq` planes to a helper: returns the four IPC blobs the helper needs
+        (plane stack, shared image, partial image, mailbox)."""
+        buf = C.create_string_buffer(4 * _lib.IPC_BLOB_BYTES)
+        _lib.check(self._lib.pfbg_split_owner_init(self._h, int(nq), buf))
+        return buf.raw
+
+    def split_owner_connect(self, helper_mailbox: bytes):
+        buf = C.create_string_buffer(bytes(helper_mailbox), _lib.IPC_BLOB_BYTES)
+        _lib.check(self._lib.pfbg_split_owner_connect(self._h, buf))
+
+    def split_timed_out(self, stream=None) -> bool:
+        t = C.c_int32(0)
+        _lib.check(self._lib.pfbg_split_status(self._h, stream, C.byref(t)))
+        return bool(t.value)
+
+    def split_end(self):
+        _lib.check(self._lib.pfbg_split_end(self._h))
+
     def set_profiling(self, on=True):
         _lib.check(self._lib.pfbg_set_profiling(self._h, int(on)))
 
@@ -247,6 +289,51 @@ class GridderPlan:
         n = C.c_int32(0)
         _lib.check(self._lib.pfbg_get_timings(self._h, ms, 8, C.byref(n)))
         return [ms[i] for i in range(n.value)]
+
+
+class SplitHelper:
+    """Transform helper of a band whose owner lives on another GPU / in another process: holds the band's geometry
+    (no visibilities) and the last `nq` planes; ``serve`` enqueues one Hessian apply worth of helper work."""
+
+    def __init__(self, plan: Plan, nq: int, window, owner_blobs: bytes, device: int | None = None):
+        self.plan, self.nq = plan, int(nq)
+        self.device = current_device() if device is None else int(device)
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        d, self._keep = _plan_desc(plan, self.device)
+        win = (C.c_int32 * 4)(*[int(v) for v in window])
+        blobs = C.create_string_buffer(bytes(owner_blobs), 4 * _lib.IPC_BLOB_BYTES)
+        mb = C.create_string_buffer(_lib.IPC_BLOB_BYTES)
+        _lib.check(self._lib.pfbg_split_helper_create(C.byref(d), self.nq, win, blobs, C.byref(self._h), mb))
+        self.mailbox_blob = mb.raw
+
+    def serve(self, stream=None):
+        _lib.check(self._lib.pfbg_split_helper_serve(self._h, stream))
+
+    def timed_out(self, stream=None) -> bool:
+        t = C.c_int32(0)
+        _lib.check(self._lib.pfbg_split_status(self._h, stream, C.byref(t)))
+        return bool(t.value)
+
+    def set_profiling(self, on=True):
+        _lib.check(self._lib.pfbg_set_profiling(self._h, int(on)))
+
+    def timings(self):
+        ms = (C.c_float * 8)()
+        n = C.c_int32(0)
+        _lib.check(self._lib.pfbg_get_timings(self._h, ms, 8, C.byref(n)))
+        return [ms[i] for i in range(n.value)]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pfbg_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---------------------------------------------------------------------------

@@ -79,3 +79,27 @@ def test_sara_has_no_cpu_fallback():
 
     with pytest.raises(RuntimeError, match="pfbgrid error"):
         PsiNocopyt(1, 64, 64, ["self", "db1"], 1, 1)
+
+
+def test_host_content_hash_sees_single_element_edits():
+    """The plan cache of pfb_imaging_b200.operators validates cached bindings with pfbg_host_hash64: ONE changed
+    element anywhere in an array (a newly flagged sample, a re-weighted one) must change the hash."""
+    from pfb_imaging_b200.wgridder import content_hash
+
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 8, 31, 32, 33, 4097, 3_000_001):
+        m = rng.integers(0, 2, n).astype(np.uint8)
+        h0 = content_hash(m)
+        assert h0 == content_hash(m.copy())
+        for k in {0, n // 3, n // 2, n - 1}:
+            m2 = m.copy()
+            m2[k] ^= 1
+            assert content_hash(m2) != h0, (n, k)
+    w = rng.uniform(0.5, 1.5, (1500, 640))  # 7.7 MB: the threaded path
+    h0 = content_hash(w)
+    for idx in [(0, 0), (700, 333), (1499, 639), (1, 638)]:
+        w2 = w.copy()
+        w2[idx] = np.nextafter(w2[idx], 2.0)
+        assert content_hash(w2) != h0
+    assert content_hash(w[:, ::2]) == content_hash(np.ascontiguousarray(w[:, ::2]))  # strided views hash their content
+    assert content_hash(w[:10]) != content_hash(w[:11])

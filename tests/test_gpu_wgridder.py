@@ -519,3 +519,57 @@ def test_fast_screen_phasors_stay_inside_the_error_budget(gpu, monkeypatch):
     with W.plan_for(p["uvw"], p["freq"], npix_x=128, npix_y=96, pixsize_x=p["cell"], pixsize_y=p["cell"],
                     epsilon=1e-5, precision="double", mask=p["mask"], **kw) as gp:
         assert gp.plan.fast_screen == 0
+
+
+def test_sparse_in_place_edits_invalidate_the_cached_binding(gpu):
+    """the operator-level plan cache must notice a SINGLE-element in-place edit of the mask, the
+    weights or the beam between two hessian_slice calls (the reference keeps no state between calls)."""
+    p = small_problem(nrow=3000, nchan=4, nx=64, ny=64, seed=13)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((64, 64))
+    beam = rng.uniform(0.5, 1.0, (64, 64))
+    mask, wgt = p["mask"].copy(), p["wgt"].copy()
+    mask[:] = 1
+    kw = dict(uvw=p["uvw"], weight=wgt, vis_mask=mask, freq=p["freq"], cell=p["cell"], epsilon=1e-8, beam=beam)
+    ops.clear_plan_cache()
+
+    def fresh():
+        ops.clear_plan_cache()
+        r = ops.hessian_slice(x, **kw)
+        ops.clear_plan_cache()
+        return r
+
+    h0 = ops.hessian_slice(x, **kw)
+    assert rel_l2(ops.hessian_slice(x, **kw), h0) <= 1e-12  # cache hit
+    mask[1717, 2] = 0  # one more flagged sample, off every stride a sampled checksum would look at
+    h1 = ops.hessian_slice(x, **kw)
+    assert rel_l2(h1, fresh()) <= 1e-12 and rel_l2(h1, h0) > 1e-9
+    wgt[1234, 1] *= 3.0  # one re-weighted sample
+    h2 = ops.hessian_slice(x, **kw)
+    assert rel_l2(h2, fresh()) <= 1e-12 and rel_l2(h2, h1) > 1e-9
+    beam[17, 33] = 0.1  # one patched beam pixel
+    h3 = ops.hessian_slice(x, **kw)
+    assert rel_l2(h3, fresh()) <= 1e-12 and rel_l2(h3, h2) > 1e-9
+    ops.clear_plan_cache()
+
+
+def test_no_mask_zero_leaves_flagged_samples_untouched_on_the_wide_path(gpu):
+    """include/pfbgrid.h PFBG_NO_MASK_ZERO: masked output samples keep the caller's values, also for W > 8 (the
+    cooperative-team kernels add into the output and used to clear all of it)."""
+    import ctypes as C
+
+    from pfb_imaging_b200 import _lib
+
+    p = small_problem(nrow=600, nchan=3, nx=64, ny=64, seed=2)
+    for eps, wide in ((1e-10, True), (1e-4, False)):
+        with W.plan_for(p["uvw"], p["freq"], npix_x=64, npix_y=64, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=eps,
+                        mask=p["mask"], flip_v=True, divide_by_n=False) as gp:
+            assert (gp.plan.W > 8) == wide
+            ref = gp.degrid(p["img"])
+            out = np.full(ref.shape, 7.0 - 3.0j)
+            img = np.ascontiguousarray(p["img"])
+            _lib.check(gp._lib.pfbg_degrid(gp._h, C.c_void_p(img.ctypes.data), C.c_void_p(out.ctypes.data), None,
+                                           _lib.HOST_PTRS | _lib.NO_MASK_ZERO, None))
+            act = p["mask"] != 0
+            assert np.all(out[~act] == 7.0 - 3.0j) and (~act).sum() > 0
+            assert rel_l2(out[act], ref[act]) <= 1e-12
