@@ -328,7 +328,7 @@ def run_ours(args, cfg):
         for b, h in split.helpers.items():
             tm = h.timings()
             h.set_profiling(False)
-            if len(tm) >= 5:
+            if len(tm) >= 4:
                 helper_phases[b] = dict(wait_x=round(tm[0], 3), copy_x_fwd_planes=round(tm[1], 3),
                                         wait_grid=round(tm[2], 3), inv_planes_partial=round(tm[3], 3))
         barrier()
