@@ -33,8 +33,9 @@ from .wgridder import GridderPlan, dirty2vis, plan_for, vis2dirty
 
 __all__ = [
     "wgridder_conventions", "vis2im", "im2vis", "hessian_slice", "residual_from_partitions",
-    "compute_residual_arrays", "image_data_products_arrays", "grid_partition", "eval_beam", "clear_plan_cache",
-    "BandHessian", "BandPool",
+    "compute_residual", "compute_residual_arrays", "image_data_products", "image_data_products_arrays",
+    "grid_partition", "eval_beam", "_comps2vis_impl", "clear_plan_cache",
+    "BandHessian", "BandPool", "BandWorkerPool",
 ]
 
 
@@ -256,6 +257,199 @@ def compute_residual_arrays(uvw, wgt, mask, beam, dirty, freq, flip_u, flip_v, f
         _exact_conv(model[c], beam[c], uvw, freq, wgt[c], mask, nx, ny, cellx, celly, x0, y0,
                     (flip_u, flip_v, flip_w), epsilon, do_wgridding, out=convim[c])
     return dirty - convim
+
+
+def _open_dataset(d, drop_vars=None):
+    """A dataset handle as the reference passes it around: a zarr group path (opened through
+    pfb_imaging_b200.store — xarray / zarr are not importable here) or an already opened dataset-like object."""
+    if isinstance(d, (str, bytes)) or hasattr(d, "__fspath__"):
+        from .store import open_zarr
+
+        return open_zarr(d, drop_vars=drop_vars)
+    return d
+
+
+def _attr(ds, name, default=None):
+    if hasattr(ds, name):
+        return getattr(ds, name)
+    attrs = getattr(ds, "attrs", {})
+    if name in attrs:
+        return attrs[name]
+    if default is None:
+        raise AttributeError(f"dataset has neither attribute nor attr {name!r}")
+    return default
+
+
+def compute_residual(dsl, nx, ny, cellx, celly, output_name, model, nthreads=1, epsilon=1e-7, do_wgridding=True,
+                     double_accum=True, verbosity=1, async_write=True):
+    """Compute the residual of one band and write MODEL / RESIDUAL to its store (operators/gridder.py:1019-1148):
+    ``residual = DIRTY - R^H W R (BEAM * model)`` per correlation, returned as ``(residual, future)``.
+
+    `dsl` is a zarr group path, a list holding one, or a dataset-like object (``.UVW.values`` ..., attrs
+    ``flip_u, flip_v, flip_w, x0, y0`` as attributes or in ``.attrs``).  The write goes through the object's own
+    ``to_zarr`` when it has one; like the reference's executor block, it has completed on return."""
+    import concurrent.futures as cf
+    from time import time
+
+    tii = time()
+    if isinstance(dsl, (list, tuple)):
+        dsl = dsl[0]  # currently only a single dds (gridder.py:1043-1046)
+    ds = _open_dataset(dsl)
+    uvw, wgt, mask = ds.UVW.values, ds.WEIGHT.values, ds.MASK.values
+    beam, dirty, freq = ds.BEAM.values, ds.DIRTY.values, ds.FREQ.values
+    flip_u, flip_v, flip_w = _attr(ds, "flip_u"), _attr(ds, "flip_v"), _attr(ds, "flip_w")
+    x0, y0 = _attr(ds, "x0"), _attr(ds, "y0")
+    tread = time() - tii
+    ti = time()
+    residual = compute_residual_arrays(uvw, wgt, mask, beam, dirty, freq, flip_u, flip_v, flip_w, x0, y0, nx, ny,
+                                       cellx, celly, model, nthreads=nthreads, epsilon=epsilon,
+                                       do_wgridding=do_wgridding, double_accum=double_accum)
+    tgrid = time() - ti
+    ti = time()
+    future = None
+    if hasattr(ds, "__setitem__") and hasattr(ds, "to_zarr"):
+        ds["MODEL"] = (("corr", "x", "y"), model)
+        ds["RESIDUAL"] = (("corr", "x", "y"), residual)
+        out = ds[["RESIDUAL", "MODEL"]]  # only these two are written (gridder.py:1124-1125)
+        if async_write:
+            with cf.ThreadPoolExecutor(max_workers=1) as executor:
+                future = executor.submit(out.to_zarr, output_name, mode="a")
+        else:
+            out.to_zarr(output_name, mode="a")
+    twrite = time() - ti
+    if verbosity > 1:
+        ttot = time() - tii
+        print(f"tread = {tread / ttot}")
+        print(f"tgrid = {tgrid / ttot}")
+        print(f"twrite = {twrite / ttot}")
+    return residual, future
+
+
+def image_data_products(dsl, dsp, nx, ny, nx_psf, ny_psf, cellx, celly, output_name, attrs, model=None,
+                        robustness=None, l0=0.0, m0=0.0, nthreads=1, epsilon=1e-7, do_wgridding=True,
+                        double_accum=True, l2_reweight_dof=None, do_dirty=True, do_psf=True, do_residual=True,
+                        do_weight=True, do_noise=False, do_beam=False, min_padding=1.7, filter_counts_level=5.0,
+                        npix_super=0, fit_psf=None, rng=None):
+    """Image-space data products of one (band, time) in one go (operators/gridder.py:375-757), same signature:
+    `dsl` = list of ``.xds`` groups (paths or dataset-likes with VIS, WEIGHT (corr,row,chan), MASK, UVW, FREQ, BEAM,
+    l_beam, m_beam), concatenated along rows; `dsp` = optional dataset with the prior WEIGHT for the l2
+    re-weighting; products are written to the zarr group `output_name` and ``{residual, psf, wsum, timeid}`` is
+    returned.  ``PSFPARSN`` needs the reference's jax / scikit-image ``fitcleanbeam``: pass it as `fit_psf`,
+    otherwise that variable is not written."""
+    from .store import Dataset
+
+    flip_u, flip_v, flip_w, x0, y0 = wgridder_conventions(l0, m0)
+    x = (-nx / 2 + np.arange(nx)) * cellx + x0
+    y = (-ny / 2 + np.arange(ny)) * celly + y0
+    if isinstance(dsl, (str, bytes)) or not isinstance(dsl, (list, tuple)):
+        dsl = [dsl]
+    dsl = [_open_dataset(d) for d in dsl]
+    ncorr = dsl[0].WEIGHT.values.shape[0]
+    freq = dsl[0].FREQ.values  # must all be the same
+    # weighted sum of the partitions' beams (gridder.py:439-462)
+    beam = np.zeros((ncorr, nx, ny), dtype=float)
+    wsumb = np.zeros(ncorr, dtype=float)
+    xx, yy = np.meshgrid(np.rad2deg(x), np.rad2deg(y), indexing="ij")
+    for ds in dsl:
+        wgt_, mask_ = ds.WEIGHT.values, ds.MASK.values
+        assert (ds.FREQ.values == freq).all()
+        for c in range(ncorr):
+            wsumt = (wgt_[c] * mask_).sum()
+            wsumb[c] += wsumt
+            beam[c] += eval_beam(ds.BEAM.values[c], ds.l_beam.values, ds.m_beam.values, xx, yy) * wsumt
+    beam /= wsumb[:, None, None]
+    uvw = np.concatenate([ds.UVW.values for ds in dsl], axis=0)
+    vis = np.concatenate([ds.VIS.values for ds in dsl], axis=1)
+    wgt = np.concatenate([ds.WEIGHT.values for ds in dsl], axis=1)
+    mask = np.concatenate([ds.MASK.values for ds in dsl], axis=0)
+    wgtp = None
+    if l2_reweight_dof and dsp:
+        wgtp = _open_dataset(dsp).WEIGHT.values
+    prod = image_data_products_arrays(
+        uvw, freq, vis, wgt, mask, nx, ny, nx_psf, ny_psf, cellx, celly, l0=l0, m0=m0, epsilon=epsilon,
+        do_wgridding=do_wgridding, double_accum=double_accum, do_dirty=do_dirty, do_psf=do_psf, nthreads=nthreads,
+        model=model, robustness=robustness, l2_reweight_dof=l2_reweight_dof, wgtp=wgtp, do_residual=do_residual,
+        do_noise=do_noise, min_padding=min_padding, filter_counts_level=filter_counts_level, npix_super=npix_super,
+        rng=rng)
+    wsum = prod["wsum"]
+    dso = Dataset(attrs=dict(attrs))
+    dso["FREQ"] = (("chan",), freq)
+    dso["x"], dso["y"] = (("x",), x), (("y",), y)
+    if do_weight:
+        dso["WEIGHT"] = (("corr", "row", "chan"), prod["weight"])
+        dso["UVW"] = (("row", "three"), uvw)
+        dso["MASK"] = (("row", "chan"), mask)
+    dso["WSUM"] = (("corr",), wsum)
+    if do_dirty:
+        dso["DIRTY"] = (("corr", "x", "y"), prod["dirty"])
+    if do_psf:
+        dso["PSF"] = (("corr", "x_psf", "y_psf"), prod["psf"])
+        dso["PSFHAT"] = (("corr", "x_psf", "yo2"), prod["psfhat"])
+        if fit_psf is not None:
+            dso["PSFPARSN"] = (("corr", "bpar"), np.array(fit_psf(prod["psf"], level=0.5, pixsize=1.0)))
+    if do_residual and model is not None:
+        dso["MODEL"] = (("corr", "x", "y"), model)
+        dso["RESIDUAL"] = (("corr", "x", "y"), prod["residual"])
+    if do_noise:
+        dso["NOISE"] = (("corr", "x", "y"), prod["noise"])
+    if do_beam:
+        dso["BEAM"] = (("corr", "x", "y"), beam)
+    dso.attrs.update(wsum=wsum, x0=x0, y0=y0, l0=l0, m0=m0, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w)
+    if output_name is not None:
+        dso.to_zarr(output_name, mode="a")
+    outputs = {}
+    outputs["residual"] = prod["residual"] if (do_residual and model is not None) else prod.get("dirty")
+    if do_psf:
+        outputs["psf"] = prod["psf"]
+    outputs["wsum"] = wsum
+    outputs["timeid"] = attrs["timeid"] if "timeid" in attrs else None
+    return outputs
+
+
+def _comps2vis_impl(uvw, utime, freq, rbin_idx, rbin_cnts, tbin_idx, tbin_cnts, fbin_idx, fbin_cnts, region_mask, mds,
+                    modelf, tfunc, ffunc, epsilon=1e-7, nthreads=1, do_wgridding=True, divide_by_n=False,
+                    freq_min=-np.inf, freq_max=np.inf, product="I"):
+    """Model components -> visibilities of one row chunk (operators/gridder.py:276-367, the body of `pfb degrid`):
+    per (time bin, band) render the components into an image with `modelf(tfunc(t), ffunc(f), *coefficients)` and
+    degrid it onto that bin's rows and channels.  `mds` is the model dataset (``coefficients, location_x,
+    location_y`` variables; attrs ``cell_rad_x, npix_x, npix_y, center_x, center_y, flip_u, flip_v, flip_w``).
+    The reference passes ALL rows of the chunk to dirty2vis and assigns the result to the bin's rows, which only
+    works for one time bin per chunk; here the bin's own rows are degridded, which is the same thing in that case."""
+    rbin_idx2 = rbin_idx - rbin_idx.min()
+    tbin_idx2 = tbin_idx - tbin_idx.min()
+    fbin_idx2 = fbin_idx - fbin_idx.min()
+    ntime, nband = tbin_idx.size, fbin_idx.size
+    nrow, nchan = uvw.shape[0], freq.size
+    nstokes_out = len(product)
+    comps = mds.coefficients.values
+    vis = np.zeros((nrow, nchan, nstokes_out), dtype=np.result_type(comps.dtype, np.complex64))
+    if not ((freq >= freq_min) & (freq <= freq_max)).any():
+        return vis
+    x_index, y_index = mds.location_x.values, mds.location_y.values
+    cellx = celly = _attr(mds, "cell_rad_x")  # (sic) gridder.py:319-320
+    nx, ny = _attr(mds, "npix_x"), _attr(mds, "npix_y")
+    x0, y0 = _attr(mds, "center_x"), _attr(mds, "center_y")
+    flip_u, flip_v, flip_w = _attr(mds, "flip_u"), _attr(mds, "flip_v"), _attr(mds, "flip_w")
+    for t in range(ntime):
+        indt = slice(tbin_idx2[t], tbin_idx2[t] + tbin_cnts[t])
+        indr = slice(rbin_idx2[indt][0], rbin_idx2[indt][-1] + rbin_cnts[indt][-1])
+        for b in range(nband):
+            indf = slice(fbin_idx2[b], fbin_idx2[b] + fbin_cnts[b])
+            f = freq[indf]
+            if not ((f >= freq_min) & (f <= freq_max)).any():
+                continue
+            tout = tfunc(np.mean(utime[indt]))
+            fout = ffunc(np.mean(freq[indf]))
+            image = np.zeros((nx, ny), dtype=comps.dtype)
+            image[x_index, y_index] = modelf(tout, fout, *comps[:, :])
+            if np.any(region_mask):
+                image = np.where(region_mask, image, 0.0)
+                for c in range(nstokes_out):
+                    vis[indr, indf, c] = dirty2vis(
+                        uvw=uvw[indr], freq=f, dirty=image, pixsize_x=cellx, pixsize_y=celly, center_x=x0, center_y=y0,
+                        flip_u=flip_u, flip_v=flip_v, flip_w=flip_w, epsilon=epsilon, do_wgridding=do_wgridding,
+                        divide_by_n=divide_by_n, nthreads=nthreads)
+    return vis
 
 
 def image_data_products_arrays(uvw, freq, vis, wgt, mask, nx, ny, nx_psf, ny_psf, cellx, celly, l0=0.0, m0=0.0,
@@ -643,3 +837,6 @@ class BandPool:
     def close(self):
         for op in self.ops.values():
             op.close()
+
+
+from .band_worker import BandWorkerPool, _BandWorkerImpl  # noqa: E402,F401  (drop-in of operators/band_worker.py)

@@ -222,3 +222,55 @@ def power_method_device(apply_dev, shape, dtype=np.float64, b0=None, tol=1e-5, m
         print(f"Maximum iterations reached. eps = {eps:.3e}, beta = {beta:.3e}" if k == maxit
               else f"Success, converged after {k} iterations. beta = {beta:.3e}")
     return beta, bt.cpu().numpy()
+
+
+def pcg_dds(ds_name, eta, mask=1.0, use_psf=True, residual_name="RESIDUAL", model_name="MODEL", do_wgridding=True,
+            epsilon=5e-4, double_accum=True, nthreads=1, zero_model_outside_mask=False, tol=1e-5, maxit=500,
+            verbosity=1, report_freq=10):
+    """Flux mop of one band: CG on the EXACT Hessian ``beam R^H W R beam / wsum + eta`` (``opt/pcg.py:444-583``, the
+    one place the reference iterates on the gridder Hessian; `pfb fluxtractor`).  `ds_name` is the band's ``.dds``
+    zarr group (path, list holding one, or an opened dataset-like).  Every CG iteration is one fused device apply
+    of the band pinned by the operator-level plan cache; MODEL_MOPPED / RESIDUAL_MOPPED / UPDATE / X0 are written
+    back to the store.  Returns ``(resid, bandid)``."""
+    from functools import partial
+
+    from .operators import _attr, _open_dataset, hessian_slice
+
+    if isinstance(ds_name, (list, tuple)):
+        ds_name = ds_name[0]
+    ds = _open_dataset(ds_name, drop_vars=["PSF", "PSFHAT"])
+    geom = dict(uvw=ds.UVW.values, weight=ds.WEIGHT.values, vis_mask=ds.MASK.values, freq=ds.FREQ.values,
+                cell=_attr(ds, "cell_rad"), x0=_attr(ds, "x0"), y0=_attr(ds, "y0"), do_wgridding=do_wgridding,
+                epsilon=epsilon, double_accum=double_accum, nthreads=nthreads)
+    beam0 = ds.BEAM.values
+    beam = mask * beam0
+    if zero_model_outside_mask:
+        if model_name not in ds:
+            raise RuntimeError(f"Asked to zero model outside mask but {model_name} not in dds")
+        model = np.where(mask > 0, ds[model_name].values, 0.0)
+        print("Zeroing model outside mask")
+        resid = ds.DIRTY.values - hessian_slice(model, beam=beam0, **geom)
+        j = resid * beam
+    else:
+        model = np.array(ds[model_name].values, copy=True) if model_name in ds else np.zeros(np.shape(mask), dtype=float)
+        if residual_name in ds:
+            j = ds[residual_name].values * beam
+            ds = ds.drop_vars(residual_name)
+        else:
+            j = ds.DIRTY.values * beam
+    wsum = _attr(ds, "wsum")
+    j = j / wsum
+    x0 = ds.UPDATE.values * mask if "UPDATE" in ds else np.zeros_like(j)
+    hess = partial(hessian_slice, beam=np.ascontiguousarray(beam), flip_u=_attr(ds, "flip_u"), flip_v=_attr(ds, "flip_v"),
+                   flip_w=_attr(ds, "flip_w"), eta=eta, wsum=wsum, **geom)
+    x = pcg(hess, j, x0=np.array(x0, copy=True), precond=None, tol=tol, maxit=maxit, minit=1, verbosity=verbosity,
+            report_freq=report_freq, backtrack=False, return_resid=False)
+    model = model + x
+    resid = ds.DIRTY.values - hessian_slice(model, beam=beam0, **geom)
+    if hasattr(ds, "assign") and hasattr(ds, "to_zarr"):
+        out = ds.assign(MODEL_MOPPED=(("x", "y"), model), RESIDUAL_MOPPED=(("x", "y"), resid), UPDATE=(("x", "y"), x),
+                        X0=(("x", "y"), x0))
+        target = ds_name if isinstance(ds_name, (str, bytes)) else getattr(ds, "_path", None)
+        if target is not None:
+            out[["MODEL_MOPPED", "RESIDUAL_MOPPED", "UPDATE", "X0"]].to_zarr(target, mode="a")
+    return resid, int(_attr(ds, "bandid", 0))
