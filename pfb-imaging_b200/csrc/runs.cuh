@@ -264,6 +264,76 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t x, int src) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+// ---------------------------------------------------------------------------
+// Cyclic column ownership (W = 8, full 8-plane support, rows that do not wrap).
+// Consecutive runs of a (tile, plane) bucket come in the order (iu, iv): the next run usually starts ONE cell
+// further along v, so 7 of its 8 footprint columns are the previous run's.  Lane (j, q2) therefore owns the
+// absolute grid column c with c mod 8 == j instead of the column at offset j from the run origin: when the origin
+// moves along v only the lanes whose column leaves the footprint flush (gridding) or fetch (degridding) — one
+// lane group of eight instead of all of them, i.e. up to 8x fewer L2 atomics / gather loads at short run lengths
+// (band 7 of C2: 6.7 samples per run, the L2 was at 60 % in k_grid_runs and the FMA pipe at 35 %).  The tap a
+// lane applies is k = (j - iv0) mod 8.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool run_is_cyclic(const GParams& p, uint64_t origin) {
+  const int iu0 = (int)((origin >> 16) & 0xffffu);
+  return p.W == 8 && p.do_wgridding && iu0 >= 1 && iu0 + 8 <= p.nu;
+}
+__device__ __forceinline__ int run_column(const GParams& p, uint64_t origin, int j) {
+  const int iv0 = (int)(origin & 0xffffu);
+  int c = iv0 + ((j - iv0) & 7);
+  if (c >= p.nv) c -= p.nv;  // nv is a multiple of 8: c mod 8 stays j
+  return c;
+}
+
+// flush / fetch of ONE footprint column (absolute column iv) of the run at `origin`: 8 rows x this lane's 2 planes
+template <typename T>
+__device__ __forceinline__ void run_flush_col(const GParams& p, typename cplx_of<T>::type* __restrict__ grid,
+                                              typename cplx_of<T>::type (&acc)[8][2], uint64_t origin, int iv, int q2) {
+  const int iu0 = (int)((origin >> 16) & 0xffffu);
+  const int ip = origin_plane(origin);
+  const int plane_sz = p.nu * p.nv;
+  const int mv = iv ? p.nv - iv : 0;
+#pragma unroll
+  for (int qq = 0; qq < 2; ++qq) {
+    const int pl = ip + q2 + 4 * qq;
+    const bool mir = pl < 0;
+    typename cplx_of<T>::type* gq = grid + (mir ? (int64_t)(-pl - 1) * plane_sz + (int64_t)(p.nu - iu0) * p.nv + mv
+                                                : (int64_t)pl * plane_sz + (int64_t)iu0 * p.nv + iv);
+    const int step = mir ? -p.nv : p.nv;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomic_add_c(gq, acc[i][qq].x, mir ? -acc[i][qq].y : acc[i][qq].y);
+      gq += step;
+      acc[i][qq].x = 0;
+      acc[i][qq].y = 0;
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void run_fetch_col(const GParams& p, const typename cplx_of<T>::type* __restrict__ grid,
+                                              typename cplx_of<T>::type (&gv)[8][2], uint64_t origin, int iv, int q2) {
+  using C = typename cplx_of<T>::type;
+  const int iu0 = (int)((origin >> 16) & 0xffffu);
+  const int ip = origin_plane(origin);
+  const int plane_sz = p.nu * p.nv;
+  const int mv = iv ? p.nv - iv : 0;
+#pragma unroll
+  for (int qq = 0; qq < 2; ++qq) {
+    const int pl = ip + q2 + 4 * qq;
+    const bool mir = pl < 0;
+    const C* gq = grid + (mir ? (int64_t)(-pl - 1) * plane_sz + (int64_t)(p.nu - iu0) * p.nv + mv
+                              : (int64_t)pl * plane_sz + (int64_t)iu0 * p.nv + iv);
+    const int step = mir ? -p.nv : p.nv;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      C val = *gq;
+      if (mir) val.y = -val.y;
+      gv[i][qq] = val;
+      gq += step;
+    }
+  }
+}
+
 // the next slice [kbeg, kend) of the sorted samples for this warp (lane 0 draws it from the launch's counter).
 // The first 7/8 of the samples go out in slices of `big` (RUN_SLICE when there is enough work for every warp, see
 // run_slice() on the host), the rest in slices of RUN_SLICE_TAIL, so the warps finish within a short slice of each
@@ -307,6 +377,9 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 #pragma unroll
   for (int i = 0; i < 8; ++i) { acc[i][0].x = acc[i][0].y = 0; acc[i][1].x = acc[i][1].y = 0; }
   uint64_t cur = ~0ull;
+  bool cyc = false;  // the current run uses cyclic column ownership
+  int myc = 0;       // ... and this lane holds absolute column myc
+  int kj = j;        // v-tap this lane applies
   // slices are handed out in sort order from a device counter: their cost varies with the run length (the dense
   // core against the outer uv plane), and a fixed stride left the last warps running alone for ~5 % of the kernel
   for (;;) {
@@ -353,15 +426,27 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
       int v = 0;
       while (v < nb) {  // (c) lane <-> footprint cell, one run segment at a time
         if ((starts >> v) & 1u) {
-          if (cur != ~0ull) run_flush<T>(p, grid, acc, cur, j, q2);
-          cur = shfl_u64(org, v);
+          const uint64_t nxt = shfl_u64(org, v);
+          const bool ncyc = run_is_cyclic(p, nxt);
+          if (cur != ~0ull) {
+            if (cyc && ncyc && (cur >> 16) == (nxt >> 16)) {
+              // same rows and planes, origin moved along v: only the lanes whose column leaves the footprint flush
+              const int c = run_column(p, nxt, j);
+              if (c != myc) run_flush_col<T>(p, grid, acc, cur, myc, q2);
+            } else if (cyc) run_flush_col<T>(p, grid, acc, cur, myc, q2);
+            else run_flush<T>(p, grid, acc, cur, j, q2);
+          }
+          cur = nxt;
+          cyc = ncyc;
+          myc = run_column(p, nxt, j);
+          kj = ncyc ? ((j - (int)(nxt & 0xffffu)) & 7) : j;
         }
         const uint32_t rest = v < 31 ? (starts & (0xffffffffu << (v + 1))) : 0u;
         const int vend = rest ? min(__ffs(rest) - 1, nb) : nb;
 #pragma unroll kGridUnroll
         for (; v < vend; ++v) {
           const T* tp = taps[warp][v];
-          const T tv = tp[8 + j];
+          const T tv = tp[8 + kj];
           const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
           const C a = amp[warp][v];
           const C a0 = cmul_s(a, c0), a1 = cmul_s(a, c1);
@@ -376,7 +461,10 @@ k_grid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
       __syncwarp();
     }
   }
-  if (cur != ~0ull) run_flush<T>(p, grid, acc, cur, j, q2);
+  if (cur != ~0ull) {
+    if (cyc) run_flush_col<T>(p, grid, acc, cur, myc, q2);
+    else run_flush<T>(p, grid, acc, cur, j, q2);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -401,6 +489,8 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
 #pragma unroll
   for (int i = 0; i < 8; ++i) { gv[i][0].x = gv[i][0].y = 0; gv[i][1].x = gv[i][1].y = 0; }
   uint64_t cur = ~0ull;
+  bool cyc = false;  // cyclic column ownership, see run_is_cyclic
+  int myc = 0, kj = j;
   for (;;) {  // slices from the device counter, see k_grid_runs
     int64_t kbeg, kend;
     if (!next_slice(queue, lane, nact, slice, kbeg, kend)) break;
@@ -430,9 +520,21 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
       }
       int v = 0;
       while (v < nb) {
-        if ((starts >> v) & 1u) {  // new run: fetch its footprint once
-          cur = shfl_u64(org, v);
-          run_fetch<T>(p, grid, gv, cur, j, q2);
+        if ((starts >> v) & 1u) {  // new run: fetch its footprint once (only the columns that are new to it)
+          const uint64_t nxt = shfl_u64(org, v);
+          const bool ncyc = run_is_cyclic(p, nxt);
+          const int c = run_column(p, nxt, j);
+          const bool keep = cyc && ncyc && cur != ~0ull && (cur >> 16) == (nxt >> 16) && c == myc;
+          cur = nxt;
+          cyc = ncyc;
+          if (ncyc) {
+            if (!keep) run_fetch_col<T>(p, grid, gv, cur, c, q2);
+            myc = c;
+            kj = (j - (int)(nxt & 0xffffu)) & 7;
+          } else {
+            run_fetch<T>(p, grid, gv, cur, j, q2);
+            kj = j;
+          }
         }
         const uint32_t rest = v < 31 ? (starts & (0xffffffffu << (v + 1))) : 0u;
         const int vend = rest ? min(__ffs(rest) - 1, nb) : nb;
@@ -446,7 +548,7 @@ k_degrid_runs(GParams p, const VisRec<T>* __restrict__ recs, int64_t nact,
             a0 = cfma_s(gv[i][0], u, a0);
             a1 = cfma_s(gv[i][1], u, a1);
           }
-          const T tv = tp[8 + j];
+          const T tv = tp[8 + kj];
           const T c0 = tv * tp[16 + q2], c1 = tv * tp[20 + q2];
           part[warp][v][lane] = cfma_s(a1, c1, cmul_s(a0, c0));
         }

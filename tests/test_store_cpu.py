@@ -107,7 +107,9 @@ def make_dt_store(path, nband=2, npart=2, nx=32, nx_psf=48, nrow=120, nchan=3, s
                         WEIGHT=rng.uniform(0.5, 1.5, (ncorr, nrow, nchan)),
                         MASK=(rng.uniform(size=(nrow, nchan)) > 0.1).astype(np.uint8), FREQ=freq,
                         BEAM=rng.uniform(0.7, 1.0, (ncorr, nx, nx)),
-                        PSFHAT=rng.standard_normal((ncorr, nx_psf, nx_psf // 2 + 1)) + 1j * rng.standard_normal((ncorr, nx_psf, nx_psf // 2 + 1)),
+                        # the spectrum of a REAL point-spread function (Hermitian along x in the k_y = 0 / Nyquist columns)
+                        PSFHAT=np.fft.rfft2(rng.standard_normal((ncorr, nx_psf, nx_psf)) *
+                                            np.outer(np.hanning(nx_psf), np.hanning(nx_psf))[None], axes=(1, 2)),
                         VIS=rng.standard_normal((ncorr, nrow, nchan)) + 0j)
             pd = store.Dataset(attrs=dict(wsum=[float(part["WEIGHT"][c][part["MASK"] > 0].sum()) for c in range(ncorr)],
                                           l0=0.0, m0=0.0, cell_rad=cell))
