@@ -33,6 +33,11 @@ WORKLOADS = {
     # pfb's production default: double precision, epsilon=1e-7 (core/grid.py:50), C2 geometry
     "c2d": dict(nx=4096, ntime=775, nchan=16, precision="double", epsilon=1e-7,
                 name="C2 geometry in fp64 at pfb's default eps=1e-7: 4096^2, 25.0M vis/band"),
+    # configs[4]: pfb hci, 1024 high-cadence snapshots of 512^2 (utils/stokes2im.py:635-683: sigma_min = 2,
+    # divide_by_n = True; tests/test_hci.py:33-34: single precision, epsilon 1e-4), batched
+    "c5": dict(nx=512, nsnap=1024, nchan=16, precision="single", epsilon=1e-4, chunk=256, band=4,
+               name="pfb hci C5: 1024 snapshots x 512^2, 2016 baselines x 16 channels each (33.0M vis), fp32, eps=1e-4, "
+                    "sigma_min=2, divide_by_n, batched 256 snapshots per launch sequence"),
 }
 
 
@@ -151,6 +156,185 @@ def run_reference(args, cfg):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+
+def run_c5(args, cfg):
+    """Batched small-image workload (BASELINE configs[4]): the snapshots of one job are dealt round-robin to the
+    ranks; every rank images its share in batches of cfg["chunk"] snapshots (one bin / sort and one launch of every
+    kernel per batch)."""
+    import torch
+    import torch.distributed as dist
+
+    from pfb_imaging_b200 import _lib, synth, wgridder as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nx, nsnap, nchan, chunk = cfg["nx"], cfg["nsnap"], cfg["nchan"], cfg["chunk"]
+    rng = np.random.default_rng(1234)
+    enu = synth.meerkat_like_antennas(rng)
+    uvw_all = synth.uvw_tracks(enu, nsnap)  # time-major: rows [t * nbl, (t+1) * nbl) are snapshot t
+    nbl = uvw_all.shape[0] // nsnap
+    freq = synth.band_freqs(cfg["band"], 8, nchan)
+    cell = synth.default_cell(uvw_all, 1712e6)
+    mine = list(range(rank, nsnap, world))
+    brng = np.random.default_rng([5, rank])
+    geom = dict(npix_x=nx, npix_y=nx, pixsize_x=cell, pixsize_y=cell, epsilon=cfg["epsilon"], flip_v=True,
+                divide_by_n=True, sigma_min=2.0, sigma_max=2.6, precision=cfg["precision"])
+    batches = []
+    for c0 in range(0, len(mine), chunk):
+        ids = mine[c0:c0 + chunk]
+        uvw = [uvw_all[t * nbl:(t + 1) * nbl] for t in ids]
+        wgt = brng.uniform(0.5, 1.5, (len(ids) * nbl, nchan)).astype(np.float32)
+        gp = W.batch_plan_for(uvw, freq, device=local, **geom)
+        gp.bind_weights(wgt)
+        x = np.zeros((len(ids), nx, nx), np.float32)
+        for k in range(len(ids)):
+            x[k] = synth.point_source_image(nx, nx, nsrc=20, seed=ids[k], dtype=np.float32)
+        x_d = torch.from_numpy(x).to(dev)
+        batches.append(dict(ids=ids, uvw=uvw, wgt=wgt, gp=gp, x=x, x_d=x_d, out_d=torch.empty_like(x_d),
+                            wsum=float(wgt.sum(dtype=np.float64)), nvis=len(ids) * nbl * nchan, info=gp.info()))
+    nvis_local = sum(b["nvis"] for b in batches)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        for b in batches:
+            b["gp"].hessian_dev(b["x_d"].data_ptr(), None, b["wsum"], 0.0, b["out_d"].data_ptr(), stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.load().pfbg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.load().pfbg_launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    nv = torch.tensor([float(nvis_local)], dtype=torch.float64, device=dev)
+    la = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nv, op=dist.ReduceOp.SUM)
+        dist.all_reduce(la, op=dist.ReduceOp.SUM)
+    ms_step = float(t.item()) / args.steps
+    value = float(nv.item()) / (ms_step * 1e-3) / 1e6
+    # phases of the first batch
+    names = ["stage_in", "pad_screen_fft", "degrid", "zero_grid", "spread", "fft_crop_screen", "stage_out"]
+    b0 = batches[0]
+    b0["gp"].set_profiling(True)
+    rec = []
+    for _ in range(3):
+        b0["gp"].hessian_dev(b0["x_d"].data_ptr(), None, b0["wsum"], 0.0, b0["out_d"].data_ptr(), stream)
+        torch.cuda.synchronize()
+        rec.append(b0["gp"].timings())
+    b0["gp"].set_profiling(False)
+    phases = dict(zip(names, np.median(np.array(rec), axis=0).tolist()))
+    # ---- end to end: host cubes in and out through the bound batch plans (the apply a solver makes) -----------
+    outs = [np.empty_like(b["x"]) for b in batches]
+    for _ in range(2):
+        for b, o in zip(batches, outs):
+            b["gp"].hessian(b["x"], wsum=b["wsum"], out=o)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for b, o in zip(batches, outs):
+            b["gp"].hessian(b["x"], wsum=b["wsum"], out=o)
+    torch.cuda.synchronize()
+    te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = float(nv.item()) / float(te.item()) / 1e6
+    img_bytes = int(sum(b["x"].nbytes for b in batches)) * world
+    # ---- the hci pattern itself: one-shot imaging of snapshots from host arrays (bind + residual + PSF), batched
+    # against one pooled vis2dirty call pair per snapshot (what round 1 offered) --------------------------------
+    one_shot = None
+    if rank == 0:
+        b = batches[0]
+        ns = min(64, len(b["ids"]))
+        cdt = np.complex64
+        vis = [(brng.standard_normal((nbl, nchan)) + 1j * brng.standard_normal((nbl, nchan))).astype(cdt) for _ in range(ns)]
+        ones = [np.ones((nbl, nchan), cdt) for _ in range(ns)]
+        wl = [b["wgt"][k * nbl:(k + 1) * nbl] for k in range(ns)]
+        com = dict(freq=freq, npix_x=nx, npix_y=nx, pixsize_x=cell, pixsize_y=cell, epsilon=cfg["epsilon"], flip_v=True,
+                   divide_by_n=True, sigma_min=2.0, sigma_max=2.6)
+        for _ in range(2):
+            cube, psf = W.vis2dirty_batch(uvw=b["uvw"][:ns], vis=vis, wgt=wl, extra_vis=(ones,), **com)
+        t0 = time.perf_counter()
+        cube, psf = W.vis2dirty_batch(uvw=b["uvw"][:ns], vis=vis, wgt=wl, extra_vis=(ones,), **com)
+        t_batch = (time.perf_counter() - t0) / ns
+        for k in range(2):
+            W.vis2dirty(uvw=b["uvw"][k], vis=vis[k], wgt=wl[k], **com)
+        t0 = time.perf_counter()
+        for k in range(ns):
+            d1 = W.vis2dirty(uvw=b["uvw"][k], vis=vis[k], wgt=wl[k], **com)
+            W.vis2dirty(uvw=b["uvw"][k], vis=ones[k], wgt=wl[k], **com)
+        t_single = (time.perf_counter() - t0) / ns
+        err = float(np.linalg.norm(cube[ns - 1] - d1) / np.linalg.norm(d1))
+        one_shot = {"snapshots": ns, "ms_per_snapshot_batched": 1e3 * t_batch, "ms_per_snapshot_pooled_one_shot_calls": 1e3 * t_single,
+                    "speedup": t_single / t_batch, "batched_vs_one_shot_rel_l2": err,
+                    "what": "residual + PSF image of a snapshot from host arrays (bind, grid twice, images back), as utils/stokes2im.py:635-683"}
+        W.clear_plan_pool()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        info = b0["info"]
+        B = sum(algorithmic_bytes(dict(bb["info"], nx=nx, ny=nx), bb["nvis"], nchan, 4) for bb in batches)
+        my_ms = ms_total / args.steps
+        kb = spread_kernel_bytes(info, b0["nvis"], nchan, 4)
+        line = {
+            "metric": "Mvis/s per Hessian apply (degrid+grid)", "value": value, "unit": "Mvis/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "snapshots_total": nsnap, "snapshots_rank0": len(mine),
+                       "batches_rank0": len(batches), "nvis_total": int(nv.item()),
+                       "us_per_snapshot_apply": 1e3 * ms_step / (nsnap / world) ,
+                       "l2": "inputs larger than L2 (plane stack %.1f GB per batch)" % (info["grid_bytes"] / 1e9),
+                       "plan": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "beta")},
+                       "parallelism": f"snapshots dealt round-robin to {world} GPU(s), no data-path collective",
+                       "one_shot_snapshot_imaging": one_shot},
+            "e2e": {"value": e2e_value, "unit": "Mvis/s", "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": img_bytes,
+                    "call": "GridderPlan.hessian(x (nsnap, nx, ny) host numpy, out=) on the bound batch plans, batch after batch"},
+            "gpu_launches": int(la.item()), "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "k_grid_runs (spreading kernel, one launch per batch of snapshots)",
+                         "achieved": kb / (phases["spread"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": kb / (phases["spread"] * 1e-3) / 1e9 / peak, "traffic": None,
+                         "kernel_ms": phases["spread"], "algorithmic_bytes_per_launch": kb,
+                         "step_algorithmic_bytes_rank0": B, "step_frac": B / (my_ms * 1e-3) / 1e9 / peak,
+                         "phases_ms_first_batch": phases,
+                         "note": "small-image workload: 1024-point transforms, W = 6 (general flush path of the run kernels)"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    for b in batches:
+        b["gp"].close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(args, cfg):
@@ -599,6 +783,8 @@ def main():
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.workload == "c5":
+        run_c5(args, cfg)
     else:
         run_ours(args, cfg)
 

@@ -113,6 +113,18 @@ int pfbg_plan_get_info(const pfbg_plan* plan, pfbg_plan_info* info);
 int pfbg_plan_set_wrange(pfbg_plan* plan, double w0, int32_t nplanes, int32_t pmirror);
 
 /*
+ * Batched snapshots (`pfb hci`: utils/stokes2im.py:635-683 makes two vis2dirty calls per 512^2 snapshot, thousands
+ * of snapshots): nbatch images of ONE geometry (nx, ny, cell, centre, sigma, W, dw — everything in the plan desc)
+ * go through one bin/sort, one launch of every kernel.  Snapshot s owns snap_np[s] planes starting at w = snap_w0[s]
+ * (host arrays; the planes of all snapshots form one stack) and the rows [row_offsets[s], row_offsets[s+1]) of the
+ * arrays given to pfbg_bind_vis_batch.  Afterwards the image arguments of pfbg_grid / pfbg_degrid / pfbg_hessian are
+ * (nbatch, nx, ny).  The plan must be created without mirror planes (pmirror = 0).
+ */
+int pfbg_plan_set_batch(pfbg_plan* plan, int32_t nbatch, const double* snap_w0, const int32_t* snap_np);
+int pfbg_bind_vis_batch(pfbg_plan* plan, const double* uvw, const double* fscale, const uint8_t* mask,
+                        int64_t nrow, int32_t nchan, const int64_t* row_offsets, uint32_t flags, void* stream);
+
+/*
  * Kernel 1: upload uvw (nrow,3) f64, fscale (nchan) f64 = freq/c, optional mask
  * (nrow,nchan) u8, compute the uv-tile / w-plane bucket of every sample and
  * sort the active samples by bucket.  Cached in the plan until re-bound.

@@ -64,6 +64,8 @@ SIGNATURES = {
     "pfbg_plan_set_wrange": (C.c_int, [_vp, _dbl, _i32, _i32]),
     "pfbg_bind_vis": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32, _vp]),
     "pfbg_bind_weights": (C.c_int, [_vp, _vp, _u32, _vp]),
+    "pfbg_plan_set_batch": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "pfbg_bind_vis_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _u32, _vp]),
     "pfbg_bin_dump": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pfbg_grid": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _u32, _vp]),
     "pfbg_grid_psf": (C.c_int, [_vp, _dbl, _dbl, _dbl, _vp, _vp, _u32, _vp]),

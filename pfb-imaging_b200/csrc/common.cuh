@@ -23,6 +23,14 @@ struct GParams {
   // stored or transformed.
   int pmirror;
   int fast_screen;  // fp32: w-screen phasors from the SFU (epsilon >= 3e-6)
+  // Batched snapshots (pfb hci: thousands of small images of one geometry, utils/stokes2im.py:635-683): nbatch
+  // images share this plan; snapshot s owns rows [row offsets], planes [snap_pbase[s], + snap_np[s]) of ONE plane
+  // stack of `nplanes` planes in total, its plane 0 sits at w = snap_w0[s].  All null / 1 for an ordinary plan.
+  int nbatch;
+  const int* row_snap;      // (nrow) snapshot of every row
+  const double* snap_w0;    // (nbatch)
+  const int* snap_pbase;    // (nbatch)
+  const int* snap_np;       // (nbatch)
 };
 
 // ---------------------------------------------------------------------------
@@ -57,15 +65,22 @@ __device__ __forceinline__ VisCoord vis_coord(const GParams& p, const double* __
   if (p.do_wgridding && c.wt < 0.0) { c.ut = -c.ut; c.vt = -c.vt; c.wt = -c.wt; c.conj = 1; }
   axis_coord(c.ut, p.pixsize_x, p.nu, p.W, c.gu, c.iu0);
   axis_coord(c.vt, p.pixsize_y, p.nv, p.W, c.gv, c.iv0);
+  double w0 = p.w0;
+  int pbase = 0, np_ = p.nplanes;
+  if (p.row_snap) {  // batched snapshots: this row's own plane block
+    const int sn = p.row_snap[row];
+    w0 = p.snap_w0[sn]; pbase = p.snap_pbase[sn]; np_ = p.snap_np[sn];
+  }
   if (p.do_wgridding) {
-    c.gw = __ddiv_rn(__dsub_rn(c.wt, p.w0), p.dw);
+    c.gw = __ddiv_rn(__dsub_rn(c.wt, w0), p.dw);
     int ip = (int)floor(__dsub_rn(c.gw, 0.5 * (double)p.W)) + 1;
-    int lo = -p.pmirror, hi = p.nplanes - p.W;
+    int lo = -p.pmirror, hi = np_ - p.W;
     c.ip0 = ip < lo ? lo : (ip > hi ? hi : ip);
   } else {
     c.gw = 0.0;
     c.ip0 = 0;
   }
+  if (pbase) { c.gw += (double)pbase; c.ip0 += pbase; }  // absolute plane units (exact: small integers)
   return c;
 }
 

@@ -30,6 +30,9 @@ struct FusedTabs {
   // (band split across GPUs: the owner transforms planes [0, P - nq), a helper GPU the last nq) pass plane-stack
   // pointers biased so that logical plane q sits at `grid + q * nu * nv` whatever slot it is stored in.
   int q0;
+  // batched snapshots: w of every plane and the image it belongs to (null: w0 + q dw, image 0)
+  const double* plane_w;
+  const int* plane_img;
 };
 
 __device__ __forceinline__ bool in_window(int n, int lo, int len, int size) {
@@ -109,8 +112,9 @@ k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict
   const int a = ip < 0 ? ip + p.nu : ip;
   for (int n = tid; n < nv; n += nthr) s[fft_pad<T>(n)] = {(T)0, (T)0};
   __syncthreads();
-  const double wq = p.w0 + q * p.dw;
+  const double wq = ft.plane_w ? ft.plane_w[q] : p.w0 + q * p.dw;
   const int64_t row = (int64_t)i * p.ny;
+  if (ft.plane_img) x += (int64_t)ft.plane_img[q] * p.nx * p.ny;  // this plane's snapshot image
   const bool vec_ok = (p.ny & 7) == 0 &&
                       (((uintptr_t)x | (uintptr_t)corr | (uintptr_t)beam) & 15) == 0;  // caller-owned device pointers
   if (vec_ok) {
@@ -349,9 +353,9 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
   }
   __syncthreads();
   fft_dif<T, 1>(s, (const cx2<T>*)ft.tw_v, ft.dv, tid, nthr);
-  const double wq = p.w0 + q * p.dw;
+  const double wq = ft.plane_w ? ft.plane_w[q] : p.w0 + q * p.dw;
   const int64_t row = (int64_t)i * p.ny;
-  double* dst = accimg + row;
+  double* dst = accimg + row + (ft.plane_img ? (int64_t)ft.plane_img[q] * p.nx * p.ny : 0);
   if ((p.ny & 7) == 0) {
     // RU groups of 4 pixels in flight per thread: the nu-table / position loads are L2 round trips
     constexpr int RU = PFBG_ROWS_INV_INFLIGHT;
@@ -407,15 +411,17 @@ k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict_
 
 // out = (acc [+ acc2]) * corr [* beam] * inv_wsum [+ eta * xin]      (acc2: the planes a helper GPU transformed)
 template <typename T>
-__global__ void k_finish_image(int64_t npix, const double* __restrict__ acc, const double* __restrict__ acc2,
-                               const T* __restrict__ corr, const T* __restrict__ beam, const T* __restrict__ xin,
-                               double inv_wsum, double eta, T* __restrict__ out) {
+__global__ void k_finish_image(int64_t npix, int64_t npix_img, const double* __restrict__ acc,
+                               const double* __restrict__ acc2, const T* __restrict__ corr, const T* __restrict__ beam,
+                               const T* __restrict__ xin, double inv_wsum, double eta, T* __restrict__ out) {
+  // npix = nbatch * npix_img: the images of a batch share the correction (and beam) of their common geometry
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= npix) return;
+  const int64_t kc = npix == npix_img ? k : k % npix_img;
   double a = acc[k];
   if (acc2) a += acc2[k];
-  double r = a * (double)corr[k];
-  if (beam) r *= (double)beam[k];
+  double r = a * (double)corr[kc];
+  if (beam) r *= (double)beam[kc];
   r *= inv_wsum;
   if (xin) r += eta * (double)xin[k];
   out[k] = (T)r;

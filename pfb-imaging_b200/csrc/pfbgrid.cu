@@ -151,6 +151,9 @@ struct pfbg_plan {
   bool bound = false, has_mask = false, has_wgt = false;
   bool beam_on_device = false;  // img_beam holds the beam of the last host-pointer Hessian call
   size_t total_bytes = 0;
+  // batched snapshots (pfbg_plan_set_batch): nbatch images of one geometry share the plane stack
+  int nbatch = 1;
+  DevBuf row_snap, snap_w0, snap_pbase, snap_np, plane_w, plane_img;
   // band split across two GPUs (pfbg_split_*): the plane transforms of the last split_nq planes run on a helper
   int split_role = 0;             // 0 none, 1 owner, 2 helper
   int split_nq = 0;
@@ -197,6 +200,8 @@ static void dev_free(pfbg_plan* pl, DevBuf& b) {
 }
 
 static inline size_t real_bytes(const pfbg_plan* pl) { return pl->precision == PFBG_F32 ? 4 : 8; }
+// pixels of the image argument of grid / degrid / hessian: nbatch images for a batched plan
+static inline size_t img_elems(const pfbg_plan* pl) { return (size_t)pl->nbatch * pl->gp.nx * pl->gp.ny; }
 
 extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   if (!pl) return PFBG_OK;
@@ -204,6 +209,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   if (pl->fft_ok) cufftDestroy(pl->fft);
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx, &pl->srt_ka, &pl->srt_kb, &pl->srt_va, &pl->srt_vb, &pl->srt_tmp,
                    &pl->xshare, &pl->partial, &pl->mailbox, &pl->x_local,
+                   &pl->row_snap, &pl->snap_w0, &pl->snap_pbase, &pl->snap_np, &pl->plane_w, &pl->plane_img,
                    &pl->recs, &pl->mvis, &pl->tw_u, &pl->tw_v, &pl->rev_u, &pl->rev_v, &pl->pos_v, &pl->pos_u, &pl->cellflags, &pl->accimg, &pl->nutab, &pl->img_in, &pl->img_out, &pl->img_beam, &pl->vis_stage, &pl->wgt_stage,
                    &pl->flag};
   for (DevBuf* b : all) dev_free(pl, *b);
@@ -256,6 +262,8 @@ static int plan_create_impl(const pfbg_plan_desc* d, int stack_planes, pfbg_plan
   GParams& g = pl->gp;
   g.nx = d->nx; g.ny = d->ny; g.nu = d->nu; g.nv = d->nv; g.W = d->W; g.nplanes = d->nplanes;
   g.nchan = 0;
+  g.nbatch = 1;
+  g.row_snap = nullptr; g.snap_w0 = nullptr; g.snap_pbase = nullptr; g.snap_np = nullptr;
   g.do_wgridding = d->do_wgridding; g.divide_by_n = d->divide_by_n;
   g.beta = d->beta; g.pixsize_x = d->pixsize_x; g.pixsize_y = d->pixsize_y;
   g.center_x = d->center_x; g.center_y = d->center_y;
@@ -510,6 +518,7 @@ extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes, i
     return fail(PFBG_ERR_ARG, "mirror planes need 0 <= pmirror <= min(32, nplanes) and w0 == dw/2");
   CK(cudaSetDevice(pl->device));
   if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split");
+  if (pl->nbatch > 1) return fail(PFBG_ERR_STATE, "plan is batched (pfbg_plan_set_batch)");
   const size_t need = (size_t)nplanes * g.nu * g.nv * 2 * real_bytes(pl);
   pl->stack_planes = nplanes;
   if (need > pl->grid.bytes) {
@@ -527,6 +536,81 @@ extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes, i
   g.pmirror = pmirror;
   pl->bound = false;
   return PFBG_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Batched snapshots: nbatch small images of ONE geometry in one launch sequence (pfb hci makes thousands of
+// 512^2 vis2dirty calls, utils/stokes2im.py:635-683; a launch sequence per snapshot is launch-latency bound).
+// The snapshots share sigma, W, dw, nshift, the correction image and the transform tables; each owns a block of
+// planes of one stack and an image slot.  Afterwards pfbg_bind_vis_batch / pfbg_grid / pfbg_degrid / pfbg_hessian take
+// and return nbatch images (nbatch, nx, ny) and the rows of all snapshots concatenated.
+// ---------------------------------------------------------------------------
+extern "C" int pfbg_plan_set_batch(pfbg_plan* pl, int32_t nbatch, const double* snap_w0, const int32_t* snap_np) {
+  if (!pl || !snap_w0 || !snap_np) return fail(PFBG_ERR_ARG, "null argument");
+  if (nbatch < 1) return fail(PFBG_ERR_ARG, "nbatch must be positive");
+  if (!pl->fused) return fail(PFBG_ERR_STATE, "batched plans need the fused plane transforms (grid too large for shared memory?)");
+  if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split");
+  GParams& g = pl->gp;
+  if (g.pmirror) return fail(PFBG_ERR_ARG, "batched plans do not use mirror planes (make the plan with pmirror = 0)");
+  CK(cudaSetDevice(pl->device));
+  CK(cudaDeviceSynchronize());
+  std::vector<int> pbase(nbatch), pimg;
+  std::vector<double> pw;
+  int64_t total = 0;
+  for (int s = 0; s < nbatch; ++s) {
+    const int np_ = snap_np[s];
+    if (np_ < (g.do_wgridding ? g.W : 1) || (!g.do_wgridding && np_ != 1))
+      return fail(PFBG_ERR_ARG, "snapshot %d: %d planes for W=%d", s, np_, g.W);
+    pbase[s] = (int)total;
+    for (int q = 0; q < np_; ++q) { pw.push_back(snap_w0[s] + q * g.dw); pimg.push_back(s); }
+    total += np_;
+  }
+  if (total > (1 << 20)) return fail(PFBG_ERR_ARG, "too many planes in one batch");
+  const size_t rb = real_bytes(pl);
+  CKRC(dev_alloc(pl, pl->grid, (size_t)total * g.nu * g.nv * 2 * rb));
+  CKRC(dev_alloc(pl, pl->snap_w0, (size_t)nbatch * 8));
+  CKRC(dev_alloc(pl, pl->snap_pbase, (size_t)nbatch * 4));
+  CKRC(dev_alloc(pl, pl->snap_np, (size_t)nbatch * 4));
+  CKRC(dev_alloc(pl, pl->plane_w, (size_t)total * 8));
+  CKRC(dev_alloc(pl, pl->plane_img, (size_t)total * 4));
+  CKRC(dev_alloc(pl, pl->accimg, (size_t)nbatch * g.nx * g.ny * sizeof(double)));
+  CK(cudaMemcpy(pl->snap_w0.p, snap_w0, (size_t)nbatch * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->snap_pbase.p, pbase.data(), (size_t)nbatch * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->snap_np.p, snap_np, (size_t)nbatch * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->plane_w.p, pw.data(), (size_t)total * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pl->plane_img.p, pimg.data(), (size_t)total * 4, cudaMemcpyHostToDevice));
+  pl->nbatch = nbatch;
+  pl->stack_planes = (int)total;
+  g.nplanes = (int)total;
+  g.nbatch = nbatch;
+  g.snap_w0 = (const double*)pl->snap_w0.p;
+  g.snap_pbase = (const int*)pl->snap_pbase.p;
+  g.snap_np = (const int*)pl->snap_np.p;
+  g.row_snap = nullptr;  // set by pfbg_bind_vis_batch
+  pl->ftabs.plane_w = (const double*)pl->plane_w.p;
+  pl->ftabs.plane_img = (const int*)pl->plane_img.p;
+  pl->bound = false;
+  return PFBG_OK;
+}
+
+// rows [row_offsets[s], row_offsets[s+1]) of uvw / mask (and later vis / wgt) belong to snapshot s
+extern "C" int pfbg_bind_vis_batch(pfbg_plan* pl, const double* uvw, const double* fscale, const uint8_t* mask,
+                                   int64_t nrow, int32_t nchan, const int64_t* row_offsets, uint32_t flags, void* stream) {
+  if (!pl || !row_offsets) return fail(PFBG_ERR_ARG, "null argument");
+  if (pl->nbatch < 1 || !pl->gp.snap_w0) return fail(PFBG_ERR_STATE, "pfbg_plan_set_batch first");
+  if (flags & PFBG_DEVICE_PTRS) return fail(PFBG_ERR_ARG, "pfbg_bind_vis_batch takes host pointers");
+  if (row_offsets[0] != 0 || row_offsets[pl->nbatch] != nrow) return fail(PFBG_ERR_ARG, "row_offsets must run from 0 to nrow");
+  CK(cudaSetDevice(pl->device));
+  std::vector<int> rs((size_t)(nrow > 0 ? nrow : 1));
+  for (int s = 0; s < pl->nbatch; ++s) {
+    if (row_offsets[s + 1] < row_offsets[s]) return fail(PFBG_ERR_ARG, "row_offsets must not decrease");
+    for (int64_t r = row_offsets[s]; r < row_offsets[s + 1]; ++r) rs[(size_t)r] = s;
+  }
+  CKRC(dev_alloc(pl, pl->row_snap, rs.size() * 4));
+  CK(cudaMemcpy(pl->row_snap.p, rs.data(), rs.size() * 4, cudaMemcpyHostToDevice));
+  pl->gp.row_snap = (const int*)pl->row_snap.p;
+  return pfbg_bind_vis(pl, uvw, fscale, mask, nrow, nchan, flags, stream);
 }
 
 extern "C" int pfbg_plan_get_info(const pfbg_plan* pl, pfbg_plan_info* info) {
@@ -1132,7 +1216,7 @@ static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, cons
   ft.q0 = q0;
   const int slot0 = pl->split_role == 2 ? g.nplanes - pl->split_nq : 0;
   C* stack = (C*)pl->grid.p - (int64_t)slot0 * g.nu * g.nv;
-  const int64_t npix = (int64_t)g.nx * g.ny;
+  const int64_t npix = (int64_t)img_elems(pl);
   CK(cudaMemsetAsync(pl->accimg.p, 0, (size_t)npix * sizeof(double), s));
   if (nq == 0) return PFBG_OK;
   const dim3 cgrid(ft.b_len / CC, nq);
@@ -1163,9 +1247,9 @@ static int run_fused_inv(pfbg_plan* pl, cudaStream_t s, const void* beam, const 
   const GParams& g = pl->gp;
   const bool owner = pl->split_role == 1;
   CKRC(run_fused_inv_acc<T>(pl, s, 0, g.nplanes - (owner ? pl->split_nq : 0), nullptr));
-  const int64_t npix = (int64_t)g.nx * g.ny;
+  const int64_t npix = (int64_t)img_elems(pl);
   if (owner) CKRC(split_wait(pl, s, 1));  // the helper's partial image (its planes) has arrived
-  k_finish_image<T><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(npix, (const double*)pl->accimg.p,
+  k_finish_image<T><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(npix, (int64_t)g.nx * g.ny, (const double*)pl->accimg.p,
                                                                 owner ? (const double*)pl->partial.p : nullptr,
                                                                 (const T*)pl->corr.p, (const T*)beam, (const T*)xin,
                                                                 inv_wsum, eta, (T*)out);
@@ -1191,6 +1275,7 @@ static int run_zero_window(pfbg_plan* pl, cudaStream_t s) {
 // image -> screened, transformed plane stack (degrid direction)
 static int image_to_planes(pfbg_plan* pl, cudaStream_t s, const void* x, const void* beam) {
   if (pl->fused) return DISPATCH(run_fused_fwd, pl, s, x, beam);
+  if (pl->nbatch > 1) return fail(PFBG_ERR_STATE, "batched plans need the fused plane transforms");
   CKRC(cufft_setup(pl));
   CKRC(DISPATCH(run_img2grid, pl, s, x, beam));
   return fft_exec(pl, s, CUFFT_FORWARD);
@@ -1199,6 +1284,7 @@ static int image_to_planes(pfbg_plan* pl, cudaStream_t s, const void* x, const v
 static int planes_to_image(pfbg_plan* pl, cudaStream_t s, const void* beam, const void* xin, double inv_wsum,
                            double eta, void* out) {
   if (pl->fused) return DISPATCH(run_fused_inv, pl, s, beam, xin, inv_wsum, eta, out);
+  if (pl->nbatch > 1) return fail(PFBG_ERR_STATE, "batched plans need the fused plane transforms");
   CKRC(cufft_setup(pl));
   CKRC(fft_exec(pl, s, CUFFT_INVERSE));
   return DISPATCH(run_grid2img, pl, s, beam, xin, inv_wsum, eta, out);
@@ -1219,7 +1305,7 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
   cudaStream_t s = (cudaStream_t)stream;
   const bool dev = flags & PFBG_DEVICE_PTRS;
   const size_t rb = real_bytes(pl);
-  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  const size_t img_bytes = img_elems(pl) * rb;
   pl->n_ev = 0;
   mark(pl, s);
   const void* dvis = vis;
@@ -1255,7 +1341,7 @@ extern "C" int pfbg_grid_psf(pfbg_plan* pl, double x0, double y0, double sign, c
   cudaStream_t s = (cudaStream_t)stream;
   const bool dev = flags & PFBG_DEVICE_PTRS;
   const size_t rb = real_bytes(pl);
-  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  const size_t img_bytes = img_elems(pl) * rb;
   pl->n_ev = 0;
   mark(pl, s);
   const void* dwgt = wgt;
@@ -1294,7 +1380,7 @@ extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const vo
   cudaStream_t s = (cudaStream_t)stream;
   const bool dev = flags & PFBG_DEVICE_PTRS;
   const size_t rb = real_bytes(pl);
-  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  const size_t img_bytes = img_elems(pl) * rb;
   const size_t vis_bytes = (size_t)pl->nvis * 2 * rb;
   pl->n_ev = 0;
   mark(pl, s);
@@ -1337,7 +1423,7 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   cudaStream_t s = (cudaStream_t)stream;
   const bool dev = flags & PFBG_DEVICE_PTRS;
   const size_t rb = real_bytes(pl);
-  const size_t img_bytes = (size_t)pl->gp.nx * pl->gp.ny * rb;
+  const size_t img_bytes = img_elems(pl) * rb;
   pl->n_ev = 0;
   mark(pl, s);
   const void *dx = x, *dbeam = beam;
@@ -1355,7 +1441,7 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
   const void* dwgt = pl->has_wgt ? pl->wgt.p : nullptr;
   if (!dev) {
     // `if not x.any(): return zeros` (operators/hessian.py:47-48), checked on the device copy
-    const int64_t npix = (int64_t)pl->gp.nx * pl->gp.ny;
+    const int64_t npix = (int64_t)img_elems(pl);
     CK(cudaMemsetAsync(pl->flag.p, 0, 4, s));
     if (pl->precision == PFBG_F32)
       k_any_nonzero<float><<<(unsigned)((npix + 255) / 256), 256, 0, s>>>((const float*)dx, npix, (int*)pl->flag.p);
@@ -1542,6 +1628,7 @@ static int split_wait(pfbg_plan* pl, cudaStream_t s, int slot) {
 extern "C" int pfbg_split_owner_init(pfbg_plan* pl, int32_t nq, pfbg_ipc_blob* blobs4) {
   if (!pl || !blobs4) return fail(PFBG_ERR_ARG, "null argument");
   if (!pl->fused) return fail(PFBG_ERR_STATE, "band split needs the fused plane transforms");
+  if (pl->nbatch > 1) return fail(PFBG_ERR_STATE, "batched plans cannot be split");
   if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is already part of a band split");
   if (nq < 1 || nq >= pl->gp.nplanes) return fail(PFBG_ERR_ARG, "nq=%d outside [1, nplanes)", nq);
   CK(cudaSetDevice(pl->device));

@@ -329,3 +329,29 @@ def make_plan(
         fast_screen=int(precision == "single" and do_wgridding and epsilon >= FAST_SCREEN_EPS
                         and os.environ.get("PFBG_FAST_SCREEN", "1") != "0"),
     )
+
+
+def make_batch_plan(wranges, *, nvis_per_snapshot=0, **kw):
+    """Plan shared by a batch of snapshots of ONE image geometry (pfb hci, utils/stokes2im.py:635-683).
+
+    `wranges`: per snapshot ``(wmin, wmax)`` of ``|w| f / c`` (see :func:`w_range`).  sigma, W, beta and the plane
+    spacing come from :func:`make_plan` for the widest snapshot; every snapshot then gets its own block of planes,
+    placed like the planes of a single plan without mirroring: ``ceil((wmax - wmin) / dw) + W`` planes centred on
+    its w-range.  Returns ``(plan, snap_w0, snap_np)``; ``plan.nplanes`` is the total."""
+    wr = np.asarray(wranges, dtype=np.float64).reshape(-1, 2)
+    if wr.shape[0] == 0:
+        raise ValueError("a batch needs at least one snapshot")
+    span = wr[:, 1] - wr[:, 0]
+    k = int(np.argmax(span))
+    kw = dict(kw)
+    kw["mirror"] = False
+    plan = make_plan(wmin=float(wr[k, 0]), wmax=float(wr[k, 1]), nvis=int(nvis_per_snapshot), **kw)
+    W, dw = plan.W, plan.dw
+    if plan.do_wgridding:
+        npl = np.where(span > 0, np.ceil(span / dw).astype(np.int64) + W, W).astype(np.int32)
+        w0 = 0.5 * (wr[:, 0] + wr[:, 1]) - 0.5 * (npl - 1) * dw
+    else:
+        npl = np.ones(wr.shape[0], dtype=np.int32)
+        w0 = np.zeros(wr.shape[0])
+    plan.nplanes_std = int(npl.sum())
+    return plan, np.ascontiguousarray(w0, dtype=np.float64), np.ascontiguousarray(npl, dtype=np.int32)

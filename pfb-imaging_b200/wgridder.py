@@ -15,7 +15,7 @@ import weakref
 import numpy as np
 
 from . import _lib
-from .plan import LIGHTSPEED, Plan, make_plan, w_range
+from .plan import LIGHTSPEED, Plan, make_batch_plan, make_plan, w_range
 
 _PREC = {"single": _lib.PFBG_F32, "double": _lib.PFBG_F64}
 _RDT = {"single": np.float32, "double": np.float64}
@@ -74,6 +74,7 @@ class GridderPlan:
         d, self._keep = _plan_desc(plan, self.device)
         _lib.check(self._lib.pfbg_plan_create(C.byref(d), C.byref(self._h)))
         self.nrow = self.nchan = 0
+        self.nbatch = 0  # > 0: batched snapshots, image arguments are (nbatch, nx, ny)
         self.rdt = _RDT[plan.precision]
         self.cdt = _CDT[plan.precision]
 
@@ -116,6 +117,45 @@ class GridderPlan:
         self.nrow, self.nchan = nrow, nchan
         return self
 
+    # -- batched snapshots (include/pfbgrid.h "Batched snapshots") --------------------------------------------
+    def set_batch(self, snap_w0, snap_np):
+        """Turn this plan into a batch of len(snap_w0) snapshots sharing its geometry (plan.make_batch_plan)."""
+        w0 = np.ascontiguousarray(snap_w0, dtype=np.float64)
+        npl = np.ascontiguousarray(snap_np, dtype=np.int32)
+        if w0.ndim != 1 or w0.shape != npl.shape or w0.size == 0:
+            raise ValueError("snap_w0 / snap_np must be 1-D arrays of one length")
+        _lib.check(self._lib.pfbg_plan_set_batch(self._h, w0.size, _ptr(w0), _ptr(npl)))
+        self.nbatch = int(w0.size)
+        return self
+
+    def bind_batch(self, uvw, freq, row_offsets, mask=None, stream=None):
+        """Bind the rows of all snapshots, concatenated; rows [row_offsets[s], row_offsets[s+1]) are snapshot s."""
+        if not self.nbatch:
+            raise RuntimeError("set_batch first")
+        self._beam_fp = None
+        uvw = np.ascontiguousarray(uvw, dtype=np.float64)
+        freq = np.ascontiguousarray(freq, dtype=np.float64)
+        ro = np.ascontiguousarray(row_offsets, dtype=np.int64)
+        if uvw.ndim != 2 or uvw.shape[1] != 3:
+            raise ValueError("uvw must have shape (nrow, 3)")
+        if ro.shape != (self.nbatch + 1,):
+            raise ValueError(f"row_offsets must have {self.nbatch + 1} entries")
+        nrow, nchan = uvw.shape[0], freq.size
+        fscale = np.ascontiguousarray(freq / LIGHTSPEED)
+        if mask is not None:
+            mask = np.asarray(mask)
+            if mask.shape != (nrow, nchan):
+                raise ValueError(f"mask shape {mask.shape} != ({nrow}, {nchan})")
+            mask = np.ascontiguousarray(mask != 0 if mask.dtype != np.uint8 else mask, dtype=np.uint8)
+        _lib.check(self._lib.pfbg_bind_vis_batch(self._h, _ptr(uvw), _ptr(fscale), _ptr(mask), nrow, nchan, _ptr(ro),
+                                                 _lib.HOST_PTRS, stream))
+        self.nrow, self.nchan = nrow, nchan
+        return self
+
+    @property
+    def image_shape(self):
+        return (self.nbatch, self.plan.nx, self.plan.ny) if self.nbatch else (self.plan.nx, self.plan.ny)
+
     def bind_weights(self, wgt, stream=None):
         if wgt is not None:
             wgt = self._check_wgt(wgt)
@@ -150,8 +190,8 @@ class GridderPlan:
 
     def _check_img(self, x, name):
         x = np.asarray(x)
-        if x.shape != (self.plan.nx, self.plan.ny):
-            raise ValueError(f"{name} shape {x.shape} != ({self.plan.nx}, {self.plan.ny})")
+        if x.shape != self.image_shape:
+            raise ValueError(f"{name} shape {x.shape} != {self.image_shape}")
         if x.dtype != self.rdt:
             raise TypeError(f"{name} dtype {x.dtype} does not match precision '{self.plan.precision}'")
         return np.ascontiguousarray(x)
@@ -192,9 +232,9 @@ class GridderPlan:
 
     def _out_img(self, arr, name):
         if arr is None:
-            return np.empty((self.plan.nx, self.plan.ny), dtype=self.rdt)
-        if not isinstance(arr, np.ndarray) or arr.shape != (self.plan.nx, self.plan.ny) or arr.dtype != self.rdt:
-            raise ValueError(f"`{name}` must be a ({self.plan.nx}, {self.plan.ny}) {self.rdt.__name__} array")
+            return np.empty(self.image_shape, dtype=self.rdt)
+        if not isinstance(arr, np.ndarray) or arr.shape != self.image_shape or arr.dtype != self.rdt:
+            raise ValueError(f"`{name}` must be a {self.image_shape} {self.rdt.__name__} array")
         if not arr.flags.writeable:
             raise ValueError(f"`{name}` is read-only")
         return arr
@@ -520,3 +560,84 @@ def dirty2vis(*, uvw, freq, dirty, wgt=None, mask=None, pixsize_x, pixsize_y, ce
                   flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=divide_by_n,
                   sigma_min=sigma_min, sigma_max=sigma_max, precision=prec, mask=mask, pooled=True) as gp:
         return gp.degrid(dirty, wgt=wgt, vis=vis)
+
+
+# ---------------------------------------------------------------------------
+# batched snapshots: `pfb hci` images thousands of small snapshots, two vis2dirty calls each
+# (utils/stokes2im.py:635-683: residual + PSF, sigma_min = min_padding = 2, divide_by_n = True).  One launch
+# sequence per snapshot is launch-latency bound (1.24 ms per pooled call against ~10 us of work); a batch goes
+# through ONE bin / sort and one launch of every kernel.
+# ---------------------------------------------------------------------------
+def batch_plan_for(uvw_list, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
+                   flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True, sigma_min=1.1,
+                   sigma_max=2.6, precision="double", mask_list=None, device=None, **force) -> GridderPlan:
+    """One plan for the snapshots `uvw_list` (each (nrow_s, 3)) of a common geometry, bound and binned."""
+    freq = np.asarray(freq, dtype=np.float64)
+    wr = [w_range(u, freq) if do_wgridding else (0.0, 0.0) for u in uvw_list]
+    nrow_max = max(int(np.asarray(u).shape[0]) for u in uvw_list)
+    p, w0, npl = make_batch_plan(wr, nvis_per_snapshot=nrow_max * freq.size, nx=npix_x, ny=npix_y, pixsize_x=pixsize_x,
+                                 pixsize_y=pixsize_y, center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u,
+                                 flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=divide_by_n,
+                                 sigma_min=sigma_min, sigma_max=sigma_max, precision=precision, **force)
+    first = Plan(**{**p.__dict__, "nplanes": int(p.W if do_wgridding else 1)})  # the stack is sized by set_batch
+    gp = GridderPlan(first, device=device)
+    try:
+        gp.set_batch(w0, npl)
+        p.nplanes = int(npl.sum())
+        gp.plan = p
+        ro = np.concatenate([[0], np.cumsum([np.asarray(u).shape[0] for u in uvw_list])]).astype(np.int64)
+        uvw = np.concatenate([np.asarray(u, dtype=np.float64) for u in uvw_list], axis=0)
+        mask = None if mask_list is None else np.concatenate([np.asarray(m) for m in mask_list], axis=0)
+        gp.bind_batch(uvw, freq, ro, mask)
+        gp.row_offsets = ro
+    except Exception:
+        gp.close()
+        raise
+    return gp
+
+
+def vis2dirty_batch(*, uvw, freq, vis, wgt=None, mask=None, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0,
+                    center_y=0.0, epsilon, flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
+                    nthreads=1, sigma_min=1.1, sigma_max=2.6, double_precision_accumulation=False, verbosity=0,
+                    dirty=None, extra_vis=()):
+    """``vis2dirty`` for a list of snapshots of one geometry: `uvw`, `vis`, `wgt`, `mask` are lists (one entry per
+    snapshot, `freq` is shared); returns ``(nsnap, npix_x, npix_y)``.  `extra_vis`: further lists of visibilities
+    gridded with the same binding (the PSF visibilities of stokes2im.py:660-683); then a tuple of cubes comes back."""
+    nsnap = len(uvw)
+    prec = _precision_of(np.asarray(vis[0]).dtype, "vis")
+    gp = batch_plan_for(uvw, freq, npix_x=npix_x, npix_y=npix_y, pixsize_x=pixsize_x, pixsize_y=pixsize_y,
+                        center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w,
+                        do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min, sigma_max=sigma_max,
+                        precision=prec, mask_list=mask)
+    try:
+        w = None if wgt is None else np.concatenate([np.asarray(a) for a in wgt], axis=0)
+        outs = []
+        for k, vl in enumerate((vis,) + tuple(extra_vis)):
+            if len(vl) != nsnap:
+                raise ValueError("every visibility list needs one entry per snapshot")
+            v = np.concatenate([np.asarray(a) for a in vl], axis=0)
+            outs.append(gp.grid(v, wgt=w, dirty=dirty if k == 0 else None))
+        return outs[0] if not extra_vis else tuple(outs)
+    finally:
+        gp.close()
+
+
+def dirty2vis_batch(*, uvw, freq, dirty, wgt=None, mask=None, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
+                    flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True, nthreads=1,
+                    sigma_min=1.1, sigma_max=2.6, verbosity=0):
+    """``dirty2vis`` for a cube of snapshot images ``(nsnap, nx, ny)``: returns the list of per-snapshot visibilities."""
+    dirty = np.asarray(dirty)
+    if dirty.ndim != 3 or dirty.shape[0] != len(uvw):
+        raise ValueError("dirty must be (nsnap, nx, ny) with one image per snapshot")
+    prec = _precision_of(dirty.dtype, "dirty")
+    gp = batch_plan_for(uvw, freq, npix_x=dirty.shape[1], npix_y=dirty.shape[2], pixsize_x=pixsize_x, pixsize_y=pixsize_y,
+                        center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w,
+                        do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min, sigma_max=sigma_max,
+                        precision=prec, mask_list=mask)
+    try:
+        w = None if wgt is None else np.concatenate([np.asarray(a) for a in wgt], axis=0)
+        v = gp.degrid(dirty, wgt=w)
+        ro = gp.row_offsets
+        return [v[ro[s]:ro[s + 1]] for s in range(len(uvw))]
+    finally:
+        gp.close()

@@ -76,3 +76,19 @@ def test_w_range():
     assert np.isclose(lo, 3.0 * 1e9 / 299792458.0) and np.isclose(hi, 5.0 * 2e9 / 299792458.0)
     lo2, hi2 = w_range(uvw, f, -1.0)
     assert (lo2, hi2) == (lo, hi)
+
+
+def test_batch_plan_gives_every_snapshot_its_own_plane_block():
+    from pfb_imaging_b200.plan import make_batch_plan
+
+    wr = [(0.0, 10.0), (5.0, 400.0), (100.0, 100.0), (0.5, 60.0)]
+    plan, w0, npl = make_batch_plan(wr, nx=512, ny=512, pixsize_x=2e-5, pixsize_y=2e-5, epsilon=1e-4, precision="single",
+                                    sigma_min=2.0, sigma_max=2.6, divide_by_n=True)
+    assert plan.pmirror == 0 and plan.sigma >= 2.0
+    assert npl.dtype == np.int32 and w0.shape == (4,) and npl[2] == plan.W
+    for (lo, hi), a, n in zip(wr, w0, npl):
+        assert n >= plan.W and a <= lo + 1e-9 and a + (n - 1) * plan.dw >= hi - 1e-9
+        # the lowest sample's first plane is >= 0 and the highest sample's last plane is < n
+        assert np.floor((lo - a) / plan.dw - plan.W / 2) + 1 >= 0
+        assert np.floor((hi - a) / plan.dw - plan.W / 2) + 1 + plan.W <= n
+    assert plan.nplanes_std == int(npl.sum())
