@@ -570,8 +570,10 @@ def dirty2vis(*, uvw, freq, dirty, wgt=None, mask=None, pixsize_x, pixsize_y, ce
 # ---------------------------------------------------------------------------
 def batch_plan_for(uvw_list, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
                    flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True, sigma_min=1.1,
-                   sigma_max=2.6, precision="double", mask_list=None, device=None, **force) -> GridderPlan:
-    """One plan for the snapshots `uvw_list` (each (nrow_s, 3)) of a common geometry, bound and binned."""
+                   sigma_max=2.6, precision="double", mask_list=None, device=None, pooled=False, **force) -> GridderPlan:
+    """One plan for the snapshots `uvw_list` (each (nrow_s, 3)) of a common geometry, bound and binned.
+    ``pooled=True`` returns a context manager that hands the plan back to the pool of the one-shot calls: the next
+    batch of the same geometry re-uses its device buffers and tables (hci images chunk after chunk)."""
     freq = np.asarray(freq, dtype=np.float64)
     wr = [w_range(u, freq) if do_wgridding else (0.0, 0.0) for u in uvw_list]
     nrow_max = max(int(np.asarray(u).shape[0]) for u in uvw_list)
@@ -579,8 +581,14 @@ def batch_plan_for(uvw_list, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, cent
                                  pixsize_y=pixsize_y, center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u,
                                  flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding, divide_by_n=divide_by_n,
                                  sigma_min=sigma_min, sigma_max=sigma_max, precision=precision, **force)
-    first = Plan(**{**p.__dict__, "nplanes": int(p.W if do_wgridding else 1)})  # the stack is sized by set_batch
-    gp = GridderPlan(first, device=device)
+    dev = current_device() if device is None else int(device)
+    key = ("batch",) + _pool_key(p, dev)
+    free = _POOL.get(key) if pooled and _POOL_MAX > 0 else None
+    if free:  # same geometry, sigma, W: only the plane blocks and the bound samples change
+        gp = free.pop()
+    else:
+        first = Plan(**{**p.__dict__, "nplanes": int(p.W if do_wgridding else 1)})  # the stack is sized by set_batch
+        gp = GridderPlan(first, device=dev)
     try:
         gp.set_batch(w0, npl)
         p.nplanes = int(npl.sum())
@@ -593,7 +601,7 @@ def batch_plan_for(uvw_list, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, cent
     except Exception:
         gp.close()
         raise
-    return gp
+    return _Pooled(gp, key) if pooled and _POOL_MAX > 0 else gp
 
 
 def vis2dirty_batch(*, uvw, freq, vis, wgt=None, mask=None, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0,
@@ -608,18 +616,16 @@ def vis2dirty_batch(*, uvw, freq, vis, wgt=None, mask=None, npix_x, npix_y, pixs
     gp = batch_plan_for(uvw, freq, npix_x=npix_x, npix_y=npix_y, pixsize_x=pixsize_x, pixsize_y=pixsize_y,
                         center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w,
                         do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min, sigma_max=sigma_max,
-                        precision=prec, mask_list=mask)
-    try:
+                        precision=prec, mask_list=mask, pooled=True)
+    with gp as g:
         w = None if wgt is None else np.concatenate([np.asarray(a) for a in wgt], axis=0)
         outs = []
         for k, vl in enumerate((vis,) + tuple(extra_vis)):
             if len(vl) != nsnap:
                 raise ValueError("every visibility list needs one entry per snapshot")
             v = np.concatenate([np.asarray(a) for a in vl], axis=0)
-            outs.append(gp.grid(v, wgt=w, dirty=dirty if k == 0 else None))
+            outs.append(g.grid(v, wgt=w, dirty=dirty if k == 0 else None))
         return outs[0] if not extra_vis else tuple(outs)
-    finally:
-        gp.close()
 
 
 def dirty2vis_batch(*, uvw, freq, dirty, wgt=None, mask=None, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
@@ -633,11 +639,9 @@ def dirty2vis_batch(*, uvw, freq, dirty, wgt=None, mask=None, pixsize_x, pixsize
     gp = batch_plan_for(uvw, freq, npix_x=dirty.shape[1], npix_y=dirty.shape[2], pixsize_x=pixsize_x, pixsize_y=pixsize_y,
                         center_x=center_x, center_y=center_y, epsilon=epsilon, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w,
                         do_wgridding=do_wgridding, divide_by_n=divide_by_n, sigma_min=sigma_min, sigma_max=sigma_max,
-                        precision=prec, mask_list=mask)
-    try:
+                        precision=prec, mask_list=mask, pooled=True)
+    with gp as g:
         w = None if wgt is None else np.concatenate([np.asarray(a) for a in wgt], axis=0)
-        v = gp.degrid(dirty, wgt=w)
-        ro = gp.row_offsets
+        v = g.degrid(dirty, wgt=w)
+        ro = g.row_offsets
         return [v[ro[s]:ro[s + 1]] for s in range(len(uvw))]
-    finally:
-        gp.close()
