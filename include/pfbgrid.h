@@ -279,6 +279,14 @@ int pfbg_plan_get_window(const pfbg_plan* plan, int32_t* window4);
 int pfbg_debug_fft1d(int32_t precision, int32_t device, int32_t n, int32_t batch, const void* in,
                      void* out, int32_t mode, int32_t inverse);
 
+/*
+ * Unit-test hook for the fp32 pair engine (csrc/fft2.cuh) behind the TMA-fed column transforms: `batch` groups of
+ * 2 np interleaved transforms of length n, in / out (batch, 2 np, n) complex64 on the host.  aos != 0: the first
+ * stage reads the array-of-structures order the TMA unit delivers.
+ */
+int pfbg_debug_fft2(int32_t device, int32_t n, int32_t np, int32_t batch, const void* in, void* out,
+                    int32_t inverse, int32_t aos);
+
 #ifdef __cplusplus
 }
 #endif

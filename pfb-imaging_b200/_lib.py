@@ -84,6 +84,7 @@ SIGNATURES = {
     "pfbg_conv_set_kernel": (C.c_int, [_vp, _vp, _i32, _u32, _vp]),
     "pfbg_conv_apply": (C.c_int, [_vp, _vp, _vp, _dbl, _vp, _u32, _vp]),
     "pfbg_debug_fft1d": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32]),
+    "pfbg_debug_fft2": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32]),
     "pfbg_counts_to_weights": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32,
                                          _dbl, _dbl, _dbl, _dbl, _dbl, _u32, _vp]),
     "pfbg_l2_reweight": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _vp, _vp, _u32, _vp]),
@@ -120,7 +121,8 @@ _lib = None
 # unit takes ~2 minutes to compile, the others seconds)
 _UNITS = {
     "pfbgrid.cu": ["common.cuh", "fft.cuh", "fused_fft.cuh", "kernels.cuh", "psfconv.cuh", "runs.cuh", "weighting.cuh",
-                   "../../include/pfbgrid.h"],
+                   "cols2_api.h", "../../include/pfbgrid.h"],
+    "colsfft.cu": ["fft.cuh", "fft2.cuh", "cols2.cuh", "cols2_api.h"],
     "pfbsara.cu": ["sara.cuh", "../../include/pfbsara.h", "../../include/pfbgrid.h"],
 }
 

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "runs.cuh"
 #include "fused_fft.cuh"
+#include "cols2_api.h"
 #include "weighting.cuh"
 
 // ---------------------------------------------------------------------------
@@ -143,6 +144,7 @@ struct pfbg_plan {
   FusedTabs ftabs{};
   bool fused = false;          // tables built and sizes fit shared memory
   int col_c = 4;               // columns per CTA in the column passes
+  bool cols2 = false;          // fp32: TMA-fed pair-engine column kernels (cols2.cuh) serve this geometry
   cufftHandle fft = 0;
   int fft_batch = 1;           // planes per cuFFT execution (a divisor of nplanes; bounds the work area)
   bool fft_ok = false;
@@ -457,6 +459,11 @@ static int fused_setup_t(pfbg_plan* pl) {
   CK(cudaFuncSetAttribute(k_cols_inv<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   CK(cudaFuncSetAttribute(k_cols_fwd<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   CK(cudaFuncSetAttribute(k_cols_inv<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  pl->cols2 = false;
+  if constexpr (sizeof(T) == 4) {
+    const char* ce = getenv("PFBG_COLS");  // PFBG_COLS=old: the single-buffer column kernels of fused_fft.cuh
+    pl->cols2 = !(ce && strcmp(ce, "old") == 0) && pl->col_c == full_c && cols2_supported(g.nu, g.nv, g.nx, du);
+  }
   pl->fused = true;
   return PFBG_OK;
 }
@@ -1171,6 +1178,27 @@ static int row_threads(int n, int cap) {
   return best;
 }
 
+// TMA-fed pair-engine column pass (cols2.cuh) over logical planes [ft.q0, ft.q0 + nq): loads come from the local
+// stack (slot 0 = logical plane slot0), results go to `out_biased` (logical plane q at out_biased + q nu nv)
+static int run_cols2(pfbg_plan* pl, cudaStream_t s, const FusedTabs& ft, int slot0, int nq, bool inverse,
+                     float2* out_biased) {
+  const GParams& g = pl->gp;
+  Cols2Args a;
+  a.du = ft.du;
+  a.tw_u = (const float2*)ft.tw_u;
+  a.pos_u = ft.pos_u;
+  a.nu = g.nu; a.nv = g.nv; a.nx = g.nx;
+  a.a_lo = ft.a_lo; a.a_len = ft.a_len; a.b_lo = ft.b_lo; a.b_len = ft.b_len;
+  a.q0 = ft.q0; a.nq = nq; a.slot0 = slot0;
+  a.inverse = inverse ? 1 : 0;
+  a.debug = 0; a.dbg_stack = nullptr;
+  const char* what = "";
+  cudaError_t e = cols2_launch(a, (const float2*)pl->grid.p, pl->stack_planes, out_biased, s, &what);
+  if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  LAUNCHED();
+  return PFBG_OK;
+}
+
 // Plane subset of the fused transforms: logical planes [q0, q0 + nq).  `stack` is the local plane stack biased so
 // that logical plane q sits at stack + q * nu * nv (a helper of a split band stores plane q0 in slot 0); `remote`
 // (optional) is the peer-mapped stack of the band's owner: the forward column pass then writes there and the
@@ -1198,6 +1226,9 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
   const dim3 cgrid(ft.b_len / CC, nq);
   const size_t csm = fft_smem_bytes<T>(g.nu * CC);
   C* dst = remote ? (C*)remote : stack;
+  if constexpr (sizeof(T) == 4) {
+    if (pl->cols2) return run_cols2(pl, s, ft, slot0, nq, false, (float2*)dst);
+  }
   if (CC == 4) k_cols_fwd<T, 4><<<cgrid, 512, csm, s>>>(g, ft, stack, dst);
   else if (CC == 2) k_cols_fwd<T, 2><<<cgrid, 512, csm, s>>>(g, ft, stack, dst);
   else k_cols_fwd<T, 1><<<cgrid, 512, csm, s>>>(g, ft, stack, dst);
@@ -1222,11 +1253,20 @@ static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, cons
   const dim3 cgrid(ft.b_len / CC, nq);
   const size_t csm = fft_smem_bytes<T>(g.nu * CC);
   const C* src = remote ? (const C*)remote : stack;
-  if (CC == 4) k_cols_inv<T, 4><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
-  else if (CC == 2) k_cols_inv<T, 2><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
-  else k_cols_inv<T, 1><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
-  LAUNCHED();
-  CK(cudaGetLastError());
+  bool done = false;
+  if constexpr (sizeof(T) == 4) {
+    if (pl->cols2 && !remote) {  // (a helper's loads from the owner's peer-mapped stack stay on the old kernel)
+      CKRC(run_cols2(pl, s, ft, slot0, nq, true, (float2*)stack));
+      done = true;
+    }
+  }
+  if (!done) {
+    if (CC == 4) k_cols_inv<T, 4><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
+    else if (CC == 2) k_cols_inv<T, 2><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
+    else k_cols_inv<T, 1><<<cgrid, 512, csm, s>>>(g, ft, src, stack);
+    LAUNCHED();
+    CK(cudaGetLastError());
+  }
   auto k_rows = &k_rows_inv<T, false>;
   if constexpr (sizeof(T) == 4) {
     if (g.fast_screen) k_rows = &k_rows_inv<T, true>;
@@ -2012,6 +2052,35 @@ extern "C" int pfbg_debug_fft1d(int32_t precision, int32_t device, int32_t n, in
   CK(cudaSetDevice(device));
   return precision == PFBG_F32 ? debug_fft_t<float>(n, batch, in, out, mode, inverse)
                                : debug_fft_t<double>(n, batch, in, out, mode, inverse);
+}
+
+extern "C" int pfbg_debug_fft2(int32_t device, int32_t n, int32_t np, int32_t batch, const void* in, void* out,
+                               int32_t inverse, int32_t aos) {
+  if (!in || !out || n < 2 || batch < 1) return fail(PFBG_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(device));
+  FftDesc d;
+  if (!factorize(n, d, 16)) return fail(PFBG_ERR_ARG, "n=%d is not 2^a 3^b 5^c 7^d 11^e", n);
+  std::vector<cx2<float>> tw(n);
+  for (int t = 0; t < n; ++t) {
+    double ang = -2.0 * M_PI * (double)t / (double)n;
+    tw[t].x = (float)cos(ang);
+    tw[t].y = (float)sin(ang);
+  }
+  std::vector<int> rev, pos;
+  digit_tables(d, rev, pos);
+  const size_t bytes = (size_t)n * 8 * 2 * np * batch;
+  TmpBufs t;
+  void *dtw, *drev, *din, *dout;
+  CKRC(t.get(&dtw, tw.data(), (size_t)n * 8, false, true, 0));
+  CKRC(t.get(&drev, rev.data(), (size_t)n * 4, false, true, 0));
+  CKRC(t.get(&din, in, bytes, false, true, 0));
+  CKRC(t.get(&dout, out, bytes, false, false, 0));
+  cudaError_t e = fft2_debug_launch(d, np, (const float2*)dtw, (const int*)drev, (const float2*)din, (float2*)dout, batch,
+                                    inverse, aos);
+  if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "fft2 debug launch: %s", cudaGetErrorString(e));
+  LAUNCHED();
+  CK(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+  return PFBG_OK;
 }
 
 // ---------------------------------------------------------------------------
