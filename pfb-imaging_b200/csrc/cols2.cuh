@@ -25,7 +25,8 @@
 #include "fft2.cuh"
 #include "cols2_api.h"
 
-#define COLS2_THREADS 384
+#define COLS2_THREADS 384      // radix-16 stages, 128 registers per thread
+#define COLS2_THREADS_R8 768   // radix-8 stages (Cols2Args.du = the radix-8 factorisation): <= 85 registers, 24 warps
 #define COLS2_BOX_BIG 256
 #define COLS2_BOX_SMALL 32
 
@@ -88,7 +89,8 @@ __device__ __forceinline__ void cols2_load_rows(float4* buf, const CUtensorMap* 
   for (; r < r1; r += COLS2_BOX_SMALL) tma_load_2d(buf + 2 * r, msmall, 2 * col, rowbase + r, bar);
 }
 
-__global__ void __launch_bounds__(COLS2_THREADS, 1)
+template <bool R8>
+__global__ void __launch_bounds__(R8 ? COLS2_THREADS_R8 : COLS2_THREADS, 1)
 k_cols2(const __grid_constant__ CUtensorMap mbig, const __grid_constant__ CUtensorMap msmall,
         const __grid_constant__ Cols2Args a, float2* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem_raw1k[];
@@ -98,9 +100,10 @@ k_cols2(const __grid_constant__ CUtensorMap mbig, const __grid_constant__ CUtens
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nu * 32);
   float2* twtab = reinterpret_cast<float2*>(bar + 8);                                    // two-level twiddle table
   unsigned short* pos16 = reinterpret_cast<unsigned short*>(twtab + p2_tw_entries(nu));  // k -> position, nu entries
+  constexpr int NTHR = R8 ? COLS2_THREADS_R8 : COLS2_THREADS;
   const int tid = threadIdx.x;
-  const P2Tw tw = p2_tw_fill(twtab, a.tw_u, nu, tid, COLS2_THREADS);
-  for (int k = tid; k < nu; k += COLS2_THREADS) pos16[k] = (unsigned short)a.pos_u[k];
+  const P2Tw tw = p2_tw_fill(twtab, a.tw_u, nu, tid, NTHR);
+  for (int k = tid; k < nu; k += NTHR) pos16[k] = (unsigned short)a.pos_u[k];
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_proxy_async();
@@ -139,9 +142,9 @@ k_cols2(const __grid_constant__ CUtensorMap mbig, const __grid_constant__ CUtens
     if (a.debug & 1) {
       // debugging aid (PFBG_COLS2_DEBUG=1): plain copies instead of the TMA unit
       const float2* g = a.dbg_stack + ((int64_t)(a.q0 + q - a.slot0) * nu) * a.nv + col;
-      for (int e = s0a * 2 + tid; e < s1a * 2; e += COLS2_THREADS)
+      for (int e = s0a * 2 + tid; e < s1a * 2; e += NTHR)
         s[e] = *reinterpret_cast<const float4*>(g + (int64_t)(e >> 1) * a.nv + 2 * (e & 1));
-      for (int e = s0b * 2 + tid; e < s1b * 2; e += COLS2_THREADS)
+      for (int e = s0b * 2 + tid; e < s1b * 2; e += NTHR)
         s[e] = *reinterpret_cast<const float4*>(g + (int64_t)(e >> 1) * a.nv + 2 * (e & 1));
       if (tid == 0) mbar_arrive(bar);
     } else if (tid == 0) {
@@ -152,22 +155,22 @@ k_cols2(const __grid_constant__ CUtensorMap mbig, const __grid_constant__ CUtens
     }
     if (s1b > s0b) {  // two segments: the gap between them ([s1a, s0b) forward, [s1b, s0a) inverse)
       const int z0 = !a.inverse ? s1a : s1b, z1 = !a.inverse ? s0b : s0a;
-      for (int e = 2 * z0 + tid; e < 2 * z1; e += COLS2_THREADS) s[e] = z;
+      for (int e = 2 * z0 + tid; e < 2 * z1; e += NTHR) s[e] = z;
     } else {  // one segment [s0a, s1a): rows [0, s0a) and [s1a, nu)
-      for (int e = tid; e < 2 * s0a; e += COLS2_THREADS) s[e] = z;
-      for (int e = 2 * s1a + tid; e < 2 * nu; e += COLS2_THREADS) s[e] = z;
+      for (int e = tid; e < 2 * s0a; e += NTHR) s[e] = z;
+      for (int e = 2 * s1a + tid; e < 2 * nu; e += NTHR) s[e] = z;
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     __syncthreads();  // everybody's zero rows are in place
-    p2_fft_dif<2>(s, tw, a.du, inmode, tid, COLS2_THREADS);
+    p2_fft_dif<2, R8 ? 8 : 16>(s, tw, a.du, inmode, tid, NTHR);
     // ---- write-back: one 32-byte sector per row
     float2* go = out + (int64_t)(a.q0 + q) * nu * a.nv + col;  // `out` is biased: logical plane q at out + q nu nv
     if (a.debug & 2) {
       // debugging aid: no write-back
     } else if (!a.inverse) {
 #pragma unroll 4
-      for (int t = tid; t < a.a_len; t += COLS2_THREADS) {  // rows of the active window
+      for (int t = tid; t < a.a_len; t += NTHR) {  // rows of the active window
         int k = a.a_lo + t;
         if (k >= nu) k -= nu;
         const int e = 2 * pos16[k];
@@ -178,7 +181,7 @@ k_cols2(const __grid_constant__ CUtensorMap mbig, const __grid_constant__ CUtens
       }
     } else {
 #pragma unroll 4
-      for (int t = tid; t < a.nx; t += COLS2_THREADS) {  // the nx image rows; swap back: the transform ran on (im, re)
+      for (int t = tid; t < a.nx; t += NTHR) {  // the nx image rows; swap back: the transform ran on (im, re)
         const int k = t < hx ? t : t + (nu - a.nx);
         const int e = 2 * pos16[k];
         const float4 v0 = s[sw2(e)], v1 = s[sw2(e + 1)];  // {im0, im1, re0, re1}

@@ -219,9 +219,13 @@ __device__ __forceinline__ void p2_store(float4* __restrict__ s, int chunk, pc2 
 // elements in place: the 8 chunks of a 128-byte line trade places, and with M * NP a multiple of 8 those are 8
 // consecutive work items, i.e. lanes of ONE warp — a __syncwarp() between its loads and stores is all the ordering
 // needed (every warp iterates the same number of times; `nthr` is a multiple of 32).
-template <int R, int NP, int MODE, bool DENSE>
+// VAR: 0 = DIF stage (butterfly, then output m *= W_L^{k m}), 1 = DIF stage with DENSE input, 2 = DIT stage (input m
+// *= W_L^{k m}, then butterfly)
+enum { P2_DIF = 0, P2_DIF_DENSE = 1, P2_DIT = 2 };
+template <int R, int NP, int MODE, int VAR>
 __device__ __forceinline__ void p2_stage(float4* __restrict__ s, const P2Tw& tw, int N, int L, int swap,
                                          int tid, int nthr) {
+  constexpr bool DENSE = VAR == P2_DIF_DENSE, DIT = VAR == P2_DIT;
   constexpr int LGNP = NP == 1 ? 0 : (NP == 2 ? 1 : 2);
   const int M = L / R, MC = M * NP;
   const int tstride = N / L;
@@ -266,8 +270,9 @@ __device__ __forceinline__ void p2_stage(float4* __restrict__ s, const P2Tw& tw,
       for (int m = 0; m < R; ++m) x[m] = p2_load(s, sw2(e0 + m * MC));
     }
     if (!act) continue;
+    if (DIT && M > 1) ptwiddle<R>(x, w1);
     PDft<R>::run(x);
-    if (M > 1) ptwiddle<R>(x, w1);
+    if (!DIT && M > 1) ptwiddle<R>(x, w1);
     if constexpr (MODE == 1) {
 #pragma unroll
       for (int m = 0; m < R; ++m) p2_store(s, base + m * MC, x[m]);
@@ -284,31 +289,34 @@ __device__ __forceinline__ void p2_stage(float4* __restrict__ s, const P2Tw& tw,
   }
 }
 
-template <int R, int NP, bool DENSE>
+template <int R, int NP, int VAR>
 __device__ __forceinline__ void p2_stage_pick(float4* s, const P2Tw& tw, int N, int L, int swap, int tid, int nthr) {
   const int MC = (L / R) * NP;
-  if ((MC & 63) == 0) { p2_stage<R, NP, 1, DENSE>(s, tw, N, L, swap, tid, nthr); return; }
+  if ((MC & 63) == 0) { p2_stage<R, NP, 1, VAR>(s, tw, N, L, swap, tid, nthr); return; }
   if constexpr (R == 8 || R == 16) {
-    if (MC == 8) { p2_stage<R, NP, 2, DENSE>(s, tw, N, L, swap, tid, nthr); return; }
+    if (MC == 8) { p2_stage<R, NP, 2, VAR>(s, tw, N, L, swap, tid, nthr); return; }
   }
-  if constexpr (R == 8 && NP == 1 && !DENSE) {
-    if (MC == 1) { p2_stage<R, NP, 3, DENSE>(s, tw, N, L, swap, tid, nthr); return; }
+  if constexpr (R == 8 && NP == 1 && VAR != P2_DIF_DENSE) {
+    if (MC == 1) { p2_stage<R, NP, 3, VAR>(s, tw, N, L, swap, tid, nthr); return; }
   }
-  p2_stage<R, NP, 0, DENSE>(s, tw, N, L, swap, tid, nthr);
+  p2_stage<R, NP, 0, VAR>(s, tw, N, L, swap, tid, nthr);
 }
 
-template <int NP, bool DENSE>
+// MAXR = 8: the factorisation holds no radix-16 stage (kernels compiled for 85 registers leave that code out)
+template <int NP, int VAR, int MAXR>
 __device__ __forceinline__ void p2_stage_dispatch(int r, float4* s, const P2Tw& tw, int N, int L, int swap, int tid,
                                                   int nthr) {
+  if constexpr (MAXR >= 16) {
+    if (r == 16) { p2_stage_pick<16, NP, VAR>(s, tw, N, L, swap, tid, nthr); return; }
+  }
   switch (r) {
-    case 16: p2_stage_pick<16, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
-    case 8: p2_stage_pick<8, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
-    case 4: p2_stage_pick<4, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
-    case 2: p2_stage_pick<2, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
-    case 3: p2_stage_pick<3, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
-    case 5: p2_stage_pick<5, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
-    case 7: p2_stage_pick<7, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
-    default: p2_stage_pick<11, NP, DENSE>(s, tw, N, L, swap, tid, nthr); break;
+    case 8: p2_stage_pick<8, NP, VAR>(s, tw, N, L, swap, tid, nthr); break;
+    case 4: p2_stage_pick<4, NP, VAR>(s, tw, N, L, swap, tid, nthr); break;
+    case 2: p2_stage_pick<2, NP, VAR>(s, tw, N, L, swap, tid, nthr); break;
+    case 3: p2_stage_pick<3, NP, VAR>(s, tw, N, L, swap, tid, nthr); break;
+    case 5: p2_stage_pick<5, NP, VAR>(s, tw, N, L, swap, tid, nthr); break;
+    case 7: p2_stage_pick<7, NP, VAR>(s, tw, N, L, swap, tid, nthr); break;
+    default: p2_stage_pick<11, NP, VAR>(s, tw, N, L, swap, tid, nthr); break;
   }
 }
 
@@ -320,15 +328,27 @@ __device__ __forceinline__ void p2_sync(int nthr) { asm volatile("bar.sync 1, %0
 
 // Forward DIF transform of the NP * 2 interleaved length-N arrays.  The caller makes the input visible to the
 // `nthr` transform threads first; on return every stage is complete and synchronised among them.
-template <int NP>
+template <int NP, int MAXR = 16>
 __device__ __forceinline__ void p2_fft_dif(float4* s, const P2Tw& tw, const FftDesc& d, int inmode, int tid, int nthr) {
   int L = d.n;
   for (int st = 0; st < d.nstage; ++st) {
     if (st == 0 && inmode != P2_IN_PAIR)
-      p2_stage_dispatch<NP, true>(d.radix[0], s, tw, d.n, L, inmode == P2_IN_AOS_SWAP, tid, nthr);
+      p2_stage_dispatch<NP, P2_DIF_DENSE, MAXR>(d.radix[0], s, tw, d.n, L, inmode == P2_IN_AOS_SWAP, tid, nthr);
     else
-      p2_stage_dispatch<NP, false>(d.radix[st], s, tw, d.n, L, 0, tid, nthr);
+      p2_stage_dispatch<NP, P2_DIF, MAXR>(d.radix[st], s, tw, d.n, L, 0, tid, nthr);
     L /= d.radix[st];
+    p2_sync(nthr);
+  }
+}
+
+// Forward DIT transform: the input element n sits at (swizzled) position posmap[n] (digit-reversed), the output is
+// in natural order.
+template <int NP, int MAXR = 16>
+__device__ __forceinline__ void p2_fft_dit(float4* s, const P2Tw& tw, const FftDesc& d, int tid, int nthr) {
+  int L = 1;
+  for (int st = d.nstage - 1; st >= 0; --st) {
+    L *= d.radix[st];
+    p2_stage_dispatch<NP, P2_DIT, MAXR>(d.radix[st], s, tw, d.n, L, 0, tid, nthr);
     p2_sync(nthr);
   }
 }

@@ -140,11 +140,13 @@ struct pfbg_plan {
   cudaEvent_t stage_ev[16]{};
   bool stage_ev_ok = false;
   // fused FFT path (fused_fft.cuh)
-  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, pos_u, cellflags, accimg, nutab;
+  DevBuf tw_u, tw_v, rev_u, rev_v, pos_v, pos_u, pos_u8, pos_v8, cellflags, accimg, nutab;
   FusedTabs ftabs{};
   bool fused = false;          // tables built and sizes fit shared memory
   int col_c = 4;               // columns per CTA in the column passes
   bool cols2 = false;          // fp32: TMA-fed pair-engine column kernels (cols2.cuh) serve this geometry
+  bool rows2 = false;          // fp32: pair-engine row kernels (rows2.cuh), two planes per CTA
+  bool rows_r8 = false, cols_r8 = false;  // ... on radix-8 stages with twice the threads
   cufftHandle fft = 0;
   int fft_batch = 1;           // planes per cuFFT execution (a divisor of nplanes; bounds the work area)
   bool fft_ok = false;
@@ -463,6 +465,30 @@ static int fused_setup_t(pfbg_plan* pl) {
   if constexpr (sizeof(T) == 4) {
     const char* ce = getenv("PFBG_COLS");  // PFBG_COLS=old: the single-buffer column kernels of fused_fft.cuh
     pl->cols2 = !(ce && strcmp(ce, "old") == 0) && pl->col_c == full_c && cols2_supported(g.nu, g.nv, g.nx, du);
+    const char* re = getenv("PFBG_ROWS");  // PFBG_ROWS=old: one plane per CTA (k_rows_fwd / k_rows_inv)
+    pl->rows2 = !(re && strcmp(re, "old") == 0) && rows2_supported(g.nv);
+    // radix-8 factorisations for the pair engine (PFBG_R8: bit 0 rows, bit 1 columns)
+    ft.du8.n = ft.dv8.n = 0;
+    ft.pos_u8 = ft.pos_v8 = nullptr;
+    const char* r8e = getenv("PFBG_R8");
+    const int r8 = r8e ? atoi(r8e) : 0;
+    FftDesc d8;
+    if ((r8 & 1) && pl->rows2 && factorize(g.nv, d8, 8)) {
+      digit_tables(d8, rev, pos);
+      CKRC(dev_alloc(pl, pl->pos_v8, (size_t)g.nv * 4));
+      CK(cudaMemcpy(pl->pos_v8.p, pos.data(), (size_t)g.nv * 4, cudaMemcpyHostToDevice));
+      ft.dv8 = d8;
+      ft.pos_v8 = (const int*)pl->pos_v8.p;
+      pl->rows_r8 = true;
+    }
+    if ((r8 & 2) && pl->cols2 && factorize(g.nu, d8, 8) && cols2_supported(g.nu, g.nv, g.nx, d8)) {
+      digit_tables(d8, rev, pos);
+      CKRC(dev_alloc(pl, pl->pos_u8, (size_t)g.nu * 4));
+      CK(cudaMemcpy(pl->pos_u8.p, pos.data(), (size_t)g.nu * 4, cudaMemcpyHostToDevice));
+      ft.du8 = d8;
+      ft.pos_u8 = (const int*)pl->pos_u8.p;
+      pl->cols_r8 = true;
+    }
   }
   pl->fused = true;
   return PFBG_OK;
@@ -1184,16 +1210,16 @@ static int run_cols2(pfbg_plan* pl, cudaStream_t s, const FusedTabs& ft, int slo
                      float2* out_biased) {
   const GParams& g = pl->gp;
   Cols2Args a;
-  a.du = ft.du;
+  a.du = pl->cols_r8 ? ft.du8 : ft.du;
   a.tw_u = (const float2*)ft.tw_u;
-  a.pos_u = ft.pos_u;
+  a.pos_u = pl->cols_r8 ? ft.pos_u8 : ft.pos_u;
   a.nu = g.nu; a.nv = g.nv; a.nx = g.nx;
   a.a_lo = ft.a_lo; a.a_len = ft.a_len; a.b_lo = ft.b_lo; a.b_len = ft.b_len;
   a.q0 = ft.q0; a.nq = nq; a.slot0 = slot0;
   a.inverse = inverse ? 1 : 0;
   a.debug = 0; a.dbg_stack = nullptr;
   const char* what = "";
-  cudaError_t e = cols2_launch(a, (const float2*)pl->grid.p, pl->stack_planes, out_biased, s, &what);
+  cudaError_t e = cols2_launch(a, pl->cols_r8, (const float2*)pl->grid.p, pl->stack_planes, out_biased, s, &what);
   if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   LAUNCHED();
   return PFBG_OK;
@@ -1219,8 +1245,18 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
   if constexpr (sizeof(T) == 4) {
     if (g.fast_screen) k_rows = &k_rows_fwd<T, true>;
   }
-  k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
-      g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, stack);
+  bool rows_done = false;
+  if constexpr (sizeof(T) == 4) {
+    if (pl->rows2) {
+      cudaError_t e = rows2_fwd_launch(g, ft, nq, g.fast_screen != 0, pl->rows_r8, (const float*)x, (const float*)beam,
+                                       (const float*)pl->corr.p, (float2*)stack, s);
+      if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "k_rows2_fwd launch: %s", cudaGetErrorString(e));
+      rows_done = true;
+    }
+  }
+  if (!rows_done)
+    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+        g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, stack);
   LAUNCHED();
   CK(cudaGetLastError());
   const dim3 cgrid(ft.b_len / CC, nq);
@@ -1271,8 +1307,17 @@ static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, cons
   if constexpr (sizeof(T) == 4) {
     if (g.fast_screen) k_rows = &k_rows_inv<T, true>;
   }
-  k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
-      g, ft, stack, (double*)pl->accimg.p);
+  bool rows_done = false;
+  if constexpr (sizeof(T) == 4) {
+    if (pl->rows2) {
+      cudaError_t e = rows2_inv_launch(g, ft, nq, g.fast_screen != 0, pl->rows_r8, (const float2*)stack, (double*)pl->accimg.p, s);
+      if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "k_rows2_inv launch: %s", cudaGetErrorString(e));
+      rows_done = true;
+    }
+  }
+  if (!rows_done)
+    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+        g, ft, stack, (double*)pl->accimg.p);
   LAUNCHED();
   CK(cudaGetLastError());
   return PFBG_OK;

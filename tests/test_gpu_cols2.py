@@ -1,6 +1,7 @@
 """GPU: the fp32 pair FFT engine (csrc/fft2.cuh: packed two-wide butterflies, 128-byte XOR swizzle) against numpy, and
-the TMA-fed column transforms built on it (csrc/cols2.cuh) against the explicit DFT and against the single-buffer
-column kernels of fused_fft.cuh (PFBG_COLS=old) on the same inputs."""
+the plane transforms built on it — TMA-fed column passes (csrc/cols2.cuh), two-planes-per-CTA row passes
+(csrc/rows2.cuh) — against the explicit DFT and against the scalar-engine kernels of fused_fft.cuh
+(PFBG_COLS=old PFBG_ROWS=old) on the same inputs."""
 import ctypes as C
 
 import numpy as np
@@ -26,14 +27,14 @@ def _first_radix(n):
 
 
 @pytest.mark.parametrize("np_", [1, 2, 4])
-@pytest.mark.parametrize("aos", [0, 1])
+@pytest.mark.parametrize("aos", [0, 1, 2])  # 0: pair-element input, DIF; 1: dense AoS input, DIF; 2: DIT
 def test_pair_engine_matches_numpy(gpu, np_, aos):
     lib = _lib.load()
     rng = np.random.default_rng(11)
     for n in SIZES:
         if n * np_ * 16 > 232448:
             continue
-        if aos and (n // _first_radix(n)) * np_ % 8:
+        if aos == 1 and (n // _first_radix(n)) * np_ % 8:
             continue  # dense first-stage input needs a first stride of a multiple of 8 chunks (p2_dense_ok)
         x = (rng.standard_normal((2, 2 * np_, n)) + 1j * rng.standard_normal((2, 2 * np_, n))).astype(np.complex64)
         for inverse in (0, 1):
@@ -63,6 +64,7 @@ def test_tma_column_transforms_against_dft_and_old_kernels(gpu, monkeypatch, nx,
     for mode in ("new", "old"):
         if mode == "old":
             monkeypatch.setenv("PFBG_COLS", "old")
+            monkeypatch.setenv("PFBG_ROWS", "old")
         with W.plan_for(p["uvw"], p["freq"], npix_x=nx, npix_y=ny, pixsize_x=p["cell"], pixsize_y=p["cell"],
                         epsilon=eps, precision="single", mask=p["mask"], **kw) as gp:
             v = gp.degrid(img)
@@ -100,6 +102,7 @@ def test_tma_column_transforms_partial_uv_window(gpu, monkeypatch):
     for mode in ("new", "old"):
         if mode == "old":
             monkeypatch.setenv("PFBG_COLS", "old")
+            monkeypatch.setenv("PFBG_ROWS", "old")
         with W.plan_for(uvw, p["freq"], npix_x=nx, npix_y=ny, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=eps,
                         precision="single", **kw) as gp:
             out[mode] = (gp.degrid(img), gp.grid(vis, wgt))
