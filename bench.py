@@ -33,6 +33,13 @@ WORKLOADS = {
     # pfb's production default: double precision, epsilon=1e-7 (core/grid.py:50), C2 geometry
     "c2d": dict(nx=4096, ntime=775, nchan=16, precision="double", epsilon=1e-7,
                 name="C2 geometry in fp64 at pfb's default eps=1e-7: 4096^2, 25.0M vis/band"),
+    # configs[3]: wide field, 16 bands x 10240^2, 62.5 M vis per band (1 G vis); the field is twice as wide as
+    # config 2's (finer cells AND more of them), which is what multiplies the w-planes.  The bands of a GPU take
+    # turns on shared plane stacks (wgridder.StackArena): 62 GB of planes per band would not fit 16 times
+    "c4": dict(nx=10240, ntime=1938, nchan=16, precision="single", epsilon=1e-5, nbands=16, nband_total=16,
+               cell_div=1.25, share_stack=True,
+               name="wide field C4: 16 bands x 10240^2, 62.5M vis/band (1.0G vis), MeerKAT-like, fp32, eps=1e-5, "
+                    "plane stacks shared by the bands of a GPU"),
     # configs[4]: pfb hci, 1024 high-cadence snapshots of 512^2 (utils/stokes2im.py:635-683: sigma_min = 2,
     # divide_by_n = True; tests/test_hci.py:33-34: single precision, epsilon 1e-4), batched
     "c5": dict(nx=512, nsnap=1024, nchan=16, precision="single", epsilon=1e-4, chunk=256, band=4,
@@ -87,8 +94,9 @@ class ClockSampler(threading.Thread):
 def make_inputs(cfg, band, with_vis=False):
     from pfb_imaging_b200 import synth
 
-    d = synth.make_band(cfg["ntime"], cfg["nchan"], band=band, nband=8, precision=cfg["precision"], with_vis=with_vis)
-    cell = synth.default_cell(d["uvw"], 1712e6)  # one cell size for all bands (top of L-band)
+    d = synth.make_band(cfg["ntime"], cfg["nchan"], band=band, nband=cfg.get("nband_total", 8), precision=cfg["precision"],
+                        with_vis=with_vis)
+    cell = synth.default_cell(d["uvw"], 1712e6) / cfg.get("cell_div", 1.0)  # one cell size for all bands (top of L-band)
     rdt = np.float32 if cfg["precision"] == "single" else np.float64
     x = synth.point_source_image(cfg["nx"], cfg["nx"], dtype=rdt)
     return d, cell, x
@@ -375,7 +383,7 @@ def run_ours(args, cfg):
         probe, cell0, _ = make_inputs(cfg, job_bands[0])
         est = []
         for b in job_bands:
-            fr = synth.band_freqs(b, 8, cfg["nchan"])
+            fr = synth.band_freqs(b, cfg.get("nband_total", 8), cfg["nchan"])
             wmin, wmax = w_range(probe["uvw"], fr)
             pl = make_plan(nx=cfg["nx"], ny=cfg["nx"], pixsize_x=cell0, pixsize_y=cell0, epsilon=cfg["epsilon"],
                            flip_v=True, divide_by_n=False, sigma_min=1.1, sigma_max=3.0, precision=cfg["precision"],
@@ -391,13 +399,20 @@ def run_ours(args, cfg):
         d, cell, x = make_inputs(cfg, b)
         gp = W.plan_for(d["uvw"], d["freq"], npix_x=cfg["nx"], npix_y=cfg["nx"], pixsize_x=cell, pixsize_y=cell,
                         epsilon=cfg["epsilon"], flip_v=True, divide_by_n=False, precision=cfg["precision"],
-                        mask=d["mask"], sigma_min=1.1, sigma_max=3.0, device=local)
+                        mask=d["mask"], sigma_min=1.1, sigma_max=3.0, device=local,
+                        external_stack=bool(cfg.get("share_stack")))
         gp.bind_weights(d["wgt"])
         x_d = torch.from_numpy(x).to(dev)
         bands.append(dict(b=b, d=d, cell=cell, x=x, gp=gp, x_d=x_d, out_d=torch.empty_like(x_d), info=gp.info(),
                           wsum=float(d["wgt"].sum(dtype=np.float64)), nvis=d["uvw"].shape[0] * d["freq"].size))
     nvis_local = sum(bd["nvis"] for bd in bands)
     stream = torch.cuda.current_stream().cuda_stream
+    arena = None
+    if cfg.get("share_stack") and bands:
+        # two stacks (one per compute stream) when they fit next to everything else that is resident, else one
+        need = max(int(bd["info"]["grid_bytes"]) for bd in bands)
+        free_b, _tot = torch.cuda.mem_get_info(dev)
+        arena = W.StackArena([bd["gp"] for bd in bands], nslots=2 if free_b > 2 * need + (24 << 30) else 1, device=local)
 
     def barrier():
         torch.cuda.synchronize()
@@ -439,7 +454,8 @@ def run_ours(args, cfg):
         costs = [all_stats[b]["ms"] for b in job_bands]
         tpl = [all_stats[b]["t_plane"] for b in job_bands]
         npl = [all_stats[b]["P"] for b in job_bands]
-        off_idx, model_loads = ({}, None) if args.no_offload else bsplit.plan_offloads(costs, tpl, npl, owner, world)
+        off_idx, model_loads = (({}, None) if args.no_offload or cfg.get("share_stack") else
+                                bsplit.plan_offloads(costs, tpl, npl, owner, world))  # (lent stacks are not exported to helpers)
         offloads = {job_bands[i]: o for i, o in off_idx.items()}
         if offloads:
             split = bsplit.BandSplit({bd["b"]: bd["gp"] for bd in bands}, offloads, rank, local, gather_obj)
@@ -449,7 +465,7 @@ def run_ours(args, cfg):
     # the bands of a GPU are independent: they alternate between two compute streams, so the tail of one band's
     # kernels overlaps the head of the next band's (measured: 100.4 -> 89.5 ms for the 8 bands of C2; more than
     # two streams bring nothing).  Every step forks from / joins the current stream, where the events are recorded.
-    cstreams = [torch.cuda.Stream(dev) for _ in range(2)] if len(bands) > 1 else []
+    cstreams = [torch.cuda.Stream(dev) for _ in range(2)] if len(bands) > 1 and (arena is None or arena.nslots > 1) else []
 
     def step_dev():
         cur = torch.cuda.current_stream()
@@ -535,23 +551,30 @@ def run_ours(args, cfg):
             ops.hessian_slice(bd["x"], xout=bd["xo"], uvw=d["uvw"], weight=d["wgt"], vis_mask=d["mask"], freq=d["freq"],
                               cell=bd["cell"], epsilon=cfg["epsilon"], wsum=bd["wsum"], flip_v=True)
 
+    shared = bool(cfg.get("share_stack"))
+    nslots = arena.nslots if arena is not None else 0
     for bd in bands:
         bd["gp"].close()  # free the device-resident plans before the operator-level cache binds its own
         bd["xo"] = np.empty_like(bd["x"])
-    for _ in range(2):
-        step_e2e()  # first call binds the band (like load_band); later calls hit the plan cache
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) / args.steps
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = float(nvis_all.item()) / float(te.item()) / 1e6
-    info = None
-    if bands:
+        bd["x_d"] = bd["out_d"] = None
+    arena = None
+    torch.cuda.empty_cache()
+    e2e_value = None
+    if not shared:  # (the operator-level plan cache gives every band its own stack: not for config 4)
+        for _ in range(2):
+            step_e2e()  # first call binds the band (like load_band); later calls hit the plan cache
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / args.steps
+        te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = float(nvis_all.item()) / float(te.item()) / 1e6
+    info = bands[0]["info"] if bands else None
+    if bands and not shared:
         gp0 = ops._cached_plan(bands[0]["d"]["uvw"], bands[0]["d"]["freq"], bands[0]["d"]["mask"], bands[0]["d"]["wgt"],
                                npix_x=cfg["nx"], npix_y=cfg["nx"], pixsize_x=float(bands[0]["cell"]),
                                pixsize_y=float(bands[0]["cell"]), center_x=0.0, center_y=0.0, epsilon=float(cfg["epsilon"]),
@@ -567,8 +590,8 @@ def run_ours(args, cfg):
         d = bd["d"]
         pool_ops[i] = ops.BandHessian(d["uvw"], d["freq"], d["wgt"], d["mask"], cfg["nx"], cfg["nx"], float(bd["cell"]),
                                       epsilon=float(cfg["epsilon"]), precision=cfg["precision"], wsum=bd["wsum"],
-                                      device=local)
-    pool = ops.BandPool(pool_ops, nband=len(bands))
+                                      device=local, external_stack=shared)
+    pool = ops.BandPool(pool_ops, nband=len(bands), share_stacks=nslots if shared else False)
     xcube = np.stack([bd["x"] for bd in bands]) if bands else None
     e2e_pool_value = None
     t_pool = 0.0
@@ -635,8 +658,8 @@ def run_ours(args, cfg):
         # ducc0-style gridder transforms): the work this implementation removed still counts there
         B_std = sum(algorithmic_bytes(dict(bd["info"], nplanes=bd["info"]["nplanes_std"]), bd["nvis"], nchan, p) for bd in bands)
         kernel_phase = {"spread": "k_grid_runs (spreading kernel)", "degrid": "k_degrid_runs (gathering kernel)",
-                        "pad_screen_fft": "k_rows_fwd + k_cols_fwd (fused pad/screen/FFT)",
-                        "fft_crop_screen": "k_cols_inv + k_rows_inv (fused FFT/screen/crop)"}
+                        "pad_screen_fft": "k_rows2_fwd + k_cols2 (fused pad/screen/FFT; fp64: k_rows_fwd + k_cols_fwd)",
+                        "fft_crop_screen": "k_cols2 + k_rows2_inv (fused FFT/screen/crop; fp64: k_cols_inv + k_rows_inv)"}
         dom = max(kernel_phase, key=lambda k: phases.get(k, 0.0))
         # roofline of the gridding (spreading) kernel, the hand-written kernel SURVEY §8(d) models per sample
         kb = sum(spread_kernel_bytes(bd["info"], bd["nvis"], nchan, p) for bd in bands) / len(bands)
@@ -722,7 +745,7 @@ def run_ours(args, cfg):
             "ms_per_band_rank0": per_band,
         }
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not cfg.get("share_stack"):  # (c4: the fp64 host planes alone are 124 GB)
             c = cpu_hessian_sample(cfg, bands[0]["b"], args.cpu_row_step)
             how = "all rows" if args.cpu_row_step == 1 else f"every {args.cpu_row_step}th row for the per-visibility loops (extrapolated)"
             cpu = {"value": c["value"], "unit": "Mvis/s", "cores": c["cores"], "kind": "port",
@@ -747,7 +770,8 @@ def run_ours(args, cfg):
                        "nvis_total": int(nvis_all.item()),
                        "l2": "inputs larger than L2 (plane stack %.1f GB per band)" % (info["grid_bytes"] / 1e9),
                        "plan_first_band": {k: info[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "nplanes_std", "pmirror", "beta")},
-                       "streams": "the bands of a GPU alternate between 2 compute streams" if len(bands) > 1 else "one stream",
+                       "streams": "the bands of a GPU alternate between 2 compute streams" if cstreams else "one stream",
+                       "plane_stacks_rank0": (f"{nslots} shared by {len(bands)} bands" if shared else f"{len(bands)} (one per band)"),
                        "parallelism": (f"{nbands} bands of ONE job partitioned over {world} GPUs (longest-processing-time first); "
                                        f"plane transforms of {len(offloads)} band(s) offloaded to the least loaded GPUs over NVLink "
                                        "peer memory (fused into the transform kernels, flags in device memory, no collective)"

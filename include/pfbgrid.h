@@ -51,6 +51,9 @@ extern "C" {
 #define PFBG_DEVICE_PTRS 1u   /* data pointers are device pointers; call is asynchronous on `stream` */
 #define PFBG_APPLY_WGT 2u     /* degrid: multiply the output by the bound/passed weights */
 #define PFBG_NO_MASK_ZERO 4u  /* degrid: leave masked output samples untouched instead of zeroing */
+/* pfbg_plan_desc.flags */
+#define PFBG_PLAN_EXTERNAL_STACK 1 /* do not allocate the plane stack: the caller lends one (pfbg_plan_set_stack) */
+
 #define PFBG_PINNED_IN 16u    /* host-pointer calls: the input image(s) are page-locked (pfbg_host_register): DMA directly */
 #define PFBG_PINNED_OUT 32u   /* host-pointer calls: the output image is page-locked */
 #define PFBG_BEAM_CACHED 64u  /* pfbg_hessian, host pointers: `beam` equals the beam of the previous call on this plan
@@ -85,7 +88,7 @@ typedef struct pfbg_plan_desc {
                           * instead of planes that would have to be stored and transformed */
   int32_t fast_screen;   /* fp32 plans only: w-screen phasors from the SFU (sin.approx / cos.approx after the fp64
                           * range reduction, abs. error ~5e-7) instead of sincospif; for epsilon >= 3e-6 */
-  int32_t reserved;
+  int32_t flags;         /* PFBG_PLAN_* bits */
 } pfbg_plan_desc;
 
 typedef struct pfbg_plan_info {
@@ -111,6 +114,14 @@ int pfbg_plan_get_info(const pfbg_plan* plan, pfbg_plan_info* info);
  * geometry, sigma and W is kept.  Unbinds the visibilities.  Used to pool plans across the thousands of
  * small snapshot images of `pfb hci` (utils/stokes2im.py:635-683). */
 int pfbg_plan_set_wrange(pfbg_plan* plan, double w0, int32_t nplanes, int32_t pmirror);
+/*
+ * Lend the plan a plane stack (device memory of the plan's device, 256-byte aligned, at least nplanes * nu * nv
+ * complex cells).  The stack is scratch between calls, so the bands that share a GPU — the reference keeps one
+ * worker per band, operators/band_worker.py:217-246 — can take turns on one stack per compute stream instead of
+ * holding one each (config 4: 62 GB per band at 10240^2).  The caller keeps calls that share a stack on one stream.
+ * dev_ptr == NULL takes the loan back.  Plans of a split band (pfbg_split_*) cannot borrow.
+ */
+int pfbg_plan_set_stack(pfbg_plan* plan, void* dev_ptr, uint64_t bytes);
 
 /*
  * Batched snapshots (`pfb hci`: utils/stokes2im.py:635-683 makes two vis2dirty calls per 512^2 snapshot, thousands

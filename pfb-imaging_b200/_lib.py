@@ -19,6 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 PFBG_F32, PFBG_F64 = 0, 1
 HOST_PTRS, DEVICE_PTRS, APPLY_WGT, NO_MASK_ZERO = 0, 1, 2, 4
 PINNED_IN, PINNED_OUT, BEAM_CACHED = 16, 32, 64
+PLAN_EXTERNAL_STACK = 1
 IPC_BLOB_BYTES = 96
 
 NVCC_FLAGS = [
@@ -39,7 +40,7 @@ class PlanDesc(C.Structure):
         ("w0", C.c_double), ("dw", C.c_double), ("nshift", C.c_double),
         ("corr_u", C.c_void_p), ("corr_v", C.c_void_p),
         ("gl_x", C.c_void_p), ("gl_w", C.c_void_p),
-        ("n_gl", C.c_int32), ("pmirror", C.c_int32), ("fast_screen", C.c_int32), ("reserved", C.c_int32),
+        ("n_gl", C.c_int32), ("pmirror", C.c_int32), ("fast_screen", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -62,6 +63,7 @@ SIGNATURES = {
     "pfbg_plan_destroy": (C.c_int, [_vp]),
     "pfbg_plan_get_info": (C.c_int, [_vp, C.POINTER(PlanInfo)]),
     "pfbg_plan_set_wrange": (C.c_int, [_vp, _dbl, _i32, _i32]),
+    "pfbg_plan_set_stack": (C.c_int, [_vp, _vp, C.c_uint64]),
     "pfbg_bind_vis": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32, _vp]),
     "pfbg_bind_weights": (C.c_int, [_vp, _vp, _u32, _vp]),
     "pfbg_plan_set_batch": (C.c_int, [_vp, _i32, _vp, _vp]),

@@ -121,6 +121,8 @@ struct pfbg_plan {
   // device state
   DevBuf corr;                 // (nx,ny) T
   DevBuf grid;                 // (nplanes,nu,nv) C
+  bool grid_external = false;  // the stack is lent by the caller (pfbg_plan_set_stack): never allocated / freed here
+  bool grid_lazy = false;      // PFBG_PLAN_EXTERNAL_STACK: no stack until one is lent
   DevBuf uvw, fscale, mask;    // bound geometry
   DevBuf wgt;                  // bound weights (nrow,nchan) T
   DevBuf sorted_idx;           // (nactive) u32
@@ -175,6 +177,16 @@ struct pfbg_plan {
   int n_ev = 0;
 };
 
+static int dev_alloc(pfbg_plan* pl, DevBuf& b, size_t bytes);
+// (re)size the plane stack: a lent stack is never reallocated, it must be large enough
+static int stack_alloc(pfbg_plan* pl, size_t bytes) {
+  if (pl->grid_external) {
+    if (pl->grid.bytes < bytes) return fail(PFBG_ERR_NOMEM, "the lent plane stack holds %zu bytes, %zu are needed", pl->grid.bytes, bytes);
+    return PFBG_OK;
+  }
+  if (pl->grid_lazy) return PFBG_OK;  // sized when a stack is lent
+  return dev_alloc(pl, pl->grid, bytes);
+}
 static int dev_alloc(pfbg_plan* pl, DevBuf& b, size_t bytes) {
   if (b.bytes >= bytes && b.p) return PFBG_OK;
   if (b.p) {
@@ -211,6 +223,7 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   if (!pl) return PFBG_OK;
   cudaSetDevice(pl->device);
   if (pl->fft_ok) cufftDestroy(pl->fft);
+  if (pl->grid_external) { pl->grid.p = nullptr; pl->grid.bytes = 0; }
   DevBuf* all[] = {&pl->corr, &pl->grid, &pl->uvw, &pl->fscale, &pl->mask, &pl->wgt, &pl->sorted_idx, &pl->srt_ka, &pl->srt_kb, &pl->srt_va, &pl->srt_vb, &pl->srt_tmp,
                    &pl->xshare, &pl->partial, &pl->mailbox, &pl->x_local,
                    &pl->row_snap, &pl->snap_w0, &pl->snap_pbase, &pl->snap_np, &pl->plane_w, &pl->plane_img,
@@ -224,6 +237,32 @@ extern "C" int pfbg_plan_destroy(pfbg_plan* pl) {
   if (pl->h_in) cudaFreeHost(pl->h_in);
   if (pl->h_out) cudaFreeHost(pl->h_out);
   delete pl;
+  return PFBG_OK;
+}
+
+// Lend the plan a plane stack owned by the caller (device memory of the plan's device).  The stack is scratch
+// between calls — every grid / degrid / Hessian call rebuilds it — so the plans of the bands of one GPU can take
+// turns on ONE stack per compute stream instead of holding nplanes * nu * nv cells each (C4: 62 GB per band).
+// dev_ptr == NULL takes the loan back (a plan created without PFBG_PLAN_EXTERNAL_STACK allocates its own again).
+extern "C" int pfbg_plan_set_stack(pfbg_plan* pl, void* dev_ptr, uint64_t bytes) {
+  if (!pl) return fail(PFBG_ERR_ARG, "null plan");
+  if (pl->split_role != 0) return fail(PFBG_ERR_STATE, "the stack of a split band is exported to its helper and cannot be replaced");
+  CK(cudaSetDevice(pl->device));
+  const size_t need = (size_t)pl->stack_planes * pl->gp.nu * pl->gp.nv * 2 * real_bytes(pl);
+  if (!dev_ptr) {
+    if (pl->grid_external) { pl->grid.p = nullptr; pl->grid.bytes = 0; pl->grid_external = false; }
+    if (!pl->grid_lazy) CKRC(dev_alloc(pl, pl->grid, need));
+    return PFBG_OK;
+  }
+  if (bytes < need) return fail(PFBG_ERR_ARG, "the lent stack holds %llu bytes, the plan needs %zu", (unsigned long long)bytes, need);
+  if (((uintptr_t)dev_ptr & 255) != 0) return fail(PFBG_ERR_ARG, "the lent stack must be 256-byte aligned");
+  cudaPointerAttributes at;
+  CK(cudaPointerGetAttributes(&at, dev_ptr));
+  if (at.type != cudaMemoryTypeDevice || at.device != pl->device) return fail(PFBG_ERR_ARG, "the lent stack is not device memory of device %d", pl->device);
+  if (!pl->grid_external) dev_free(pl, pl->grid);
+  pl->grid.p = dev_ptr;
+  pl->grid.bytes = (size_t)bytes;
+  pl->grid_external = true;
   return PFBG_OK;
 }
 
@@ -283,7 +322,8 @@ static int plan_create_impl(const pfbg_plan_desc* d, int stack_planes, pfbg_plan
   int rc;
   if ((rc = dev_alloc(pl, pl->corr, (size_t)g.nx * g.ny * rb))) return bail(rc);
   pl->stack_planes = stack_planes;
-  if ((rc = dev_alloc(pl, pl->grid, (size_t)stack_planes * g.nu * g.nv * 2 * rb))) return bail(rc);
+  pl->grid_lazy = (d->flags & PFBG_PLAN_EXTERNAL_STACK) != 0;
+  if (!pl->grid_lazy && (rc = dev_alloc(pl, pl->grid, (size_t)stack_planes * g.nu * g.nv * 2 * rb))) return bail(rc);
   if ((rc = dev_alloc(pl, pl->flag, 128))) return bail(rc);
 
   // correction image
@@ -556,7 +596,7 @@ extern "C" int pfbg_plan_set_wrange(pfbg_plan* pl, double w0, int32_t nplanes, i
   pl->stack_planes = nplanes;
   if (need > pl->grid.bytes) {
     CK(cudaDeviceSynchronize());
-    CKRC(dev_alloc(pl, pl->grid, need));
+    CKRC(stack_alloc(pl, need));
   }
   if (nplanes != g.nplanes && pl->fft_ok) {  // the cuFFT batch depends on the plane count: rebuild lazily
     cufftDestroy(pl->fft);
@@ -601,7 +641,7 @@ extern "C" int pfbg_plan_set_batch(pfbg_plan* pl, int32_t nbatch, const double* 
   }
   if (total > (1 << 20)) return fail(PFBG_ERR_ARG, "too many planes in one batch");
   const size_t rb = real_bytes(pl);
-  CKRC(dev_alloc(pl, pl->grid, (size_t)total * g.nu * g.nv * 2 * rb));
+  CKRC(stack_alloc(pl, (size_t)total * g.nu * g.nv * 2 * rb));
   CKRC(dev_alloc(pl, pl->snap_w0, (size_t)nbatch * 8));
   CKRC(dev_alloc(pl, pl->snap_pbase, (size_t)nbatch * 4));
   CKRC(dev_alloc(pl, pl->snap_np, (size_t)nbatch * 4));
@@ -650,7 +690,9 @@ extern "C" int pfbg_plan_get_info(const pfbg_plan* pl, pfbg_plan_info* info) {
   if (!pl || !info) return fail(PFBG_ERR_ARG, "null argument");
   memset(info, 0, sizeof *info);
   info->nrow = pl->nrow; info->nvis = pl->nvis; info->nactive = pl->nactive;
-  info->grid_bytes = (int64_t)pl->grid.bytes; info->total_bytes = (int64_t)pl->total_bytes;
+  // bytes of plane stack this plan needs (== what it holds when it owns its stack; a lent stack may be larger)
+  info->grid_bytes = (int64_t)((size_t)pl->stack_planes * pl->gp.nu * pl->gp.nv * 2 * real_bytes(pl));
+  info->total_bytes = (int64_t)pl->total_bytes;
   info->nchan = pl->gp.nchan; info->nplanes = pl->gp.nplanes;
   info->nu = pl->gp.nu; info->nv = pl->gp.nv; info->W = pl->gp.W;
   info->n_work_items = 0;
@@ -1055,6 +1097,7 @@ extern "C" int pfbg_bin_dump(pfbg_plan* pl, int32_t* iu0, int32_t* iv0, int32_t*
                              uint32_t* sorted_idx) {
   if (!pl) return fail(PFBG_ERR_ARG, "null plan");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (!pl->grid.p) return fail(PFBG_ERR_STATE, "the plan has no plane stack (created with PFBG_PLAN_EXTERNAL_STACK): lend one with pfbg_plan_set_stack");
   CK(cudaSetDevice(pl->device));
   int64_t n = pl->nvis;
   if (n > 0 && (iu0 || iv0 || ip0 || key)) {
@@ -1385,6 +1428,7 @@ extern "C" int pfbg_grid(pfbg_plan* pl, const void* vis, int64_t vis_rs, int64_t
   if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
   if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split: only pfbg_hessian / pfbg_split_helper_serve");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (!pl->grid.p) return fail(PFBG_ERR_STATE, "the plan has no plane stack (created with PFBG_PLAN_EXTERNAL_STACK): lend one with pfbg_plan_set_stack");
   if (!vis && pl->nvis > 0) return fail(PFBG_ERR_ARG, "null vis");
   CK(cudaSetDevice(pl->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -1421,6 +1465,7 @@ extern "C" int pfbg_grid_psf(pfbg_plan* pl, double x0, double y0, double sign, c
   if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
   if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split: only pfbg_hessian / pfbg_split_helper_serve");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (!pl->grid.p) return fail(PFBG_ERR_STATE, "the plan has no plane stack (created with PFBG_PLAN_EXTERNAL_STACK): lend one with pfbg_plan_set_stack");
   if (x0 * x0 + y0 * y0 >= 1.0) return fail(PFBG_ERR_ARG, "phase centre outside the unit sphere");
   CK(cudaSetDevice(pl->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -1460,6 +1505,7 @@ extern "C" int pfbg_degrid(pfbg_plan* pl, const void* dirty, void* vis, const vo
   if (!pl || !dirty) return fail(PFBG_ERR_ARG, "null argument");
   if (pl->split_role) return fail(PFBG_ERR_STATE, "plan is part of a band split: only pfbg_hessian / pfbg_split_helper_serve");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (!pl->grid.p) return fail(PFBG_ERR_STATE, "the plan has no plane stack (created with PFBG_PLAN_EXTERNAL_STACK): lend one with pfbg_plan_set_stack");
   if (!vis && pl->nvis > 0) return fail(PFBG_ERR_ARG, "null vis");
   CK(cudaSetDevice(pl->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -1502,6 +1548,7 @@ extern "C" int pfbg_hessian(pfbg_plan* pl, const void* x, const void* beam, doub
                             uint32_t flags, void* stream) {
   if (!pl || !x || !out) return fail(PFBG_ERR_ARG, "null argument");
   if (!pl->bound) return fail(PFBG_ERR_STATE, "no visibilities bound");
+  if (!pl->grid.p) return fail(PFBG_ERR_STATE, "the plan has no plane stack (created with PFBG_PLAN_EXTERNAL_STACK): lend one with pfbg_plan_set_stack");
   if (pl->split_role == 2) return fail(PFBG_ERR_STATE, "split helper plans only serve (pfbg_split_helper_serve)");
   if (pl->split_role == 1 && !(flags & PFBG_DEVICE_PTRS)) return fail(PFBG_ERR_STATE, "split plans take device pointers");
   CK(cudaSetDevice(pl->device));

@@ -640,11 +640,12 @@ class BandHessian:
 
     def __init__(self, uvw, freq, weight, mask, nx, ny, cell, beam=None, x0=0.0, y0=0.0, flip_u=False, flip_v=True,
                  flip_w=False, epsilon=1e-7, do_wgridding=True, precision="double", eta=None, wsum=None,
-                 device=None, sigma_min=1.1, sigma_max=3.0):
+                 device=None, sigma_min=1.1, sigma_max=3.0, external_stack=False):
+        # external_stack=True: the band owns no plane stack; the pool lends one (BandPool(share_stacks=True))
         self.gp = plan_for(uvw, freq, npix_x=nx, npix_y=ny, pixsize_x=cell, pixsize_y=cell, center_x=x0, center_y=y0,
                            epsilon=epsilon, flip_u=flip_u, flip_v=flip_v, flip_w=flip_w, do_wgridding=do_wgridding,
                            divide_by_n=False, precision=precision, mask=mask, device=device,
-                           sigma_min=sigma_min, sigma_max=sigma_max)
+                           sigma_min=sigma_min, sigma_max=sigma_max, external_stack=external_stack)
         if weight is not None:
             self.gp.bind_weights(np.ascontiguousarray(weight, dtype=self.gp.rdt))
         self.beam = None if beam is None else np.ascontiguousarray(beam, dtype=self.gp.rdt)
@@ -695,15 +696,25 @@ class BandPool:
     """Cube-level facade over per-band pinned operators: the B200 counterpart of ``BandWorkerPool``
     (operators/band_worker.py:209-319) for the roles on the hot path — ``hess_dot``, ``hess_cg`` and the
     exact ``residual``.  Bands this process does not own (``dist.local_bands``) are skipped; with
-    ``gather=True`` the (nband, ...) result is completed on every rank by one all-reduce."""
+    ``gather=True`` the (nband, ...) result is completed on every rank by one all-reduce.
 
-    def __init__(self, band_ops, nband=None, gather=False):
+    ``share_stacks``: the bands take turns on ``share_stacks`` plane stacks (1 or 2; ``True`` = 2, one per compute
+    stream of the pipelined ``hess_dot``) instead of holding one each — the stack is scratch between applies
+    (``wgridder.StackArena``).  16 bands of config 4 (62 GB of planes each) then fit one GPU."""
+
+    def __init__(self, band_ops, nband=None, gather=False, share_stacks=False):
         from . import dist
 
         self.ops = dict(band_ops) if isinstance(band_ops, dict) else dict(enumerate(band_ops))
         self.nband = (max(self.ops) + 1) if nband is None else nband
         self.gather = gather and dist.world_size() > 1
         self._dist = dist
+        self._arena = None
+        if share_stacks and self.ops:
+            from .wgridder import StackArena
+
+            # band i of the pipelined hess_dot computes on stream i & 1: slot i % nslots follows
+            self._arena = StackArena([op.gp for op in self.ops.values()], nslots=2 if share_stacks is True else int(share_stacks))
 
     def _finish(self, out):
         return self._dist.allreduce_sum(out) if self.gather else out
@@ -776,7 +787,7 @@ class BandPool:
         used = [False] * NS
         for i, (b, op) in enumerate(ops_):
             k = i % NS
-            s_cmp = st["s_cmp"][k & 1]
+            s_cmp = st["s_cmp"][k & 1 if (self._arena is None or self._arena.nslots > 1) else 0]
             xb = x[b]
             if not _any_nonzero(xb):  # operators/hessian.py:47-48
                 out[b] = 0

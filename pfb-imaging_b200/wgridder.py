@@ -66,12 +66,15 @@ class GridderPlan:
     """A plan bound to one set of (uvw, freq, mask): the analogue of the state a
     band worker pins (``operators/band_worker.py:61-106``)."""
 
-    def __init__(self, plan: Plan, device: int | None = None):
+    def __init__(self, plan: Plan, device: int | None = None, external_stack: bool = False):
         self.plan = plan
         self.device = current_device() if device is None else int(device)
         self._h = C.c_void_p()
         self._lib = _lib.load()
         d, self._keep = _plan_desc(plan, self.device)
+        if external_stack:  # no plane stack of its own: one is lent with set_stack() (StackArena)
+            d.flags |= _lib.PLAN_EXTERNAL_STACK
+        self._stack_ref = None
         _lib.check(self._lib.pfbg_plan_create(C.byref(d), C.byref(self._h)))
         self.nrow = self.nchan = 0
         self.nbatch = 0  # > 0: batched snapshots, image arguments are (nbatch, nx, ny)
@@ -83,6 +86,7 @@ class GridderPlan:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.pfbg_plan_destroy(self._h)
             self._h = C.c_void_p()
+        self._stack_ref = None  # a lent plane stack goes back to its owner
 
     def __del__(self):
         try:
@@ -95,6 +99,14 @@ class GridderPlan:
 
     def __exit__(self, *a):
         self.close()
+
+    def set_stack(self, dev_ptr, nbytes, keep=None):
+        """Lend the plan a plane stack (``pfbg_plan_set_stack``): device memory of this plan's device, at least
+        ``info()["grid_bytes"]`` bytes.  The stack is scratch between calls, so the bands sharing a GPU can take
+        turns on one stack per compute stream.  ``keep`` is held to keep the memory alive (e.g. a torch tensor)."""
+        _lib.check(self._lib.pfbg_plan_set_stack(self._h, C.c_void_p(int(dev_ptr) if dev_ptr else None),
+                                                 C.c_uint64(int(nbytes))))
+        self._stack_ref = keep
 
     # -- binding ------------------------------------------------------------
     def bind(self, uvw, freq, mask=None, stream=None):
@@ -368,6 +380,7 @@ class SplitHelper:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.pfbg_plan_destroy(self._h)
             self._h = C.c_void_p()
+        self._stack_ref = None  # a lent plane stack goes back to its owner
 
     def __del__(self):
         try:
@@ -494,8 +507,9 @@ def _precision_of(dtype, what):
 def plan_for(uvw, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
              flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
              sigma_min=1.1, sigma_max=2.6, precision="double", mask=None, device=None, pooled=False,
-             **force) -> GridderPlan:
-    """Build a plan for the geometry and bind (uvw, freq, mask) to it."""
+             external_stack=False, **force) -> GridderPlan:
+    """Build a plan for the geometry and bind (uvw, freq, mask) to it.  ``external_stack=True``: the plan owns no
+    plane stack; lend it one (``GridderPlan.set_stack`` / ``StackArena``) before the first transform call."""
     uvw = np.asarray(uvw)
     freq = np.asarray(freq)
     wmin, wmax = w_range(uvw, freq, -1.0 if flip_w else 1.0) if do_wgridding else (0.0, 0.0)
@@ -519,13 +533,39 @@ def plan_for(uvw, freq, *, npix_x, npix_y, pixsize_x, pixsize_y, center_x=0.0, c
             gp.close()
             raise
         return _Pooled(gp, key)
-    gp = GridderPlan(p, device=device)
+    gp = GridderPlan(p, device=device, external_stack=external_stack)
     try:
         gp.bind(uvw, freq, mask)
     except Exception:
         gp.close()
         raise
     return gp
+
+
+class StackArena:
+    """Plane stacks shared by the band plans of one GPU.
+
+    A plan's plane stack (nplanes x nu x nv complex cells: 2.4-3.3 GB per config-2 band, 62 GB per config-4 band) is
+    scratch between calls, so ``nslots`` stacks — one per compute stream — serve any number of bands: band i uses
+    slot ``i % nslots`` and the caller keeps the calls of a slot on one stream.  The reference keeps one worker
+    process per band (``operators/band_worker.py:217-246``), each with its own ducc0 grid."""
+
+    def __init__(self, plans, nslots=1, device=None):
+        import torch
+
+        plans = list(plans)
+        self.nslots = max(1, min(int(nslots), len(plans)))
+        dev = plans[0].device if device is None else int(device)
+        need = max(int(gp.info()["grid_bytes"]) for gp in plans)
+        self.nbytes = (need + 255) // 256 * 256
+        self.buffers = [torch.empty(self.nbytes, dtype=torch.uint8, device=torch.device("cuda", dev))
+                        for _ in range(self.nslots)]
+        for i, gp in enumerate(plans):
+            buf = self.buffers[i % self.nslots]
+            gp.set_stack(buf.data_ptr(), self.nbytes, keep=buf)
+
+    def slot(self, i):
+        return i % self.nslots
 
 
 def vis2dirty(*, uvw, freq, vis, wgt=None, mask=None, npix_x, npix_y, pixsize_x, pixsize_y,

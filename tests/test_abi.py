@@ -42,7 +42,7 @@ def test_binding_covers_header():
 
 
 def test_struct_layout_matches_header():
-    # 8 int32 + 2 int32 + 11 doubles + 4 pointers + 4 int32 (n_gl, pmirror, fast_screen, reserved)
+    # 8 int32 + 2 int32 + 11 doubles + 4 pointers + 4 int32 (n_gl, pmirror, fast_screen, flags)
     assert ctypes.sizeof(_lib.PlanDesc) == 10 * 4 + 11 * 8 + 4 * 8 + 4 * 4
     assert ctypes.sizeof(_lib.PlanInfo) == 5 * 8 + 6 * 4
 

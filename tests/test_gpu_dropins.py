@@ -289,3 +289,49 @@ def test_direct_mode_and_cube_convolutions(gpu):
         H.idot(x, mode="nope")
     H.close()
     P.clear_convolver_cache()
+
+
+def test_band_pool_on_shared_plane_stacks(gpu):
+    """The bands of a GPU take turns on lent plane stacks (pfbg_plan_set_stack, wgridder.StackArena): one or two
+    stacks for three bands give the results of three owned stacks, through the pipelined pool call and band by band;
+    a plan without a stack refuses to transform."""
+    from pfb_imaging_b200 import wgridder as Wg
+
+    p = small_problem(nrow=600, nchan=4, nx=96, ny=64, seed=77, wscale=2.0)
+    rng = np.random.default_rng(1)
+    freqs = [p["freq"] * f for f in (1.0, 1.1, 1.25)]
+    x = rng.standard_normal((3, 96, 64)).astype(np.float32)
+
+    def make(external):
+        return {b: ops.BandHessian(p["uvw"], fr, p["wgt"].astype(np.float32), p["mask"], 96, 64, p["cell"], epsilon=1e-5,
+                                   precision="single", wsum=3.0, external_stack=external) for b, fr in enumerate(freqs)}
+
+    own = ops.BandPool(make(False), nband=3)
+    ref = own.hess_dot(x)
+    own.close()
+    lone = make(True)[0]
+    with pytest.raises(RuntimeError, match="no plane stack"):
+        lone.dot(x[0])
+    lone.close()
+    for nslots in (1, 2):
+        pool = ops.BandPool(make(True), nband=3, share_stacks=nslots)
+        assert pool._arena.nslots == nslots and len(pool._arena.buffers) == nslots
+        got = pool.hess_dot(x)
+        assert rel_l2(got, ref) <= 1e-6
+        for b in range(3):
+            assert rel_l2(pool.ops[b].dot(x[b]), ref[b]) <= 1e-6
+        pool.close()
+    # plans that own a stack give it up when one is lent
+    pool = ops.BandPool(make(False), nband=3, share_stacks=True)
+    assert rel_l2(pool.hess_dot(x), ref) <= 1e-6
+    pool.close()
+    with pytest.raises(RuntimeError, match="lent stack holds"):
+        gp = Wg.plan_for(p["uvw"], p["freq"], npix_x=96, npix_y=64, pixsize_x=p["cell"], pixsize_y=p["cell"], epsilon=1e-5,
+                         precision="single", external_stack=True)
+        try:
+            import torch
+
+            small = torch.empty(4096, dtype=torch.uint8, device="cuda")
+            gp.set_stack(small.data_ptr(), small.numel(), keep=small)
+        finally:
+            gp.close()

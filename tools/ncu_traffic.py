@@ -36,7 +36,15 @@ def parse(path):
     out = {}
     for r in data:
         name = re.sub(r"[<(].*", "", r[kcol]).replace("void ", "").strip()
-        ent = {}
+        # logical pass names: the pair-engine kernels (rows2.cuh / cols2.cuh) keep the keys of the passes they replace;
+        # k_cols2 serves both directions, in launch order forward then inverse
+        if name == "k_cols2":
+            name = "k_cols_fwd" if "k_cols_fwd" not in out else "k_cols_inv"
+            kern = "k_cols2"
+        else:
+            kern = name
+            name = {"k_rows2_fwd": "k_rows_fwd", "k_rows2_inv": "k_rows_inv"}.get(name, name)
+        ent = {"kernel": kern}
         for m, key in KEEP.items():
             if m not in hdr:
                 continue
