@@ -40,6 +40,11 @@ WORKLOADS = {
                cell_div=1.25, share_stack=True,
                name="wide field C4: 16 bands x 10240^2, 62.5M vis/band (1.0G vis), MeerKAT-like, fp32, eps=1e-5, "
                     "plane stacks shared by the bands of a GPU"),
+    # configs[2]: pfb sara, the backward step of the deconvolution: primal-dual iterations (Psi^T, l21 dual update with
+    # the cross-band all-reduce, Psi, PSF-convolution Hessian gradient, positivity) on the device, bands over the GPUs
+    "c3": dict(nx=4096, nbands=8, nlevel=3, bases=("self", "db1", "db2", "db3"), precision="double",
+               name="pfb sara C3: 8 bands x 4096^2, primal-dual iterations with bases self,db1,db2,db3 x 3 levels, "
+                    "PSF-convolution Hessian at 5760^2, fp64, NCCL all-reduce of the l21 band sum"),
     # configs[4]: pfb hci, 1024 high-cadence snapshots of 512^2 (utils/stokes2im.py:635-683: sigma_min = 2,
     # divide_by_n = True; tests/test_hci.py:33-34: single precision, epsilon 1e-4), batched
     "c5": dict(nx=512, nsnap=1024, nchan=16, precision="single", epsilon=1e-4, chunk=256, band=4,
@@ -165,6 +170,134 @@ def run_reference(args, cfg):
     }
     print(json.dumps(line), flush=True)
 
+
+
+def run_c3(args, cfg):
+    """BASELINE configs[2]: `steps` primal-dual iterations of the SARA backward step, everything resident on the
+    device, the bands of ONE job dealt to the ranks (strong scaling); the l21 band sum is the NCCL all-reduce
+    north_star names.  A step is one iteration; the end-to-end number is a whole `solve()` call from host arrays."""
+    import torch
+
+    from pfb_imaging_b200 import _lib, dist
+    from pfb_imaging_b200.plan import good_size
+    from pfb_imaging_b200.psf import HessPSF, PsfGradient
+    from pfb_imaging_b200.sara import L21, PrimalDual, PsiNocopyt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init()
+    rank = dist.rank()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nx = ny = cfg["nx"]
+    nxp = nyp = good_size(int(1.4 * nx))
+    bands = dist.local_bands(cfg["nbands"])
+    nb = len(bands)
+    bases = list(cfg["bases"])
+    rng = np.random.default_rng(100 + rank)
+    xx = np.fft.fftfreq(nxp)[:, None] * nxp
+    yy = np.fft.rfftfreq(nyp)[None, :] * nyp
+    abspsf = np.stack([np.exp(-2.0 * (np.pi * (1.5 + 0.2 * b)) ** 2 * ((xx / nxp) ** 2 + (yy / nyp) ** 2)) for b in bands])
+    truth = np.zeros((nb, nx, ny))
+    truth[:, rng.integers(0, nx, 200), rng.integers(0, ny, 200)] = np.exp(rng.standard_normal(200))
+    hess = HessPSF(nx, ny, abspsf, beam=None, eta=1e-3)
+    dirty = hess.dot(truth) + 1e-3 * rng.standard_normal(truth.shape)
+    psi = PsiNocopyt(nb, nx, ny, bases, cfg["nlevel"], 1, device=local)
+    reg = L21(psi, bases, nu=len(bases))
+    hooks = dict(reduce_tensor=dist.allreduce_sum, reduce_scalars=dist.allreduce_sum) if world > 1 else {}
+    pd = PrimalDual(tol=0.0, maxit=max(args.warmup, 3), verbosity=0, positivity=1, **hooks)
+    pd.setup(reg, 1.0 + 1e-3)
+    pd.set_grad(PsfGradient(hess, dirty))
+    x0 = np.zeros_like(dirty)
+    pd.solve(x0, 1e-4)  # warm-up iterations (allocations, first launches)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.load().pfbg_launch_count()
+    # a solve() call = upload of weights / start model, K iterations, download of the model: two calls of different
+    # length separate the per-iteration cost (device-resident `value`) from the per-call copies (`e2e`)
+    times = {}
+    nshort = 5
+    for n in (nshort, nshort + args.steps):
+        pd.maxit = n
+        pd.reset()
+        barrier()
+        t0 = time.perf_counter()
+        x = pd.solve(x0, 1e-4)
+        torch.cuda.synchronize()
+        times[n] = time.perf_counter() - t0
+    launches = _lib.load().pfbg_launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    ms_it = (times[nshort + args.steps] - times[nshort]) / args.steps * 1e3
+    t = torch.tensor([ms_it, times[nshort + args.steps] * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.allreduce_max(t)
+    ms_it, ms_call = float(t[0].item()), float(t[1].item())
+    split = {}
+    if rank == 0:
+        x_t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        v_t = torch.empty(psi.coeff_shape, dtype=torch.float64, device=dev)
+        o_t = torch.empty_like(x_t)
+        grad = PsfGradient(hess, dirty)
+
+        def timed(fn, n=5):
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        split = {"psi_dot_ms": timed(lambda: psi.dot_dev(x_t, v_t)), "psi_hdot_ms": timed(lambda: psi.hdot_dev(v_t, o_t)),
+                 "psf_hessian_grad_ms": timed(lambda: grad.device_apply(x_t, o_t))}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ncoef = int(np.prod(psi.coeff_shape))
+        # compulsory traffic of Psi^T + Psi on rank 0: the coefficient cube written once and read once (fp64), the image
+        # cube read and written once each way
+        psi_bytes = 2.0 * ncoef * 8 + 4.0 * nb * nx * ny * 8
+        psi_ms = split["psi_dot_ms"] + split["psi_hdot_ms"]
+        line = {
+            "metric": "primal-dual iterations/s (SARA backward step, config 3)", "value": 1e3 / ms_it, "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3) + nshort, "ms_per_step": ms_it,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "bands_total": cfg["nbands"], "bands_on_rank0": list(bands),
+                       "nx_psf": nxp, "coefficients_rank0": ncoef,
+                       "l2": "inputs larger than L2 (coefficient cube %.1f GB on rank 0)" % (ncoef * 8 / 1e9),
+                       "collective": ("NCCL all-reduce (SUM) of the (nbasis, nymax, nxmax) l21 band sum + 2 doubles per iteration"
+                                      if world > 1 else "none (all bands on one GPU)"),
+                       "parallelism": f"{cfg['nbands']} bands of ONE job over {world} GPU(s)"},
+            "e2e": {"value": (nshort + args.steps) / (ms_call * 1e-3), "unit": "iterations/s",
+                    "h2d_bytes_per_step": int(2 * x0.nbytes / (nshort + args.steps)),
+                    "d2h_bytes_per_step": int(x0.nbytes / (nshort + args.steps)),
+                    "call": f"PrimalDual.solve(x0 host cube, ...) -> host model, {nshort + args.steps} iterations per call (opt/primal_dual.py:284-448)"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "Psi + Psi^T (db1-db3 x 3 levels wavelet analysis / synthesis, pfbs_psi_dot / pfbs_psi_hdot)",
+                         "achieved": psi_bytes / (psi_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": psi_bytes / (psi_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "rank0_split_ms": split,
+                         "note": "achieved = compulsory bytes of one Psi^T + Psi pair on rank 0 over their time"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def run_c5(args, cfg):
@@ -809,6 +942,8 @@ def main():
         run_reference(args, cfg)
     elif args.workload == "c5":
         run_c5(args, cfg)
+    elif args.workload == "c3":
+        run_c3(args, cfg)
     else:
         run_ours(args, cfg)
 

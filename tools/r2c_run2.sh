@@ -10,6 +10,7 @@ try:
 except Exception as e:
     print("c4 no line", e)
 PY
+timeout 600 python bench.py --workload c3 --steps 50 --warmup 3 > $OUT/r2c_bench_c3.json 2> $OUT/r2c_bench_c3.err; echo "c3 rc=$?"; tail -2 $OUT/r2c_bench_c3.err; cut -c1-600 $OUT/r2c_bench_c3.json
 bash tools/profile_bands.sh r2c > $OUT/r2c_profile.log 2>&1; tail -3 $OUT/r2c_profile.log
 timeout 900 python bench.py > $OUT/r2c_bench_default.json 2> $OUT/r2c_bench_default.err
 echo "bench rc=$?"; tail -2 $OUT/r2c_bench_default.err
