@@ -122,7 +122,7 @@ _lib = None
 # translation units of libpfbgrid.so and the files each one includes (incremental rebuilds: the gridder
 # unit takes ~2 minutes to compile, the others seconds)
 _UNITS = {
-    "pfbgrid.cu": ["common.cuh", "fft.cuh", "fused_fft.cuh", "kernels.cuh", "psfconv.cuh", "runs.cuh", "weighting.cuh",
+    "pfbgrid.cu": ["common.cuh", "fft.cuh", "fused_fft.cuh", "kernels.cuh", "psfconv.cuh", "runs.cuh", "runs_mma.cuh", "weighting.cuh",
                    "cols2_api.h", "fused_common.cuh", "../../include/pfbgrid.h"],
     "colsfft.cu": ["common.cuh", "fft.cuh", "fft2.cuh", "cols2.cuh", "rows2.cuh", "cols2_api.h", "fused_common.cuh"],
     "pfbsara.cu": ["sara.cuh", "../../include/pfbsara.h", "../../include/pfbgrid.h"],

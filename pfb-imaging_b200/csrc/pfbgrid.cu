@@ -17,6 +17,7 @@
 #include "../../include/pfbgrid.h"
 #include "kernels.cuh"
 #include "runs.cuh"
+#include "runs_mma.cuh"
 #include "fused_fft.cuh"
 #include "cols2_api.h"
 #include "weighting.cuh"
@@ -940,6 +941,22 @@ static int wide_blocks(const pfbg_plan* pl, int64_t nact, int team) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// fp64, 9 <= W <= 12: the DMMA run kernels (runs_mma.cuh) unless PFBG_WIDE_MMA=0 asks for the scalar team kernels
+static bool use_mma(const pfbg_plan* pl) {
+  if (pl->precision == PFBG_F32 || pl->gp.W < 9 || pl->gp.W > 12) return false;
+  const char* e = getenv("PFBG_WIDE_MMA");
+  return !(e && e[0] == '0');
+}
+
+static int mma_blocks(const pfbg_plan* pl, int64_t nact) {
+  int sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
+  int64_t nslice = (nact + MMA_SLICE - 1) / MMA_SLICE;
+  int64_t want = (nslice + MMA_TEAMS - 1) / MMA_TEAMS;
+  int64_t cap = (int64_t)sm * 5;  // 5 resident 96-thread CTAs per SM (128 registers)
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
 static int grid_blocks(const pfbg_plan* pl, int64_t nact) {
   int sm = 148;
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, pl->device);
@@ -1132,7 +1149,17 @@ static int run_spread(pfbg_plan* pl, cudaStream_t s, const void* vis, int64_t rs
   if (pl->nactive > 0 && pl->use_runs && pl->gp.W > 8) {
     unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 16);  // slice counter of this launch
     CK(cudaMemsetAsync(queue, 0, 8, s));
-    if (pl->gp.W <= 12)
+    bool mma = false;
+    if constexpr (sizeof(T) == 8) {
+      if (use_mma(pl)) {
+        mma = true;
+        k_grid_runs_mma<<<mma_blocks(pl, pl->nactive), MMA_R * MMA_TEAMS * 32, 0, s>>>(
+            pl->gp, (const VisRec<double>*)pl->recs.p, pl->nactive, (const double2*)vis, rs, cs, (const double*)wgt,
+            (double2*)pl->grid.p, vis_sorted, apply_phase, queue);
+      }
+    }
+    if (mma) {
+    } else if (pl->gp.W <= 12)
       k_grid_runs_wide<T, 3, 6, 4><<<wide_blocks(pl, pl->nactive, 4), WIDE_WARPS * 32, 0, s>>>(
           pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)vis, rs, cs, (const T*)wgt, (C*)pl->grid.p,
           vis_sorted, apply_phase, queue);
@@ -1176,11 +1203,22 @@ static int run_gather(pfbg_plan* pl, cudaStream_t s, const void* wgt, void* vis_
     }
     unsigned long long* queue = (unsigned long long*)((char*)pl->flag.p + 32);  // one slice counter per row group (<= 8)
     CK(cudaMemsetAsync(queue, 0, 64, s));
+    bool mma = false;
+    if constexpr (sizeof(T) == 8) {
+      if (use_mma(pl)) {
+        mma = true;
+        k_degrid_runs_mma<<<mma_blocks(pl, pl->nactive), MMA_R * MMA_TEAMS * 32, 0, s>>>(
+            pl->gp, (const VisRec<double>*)pl->recs.p, pl->nactive, (const double2*)pl->grid.p, (const double*)wgt,
+            (double2*)vis_out, (double2*)out_sorted, apply_phase, queue);
+      }
+    }
     const size_t psm = (size_t)WIDE_WARPS * 16 * 32 * sizeof(C);  // per-sample lane partials (see k_degrid_runs_wide)
     // (per device and cheap: set on every launch rather than caching it per process)
-    if (pl->gp.W <= 12) CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 3, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    if (mma) {
+    } else if (pl->gp.W <= 12) CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 3, 6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     else CK(cudaFuncSetAttribute(k_degrid_runs_wide<T, 2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-    if (pl->gp.W <= 12)
+    if (mma) {
+    } else if (pl->gp.W <= 12)
       k_degrid_runs_wide<T, 3, 6, 4><<<wide_blocks(pl, pl->nactive, 4), WIDE_WARPS * 32, psm, s>>>(
           pl->gp, (const VisRec<T>*)pl->recs.p, pl->nactive, (const C*)pl->grid.p, (const T*)wgt, (C*)vis_out,
           (C*)out_sorted, apply_phase, queue);
