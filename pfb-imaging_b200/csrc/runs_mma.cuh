@@ -26,7 +26,8 @@
 #define MMA_R 3        /* warps per team */
 #define MMA_TEAMS 1    /* teams per CTA */
 #define MMA_NB 32      /* samples staged per batch */
-#define MMA_TS 40      /* doubles per staged sample: 12 u-, 12 v-, 12 w-taps, 2 amplitude / phase, 2 spare */
+#define MMA_TS 44      /* doubles per staged sample: 12 u-, 12 v-, 12 w-taps, amplitude / phase (3); 44 = 12 mod 16 keeps the
+                          4 rows x 4 consecutive slots of a half-warp operand load on distinct 8-byte banks */
 #define MMA_ROWS (MMA_NB + 8)  /* MMA steps may read (never use) up to 7 rows past the batch */
 #define MMA_SLICE 256
 
@@ -38,59 +39,57 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // ES tap in fp64 without the library's special-case handling: a * rsqrt(a) from the MUFU seed and one third-order
 // Newton step instead of the correctly rounded sqrt, e^y (y in [-beta, 0]) by Cody-Waite reduction and a degree-13
-// Taylor polynomial on |r| <= ln2 / 2.  Relative error <= ~1e-15 beta (test_gpu_mma.py checks it against exp / sqrt);
-// ~35 instead of ~73 instructions per tap, and the taps are 40 % of the instructions of these kernels.
+// Taylor polynomial on |r| <= ln2 / 2 (coefficients in constant memory: an fp64 immediate costs two extra moves).
+// Relative error ~1e-15 beta (tests/test_gpu_mma.py compares the kernels built on it with the exp / sqrt ones);
+// ~40 instead of ~73 instructions per tap.
+__constant__ double kExpC[12] = {1.6059043836821613e-10, 2.08767569878681e-09,   2.505210838544172e-08,
+                                 2.755731922398589e-07,  2.7557319223985893e-06, 2.48015873015873e-05,
+                                 1.984126984126984e-04,  1.388888888888889e-03,  8.333333333333333e-03,
+                                 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5};  // 1/13! .. 1/2!
 __device__ __forceinline__ double exp_neg_fast(double y) {
   const double t = fma(y, 1.4426950408889634, 6755399441055744.0);  // round to nearest through 1.5 * 2^52
   const int n = __double2loint(t);
   const double fn = t - 6755399441055744.0;
   double r = fma(fn, -6.93147180369123816490e-01, y);
   r = fma(fn, -1.90821492927058770002e-10, r);
-  double q = 1.6059043836821613e-10;       // 1/13!
-  q = fma(q, r, 2.08767569878681e-09);     // 1/12!
-  q = fma(q, r, 2.505210838544172e-08);    // 1/11!
-  q = fma(q, r, 2.755731922398589e-07);    // 1/10!
-  q = fma(q, r, 2.7557319223985893e-06);   // 1/9!
-  q = fma(q, r, 2.48015873015873e-05);     // 1/8!
-  q = fma(q, r, 1.984126984126984e-04);    // 1/7!
-  q = fma(q, r, 1.388888888888889e-03);    // 1/6!
-  q = fma(q, r, 8.333333333333333e-03);    // 1/5!
-  q = fma(q, r, 4.1666666666666664e-02);   // 1/4!
-  q = fma(q, r, 1.6666666666666666e-01);   // 1/3!
-  q = fma(q, r, 0.5);
+  double q = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) q = fma(q, r, kExpC[i]);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
   return __hiloint2double(__double2hiint(q) + (n << 20), __double2loint(q));  // * 2^n (q in [0.7, 1.42], n >= -60)
 }
+// x in [-1, 1] (the taps of a sample never leave the support; |a| absorbs an x that exceeds 1 by a rounding error)
 __device__ __forceinline__ double es_fast64(double x, double beta) {
-  const double a = fma(-x, x, 1.0);
+  const double a = fabs(fma(-x, x, 1.0));
   double y0;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(fmax(a, 1e-300)));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a + 1e-300));  // a == 0 (x == 1): s = 0 * 1e150 = 0
   const double e = fma(a * y0, -y0, 1.0);
   const double y1 = fma(fma(e, 0.375, 0.5), y0 * e, y0);  // 1/sqrt(a) to ~1 ulp
-  const double s = a * y1;
-  return a < 0.0 ? 0.0 : exp_neg_fast(beta * (s - 1.0));  // a == 0: s = 0, e^{-beta}
+  return exp_neg_fast(beta * fma(a, y1, -1.0));
 }
 
-// the 36 taps of the staged samples, once per team (rows >= nb keep finite values from x0 = 0)
-__device__ __forceinline__ void mma_taps(const GParams& p, const double (*x0s)[4], double (*st)[MMA_TS], int nb, int ttid,
-                                         double bscale, double xs) {
-  const int W = p.W;
-  for (int idx = ttid; idx < 36 * nb; idx += 32 * MMA_R) {
-    const int v = idx / 36, t = idx - v * 36;
-    const int axis = t / 12, k = t - axis * 12;
-    double val = k < W ? es_fast64((x0s[v][axis] + (double)k) * xs, bscale) : 0.0;
-    if (axis == 2 && !p.do_wgridding) val = (k == 0) ? 1.0 : 0.0;
-    st[v][t] = val;
+// warp r of the team evaluates the 12 taps of axis r for the sample of its lane (lane <-> sample, no index
+// arithmetic, 12 independent evaluations in flight) and writes them as six 16-byte stores
+__device__ __forceinline__ void mma_taps_axis(int W, bool flat, double x0, double* __restrict__ dst, double bscale, double xs) {
+#pragma unroll
+  for (int k = 0; k < 12; k += 2) {
+    double t0 = k < W ? es_fast64((x0 + (double)k) * xs, bscale) : 0.0;
+    double t1 = k + 1 < W ? es_fast64((x0 + (double)(k + 1)) * xs, bscale) : 0.0;
+    if (flat) { t0 = k == 0 ? 1.0 : 0.0; t1 = 0.0; }
+    *reinterpret_cast<double2*>(dst + k) = make_double2(t0, t1);
   }
 }
 
-// run origins of a batch: every warp reads the 16-byte tail of the records
-__device__ __forceinline__ uint64_t mma_origin(const VisRec<double>* __restrict__ recs, int64_t k, uint32_t& idx) {
-  const uint2* q = reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(recs + k) + 40);
-  const uint2 a = q[0], b = q[1];  // (idx, iu | iv << 16), (ip, pad)
-  idx = a.x;
-  return pack_origin(a.y & 0xffffu, a.y >> 16, (int32_t)b.x);
+// record fields every warp of the team needs: run origin (+ flat index) from the 16-byte tail, tap origin of one axis
+__device__ __forceinline__ uint64_t mma_rec(const VisRec<double>* __restrict__ recs, int64_t k, int axis, uint32_t& idx,
+                                            int32_t& ipraw, double& x0) {
+  const char* b = reinterpret_cast<const char*>(recs + k);
+  const uint2 t0 = *reinterpret_cast<const uint2*>(b + 40), t1 = *reinterpret_cast<const uint2*>(b + 48);
+  x0 = *reinterpret_cast<const double*>(b + 8 * axis);
+  idx = t0.x;
+  ipraw = (int32_t)t1.x;
+  return pack_origin(t0.y & 0xffffu, t0.y >> 16, ipraw);
 }
 
 __device__ __forceinline__ int seg_end(uint32_t starts, int a, int nb) {  // first run start after sample a, or nb
@@ -133,8 +132,8 @@ __global__ void __launch_bounds__(MMA_R* MMA_TEAMS * 32, 5)
 k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact, const double2* __restrict__ vis,
                 int64_t vis_rs, int64_t vis_cs, const double* __restrict__ wgt, double2* __restrict__ grid,
                 int vis_sorted, int apply_phase, unsigned long long* __restrict__ queue) {
-  __shared__ __align__(16) double st[MMA_TEAMS][MMA_ROWS][MMA_TS];
-  __shared__ __align__(16) double x0s[MMA_TEAMS][MMA_NB][4];
+  // staged samples, double buffered: batch b + 1 is written while slower warps of the team still read batch b
+  __shared__ __align__(16) double stb[MMA_TEAMS][2][MMA_ROWS][MMA_TS];
   __shared__ unsigned long long team_slice[MMA_TEAMS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / MMA_R, r = warp - team * MMA_R;
@@ -142,7 +141,9 @@ k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact
   const int g = lane >> 2, l3 = lane & 3;
   const int W = p.W, npl = p.do_wgridding ? W : 1;
   const double bscale = p.beta, xs = 2.0 / p.W;
+  const bool flat = r == 2 && !p.do_wgridding;
   const int64_t plane_sz = (int64_t)p.nu * p.nv;
+  int buf = 0;
   // operand slots of this lane inside a staged sample (see the tile layout above)
   const int rowl = 4 * r + (g >> 2);      // + 2 * rp : footprint row of the A / C elements
   const int cl = g & 3;                   // + 4 * jg : column class of the A / C elements
@@ -153,8 +154,8 @@ k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact
   for (int t = 0; t < 6; ++t)
 #pragma unroll
     for (int n = 0; n < 3; ++n) { acc[t][n][0] = 0; acc[t][n][1] = 0; }
-  for (int v = ttid; v < MMA_ROWS - MMA_NB; v += 32 * MMA_R)  // rows past the batch are read by masked steps: keep them finite
-    for (int t = 0; t < MMA_TS; ++t) st[team][MMA_NB + v][t] = 0.0;
+  for (int v = ttid; v < 2 * (MMA_ROWS - MMA_NB); v += 32 * MMA_R)  // rows past the batch are read by masked steps: keep them finite
+    for (int t = 0; t < MMA_TS; ++t) stb[team][v & 1][MMA_NB + (v >> 1)][t] = 0.0;
   uint64_t cur = ~0ull;
   RunPos cp;
   cp.fast = false; cp.iu0 = cp.iv0 = cp.ip = cp.m0 = 0;
@@ -222,38 +223,38 @@ k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact
     const int64_t kend = min(nact, (sl + 1) * MMA_SLICE);
     for (int64_t k0 = sl * MMA_SLICE; k0 < kend; k0 += MMA_NB) {
       const int nb = (int)min((int64_t)MMA_NB, kend - k0);
+      // lane <-> sample: run origin, the 12 taps of axis r; warp 0 also stages weight * phase * visibility
+      double (*st)[MMA_TS] = stb[team][buf];
+      buf ^= 1;
       uint64_t org = ~0ull;
-      if (r == 0) {  // lane <-> sample: weight * phase * visibility and the tap origins
-        double2 sa = make_double2(0.0, 0.0);
-        double x0[3] = {0.0, 0.0, 0.0};
-        if (lane < nb) {
-          const int64_t k = k0 + lane;
-          const VisRec<double> rec = recs[k];
-          org = pack_origin(rec.iu, rec.iv, rec.ip);
+      double x0 = 0.5 - 0.5 * W;  // lanes past the batch: any position inside the support keeps their rows finite
+      double2 sa = make_double2(0.0, 0.0);
+      if (lane < nb) {
+        const int64_t k = k0 + lane;
+        uint32_t idx;
+        int32_t ipraw;
+        org = mma_rec(recs, k, r, idx, ipraw, x0);
+        if (r == 0) {
           double2 a;
           if (vis_sorted) a = vis[k];
           else {
-            const int64_t row = rec.idx / p.nchan;
-            const int chan = (int)(rec.idx - row * p.nchan);
+            const int64_t row = idx / p.nchan;
+            const int chan = (int)(idx - row * p.nchan);
             a = vis[row * vis_rs + chan * vis_cs];
           }
-          const double w = wgt ? wgt[rec.idx] : 1.0;
-          const double pc = apply_phase ? rec.pc : 1.0, ps = apply_phase ? rec.ps : 0.0;
-          if (apply_phase && (rec.ip & REC_CONJ_BIT)) a.y = -a.y;  // folded sample (the Hessian path stays folded)
+          const double w = wgt ? wgt[idx] : 1.0;
+          double pc = 1.0, ps = 0.0;
+          if (apply_phase) {
+            pc = recs[k].pc; ps = recs[k].ps;
+            if (ipraw & REC_CONJ_BIT) a.y = -a.y;  // folded sample (the Hessian path stays folded)
+          }
           sa.x = (a.x * pc - a.y * ps) * w;
           sa.y = (a.x * ps + a.y * pc) * w;
-          x0[0] = rec.x0[0]; x0[1] = rec.x0[1]; x0[2] = rec.x0[2];
         }
-        st[team][lane][36] = sa.x;
-        st[team][lane][37] = sa.y;
-        x0s[team][lane][0] = x0[0]; x0s[team][lane][1] = x0[1]; x0s[team][lane][2] = x0[2];
-      } else if (lane < nb) {
-        uint32_t idx;
-        org = mma_origin(recs, k0 + lane, idx);
       }
+      mma_taps_axis(W, flat, x0, &st[lane][12 * r], bscale, xs);
+      if (r == 0) *reinterpret_cast<double2*>(&st[lane][36]) = sa;
       const uint32_t starts = run_starts(org, cur, lane, nb);
-      team_sync(team, 32 * MMA_R);
-      mma_taps(p, x0s[team], st[team], MMA_NB, ttid, bscale, xs);
       team_sync(team, 32 * MMA_R);
       int a = 0;
       while (a < nb) {
@@ -271,7 +272,7 @@ k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact
         }
         const int b = seg_end(starts, a, nb);
         for (int v = a; v < b; v += 4) {
-          const double* tp = st[team][v + l3];
+          const double* tp = st[v + l3];
           const bool valid = v + l3 < b;
           const double am = tp[bc];
           double B[3], A[6];
@@ -290,7 +291,6 @@ k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact
         }
         a = b;
       }
-      team_sync(team, 32 * MMA_R);  // the next batch overwrites the staging buffers
     }
   }
   if (cur != ~0ull) {
@@ -305,9 +305,8 @@ __global__ void __launch_bounds__(MMA_R* MMA_TEAMS * 32, 5)
 k_degrid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact, const double2* __restrict__ grid,
                   const double* __restrict__ wgt, double2* __restrict__ vis_out, double2* __restrict__ out_sorted,
                   int apply_phase, unsigned long long* __restrict__ queue) {
-  __shared__ __align__(16) double st[MMA_TEAMS][MMA_ROWS][MMA_TS];
-  __shared__ __align__(16) double x0s[MMA_TEAMS][MMA_NB][4];
-  __shared__ uint32_t sidx[MMA_TEAMS][MMA_NB];
+  __shared__ __align__(16) double stb[MMA_TEAMS][2][MMA_ROWS][MMA_TS];
+  __shared__ uint32_t sidxb[MMA_TEAMS][2][MMA_NB];
   __shared__ unsigned long long team_slice[MMA_TEAMS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / MMA_R, r = warp - team * MMA_R;
@@ -318,14 +317,16 @@ k_degrid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t na
   const int64_t plane_sz = (int64_t)p.nu * p.nv;
   const double* gd = reinterpret_cast<const double*>(grid);
   const int cpart = g & 1;
+  const bool flat = r == 2 && !p.do_wgridding;
+  int buf = 0;
   // B fragments: cell (row 4r + ks/3, column class 4 (ks%3) + l3), plane q = 4 nt + (lane >> 3), part c = g & 1
   double gb[12][3];
 #pragma unroll
   for (int ks = 0; ks < 12; ++ks)
 #pragma unroll
     for (int n = 0; n < 3; ++n) gb[ks][n] = 0.0;
-  for (int v = ttid; v < MMA_ROWS - MMA_NB; v += 32 * MMA_R)
-    for (int t = 0; t < MMA_TS; ++t) st[team][MMA_NB + v][t] = 0.0;
+  for (int v = ttid; v < 2 * (MMA_ROWS - MMA_NB); v += 32 * MMA_R)
+    for (int t = 0; t < MMA_TS; ++t) stb[team][v & 1][MMA_NB + (v >> 1)][t] = 0.0;
   uint64_t cur = ~0ull;
   RunPos cp;
   cp.fast = false; cp.iu0 = cp.iv0 = cp.ip = cp.m0 = 0;
@@ -391,33 +392,34 @@ k_degrid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t na
     const int64_t kend = min(nact, (sl + 1) * MMA_SLICE);
     for (int64_t k0 = sl * MMA_SLICE; k0 < kend; k0 += MMA_NB) {
       const int nb = (int)min((int64_t)MMA_NB, kend - k0);
+      // lane <-> sample: run origin, the 12 taps of axis r; warp 0 also stages phase, weight and the output slot
+      double (*st)[MMA_TS] = stb[team][buf];
+      uint32_t* sidx = sidxb[team][buf];
+      buf ^= 1;
       uint64_t org = ~0ull;
-      if (r == 0) {  // lane <-> sample: phase, weight, output slot and the tap origins
-        double pc = 1.0, ps = 0.0, w = 0.0, sg = 1.0, x0[3] = {0.0, 0.0, 0.0};
-        uint32_t idx = 0;
-        if (lane < nb) {
-          const VisRec<double> rec = recs[k0 + lane];
-          org = pack_origin(rec.iu, rec.iv, rec.ip);
-          idx = rec.idx;
-          w = wgt ? wgt[rec.idx] : 1.0;
-          if (apply_phase) { pc = rec.pc; ps = rec.ps; }
+      double x0 = 0.5 - 0.5 * W, pcw = 0.0, psw = 0.0, sg = 1.0;  // lanes past the batch: finite rows
+      uint32_t idx = 0;
+      if (lane < nb) {
+        int32_t ipraw;
+        org = mma_rec(recs, k0 + lane, r, idx, ipraw, x0);
+        if (r == 0) {
           // out = w e^{-it} sum, conjugated for folded samples:
           //   re = w (sr pc + si ps), im = +-w (si pc - sr ps); slot 38 holds the sign
-          if (apply_phase && (rec.ip & REC_CONJ_BIT)) sg = -1.0;
-          x0[0] = rec.x0[0]; x0[1] = rec.x0[1]; x0[2] = rec.x0[2];
+          const double w = wgt ? wgt[idx] : 1.0;
+          pcw = w;
+          if (apply_phase) {
+            pcw = recs[k0 + lane].pc * w; psw = recs[k0 + lane].ps * w;
+            if (ipraw & REC_CONJ_BIT) sg = -1.0;
+          }
         }
-        st[team][lane][36] = pc * w;
-        st[team][lane][37] = ps * w;
-        st[team][lane][38] = sg;
-        sidx[team][lane] = idx;
-        x0s[team][lane][0] = x0[0]; x0s[team][lane][1] = x0[1]; x0s[team][lane][2] = x0[2];
-      } else if (lane < nb) {
-        uint32_t idx;
-        org = mma_origin(recs, k0 + lane, idx);
+      }
+      mma_taps_axis(W, flat, x0, &st[lane][12 * r], bscale, xs);
+      if (r == 0) {
+        *reinterpret_cast<double2*>(&st[lane][36]) = make_double2(pcw, psw);
+        st[lane][38] = sg;
+        sidx[lane] = idx;
       }
       const uint32_t starts = run_starts(org, cur, lane, nb);
-      team_sync(team, 32 * MMA_R);
-      mma_taps(p, x0s[team], st[team], MMA_NB, ttid, bscale, xs);
       team_sync(team, 32 * MMA_R);
       int a = 0;
       while (a < nb) {
@@ -435,7 +437,7 @@ k_degrid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t na
         const int b = seg_end(starts, a, nb);
         for (int v = a; v < b; v += 8) {
           const int s = v + g;  // this lane's sample in the A / D fragments
-          const double* tp = st[team][s];
+          const double* tp = st[s];
           double ku[4], kv[3];
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii) ku[ii] = tp[4 * r + ii];
@@ -466,13 +468,12 @@ k_degrid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t na
             const double pcw = tp[36], psw = tp[37];
             // l3 == 0 adds the real part, l3 == 1 the imaginary part
             const double val = l3 == 0 ? sr * pcw + si * psw : (si * pcw - sr * psw) * tp[38];
-            double2* dst = out_sorted ? (out_sorted + k0 + s) : (vis_out + sidx[team][s]);
+            double2* dst = out_sorted ? (out_sorted + k0 + s) : (vis_out + sidx[s]);
             atomicAdd(reinterpret_cast<double*>(dst) + l3, val);
           }
         }
         a = b;
       }
-      team_sync(team, 32 * MMA_R);
     }
   }
 }
