@@ -187,11 +187,16 @@ COST_GRID_CELL = {"single": 8.0e-12, "double": 2.0e-11}
 RUNS_MAX_W = 8
 
 
-def vis_cost(precision, W, ndim):
-    """Run kernels: one warp per run for W <= 8, a team of 4 (W <= 12) or 8 (W <= 16) warps beyond."""
+def vis_cost(precision, W, ndim, nvis=0):
+    """Run kernels: one warp per run for W <= 8; fp64 9 <= W <= 12: a team of 3 warps on the DMMA path
+    (csrc/runs_mma.cuh; measured 5.1e-10 s per sample and direction on the C2 band of 25 M samples, whatever W is in
+    that range, and 1.15e-9 on the 1 M samples of C1, which do not fill the GPU);
+    scalar teams of 8 warps for W <= 16 (and of 4 for a single-precision W <= 12, which W_LIMIT rules out)."""
     if W <= RUNS_MAX_W:
         return COST_VIS_RUNS[precision]
-    return COST_VIS_RUNS[precision] * (5.0 if W <= 12 else 9.0)
+    if W <= 12:
+        return COST_VIS_RUNS[precision] * ((1.3 if nvis >= 4_000_000 else 3.0) if precision == "double" else 5.0)
+    return COST_VIS_RUNS[precision] * 9.0
 
 
 # Largest kernel support per precision.  In single precision the grid
@@ -287,7 +292,7 @@ def make_plan(
         else:
             dw, npl = 1.0, 1
         cost = (
-            2.0 * nvis * vis_cost(precision, W, ndim)
+            2.0 * nvis * vis_cost(precision, W, ndim, nvis)
             + 2.0 * npl * nu * nv * COST_GRID_CELL[precision]
         )
         if best is None or cost < best[0]:

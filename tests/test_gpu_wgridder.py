@@ -107,7 +107,9 @@ def test_parity_with_dft_and_oracle(gpu, prec, eps, geom):
     # adjointness <Rx,y> = <x,R^H y>
     lhs = np.vdot(v.astype(np.complex128), (vis * wgt * act).astype(np.complex128)).real
     rhs = float((d.astype(np.float64) * p["img"]).sum())
-    assert abs(lhs - rhs) <= (1e-12 if prec == "double" else 2e-5) * abs(rhs)
+    # (fp64: the low-sigma plans the DMMA run kernels make attractive amplify the FFT round-off at the image corners
+    #  by 1/psihat ~ exp(beta - sqrt(beta^2 - (pi W / 2 sigma)^2)) ~ 300 at sigma = 1.25: 7e-12 measured)
+    assert abs(lhs - rhs) <= (2e-11 if prec == "double" else 2e-5) * abs(rhs)
     # same plan through the numpy restatement: CUDA kernels vs CPU restatement
     v_np = wg.dirty2vis_np(gp.plan, p["uvw"], p["freq"], p["img"], mask=p["mask"])
     d_np = wg.vis2dirty_np(gp.plan, p["uvw"], p["freq"], vis, wgt, p["mask"])
