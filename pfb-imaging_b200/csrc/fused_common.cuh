@@ -35,6 +35,9 @@ __device__ __forceinline__ bool in_window(int n, int lo, int len, int size) {
 }
 
 #define ROWS_MAX_THREADS 256
+#define ROWS_BIG_THREADS_F32 768  /* one CTA per SM: 85 registers */
+#define ROWS_BIG_THREADS_F64 512  /* 128 registers */
+#define ROWS_BIG_SMEM (113 * 1024)  /* beyond this only one row CTA fits an SM */
 #ifndef PFBG_ROWS_INV_INFLIGHT
 #define PFBG_ROWS_INV_INFLIGHT 3
 #endif

@@ -20,8 +20,11 @@
 // --------------------------------------------------------------------------- degrid direction
 // grid = (plane, image row), plane fastest: the CTAs sharing an image row (x, corr, nu table) are
 // co-resident, so those rows are read from DRAM once instead of once per plane.
-template <typename T, bool FAST = false>
-__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 2))
+// BIG: rows so long that only one CTA fits an SM (> 113 KB of shared memory: fp32 rows beyond 14 k cells, config 4):
+// three (fp32) / two (fp64) times the threads on the same transform, or 6 warps per SM would have to hide everything
+template <typename T, bool FAST = false, bool BIG = false>
+__global__ void __launch_bounds__(BIG ? (sizeof(T) == 4 ? ROWS_BIG_THREADS_F32 : ROWS_BIG_THREADS_F64) : ROWS_MAX_THREADS,
+                                  BIG ? 1 : (sizeof(T) == 4 ? 3 : 2))
 k_rows_fwd(GParams p, FusedTabs ft, const T* __restrict__ x, const T* __restrict__ beam, const T* __restrict__ corr,
            typename cplx_of<T>::type* __restrict__ grid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -245,8 +248,9 @@ k_cols_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* grid, typen
 // One CTA per (plane, image row): read the row (active window only), inverse FFT along v, apply the
 // conjugate w-screen to the ny kept outputs and add their real parts to the fp64 accumulation image
 // (RED.F64; CTAs of one row are adjacent in the grid, so the 32 KB image row stays in L2).
-template <typename T, bool FAST = false>
-__global__ void __launch_bounds__(ROWS_MAX_THREADS, (sizeof(T) == 4 ? 3 : 2))
+template <typename T, bool FAST = false, bool BIG = false>
+__global__ void __launch_bounds__(BIG ? (sizeof(T) == 4 ? ROWS_BIG_THREADS_F32 : ROWS_BIG_THREADS_F64) : ROWS_MAX_THREADS,
+                                  BIG ? 1 : (sizeof(T) == 4 ? 3 : 2))
 k_rows_inv(GParams p, FusedTabs ft, const typename cplx_of<T>::type* __restrict__ grid, double* __restrict__ accimg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx2<T>* s = reinterpret_cast<cx2<T>*>(smem_raw);

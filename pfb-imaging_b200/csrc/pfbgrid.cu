@@ -484,7 +484,11 @@ static int fused_setup_t(pfbg_plan* pl) {
   CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   CK(cudaFuncSetAttribute(k_rows_inv<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CK(cudaFuncSetAttribute(k_rows_fwd<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(k_rows_fwd<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  CK(cudaFuncSetAttribute(k_rows_inv<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   if constexpr (sizeof(T) == 4) {
+    CK(cudaFuncSetAttribute(k_rows_fwd<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    CK(cudaFuncSetAttribute(k_rows_inv<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     CK(cudaFuncSetAttribute(k_rows_fwd<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     CK(cudaFuncSetAttribute(k_rows_inv<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     CK(cudaFuncSetAttribute(k_rows_inv<T, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1323,8 +1327,14 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
   const int slot0 = pl->split_role == 2 ? g.nplanes - pl->split_nq : 0;  // logical plane held by slot 0
   C* stack = (C*)pl->grid.p - (int64_t)slot0 * g.nu * g.nv;
   auto k_rows = &k_rows_fwd<T, false>;
+  int rows_cap = ROWS_MAX_THREADS;
+  const bool rows_big = fft_smem_bytes<T>(g.nv) > (size_t)ROWS_BIG_SMEM && !getenv("PFBG_ROWS_SMALL");
+  if (rows_big) {
+    k_rows = &k_rows_fwd<T, false, true>;
+    rows_cap = sizeof(T) == 4 ? ROWS_BIG_THREADS_F32 : ROWS_BIG_THREADS_F64;
+  }
   if constexpr (sizeof(T) == 4) {
-    if (g.fast_screen) k_rows = &k_rows_fwd<T, true>;
+    if (g.fast_screen) k_rows = rows_big ? &k_rows_fwd<T, true, true> : &k_rows_fwd<T, true>;
   }
   bool rows_done = false;
   if constexpr (sizeof(T) == 4) {
@@ -1336,7 +1346,7 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
     }
   }
   if (!rows_done)
-    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap), fft_smem_bytes<T>(g.nv), s>>>(
         g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, stack);
   LAUNCHED();
   CK(cudaGetLastError());
@@ -1385,8 +1395,14 @@ static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, cons
     CK(cudaGetLastError());
   }
   auto k_rows = &k_rows_inv<T, false>;
+  int rows_cap = ROWS_MAX_THREADS;
+  const bool rows_big = fft_smem_bytes<T>(g.nv) > (size_t)ROWS_BIG_SMEM && !getenv("PFBG_ROWS_SMALL");
+  if (rows_big) {
+    k_rows = &k_rows_inv<T, false, true>;
+    rows_cap = sizeof(T) == 4 ? ROWS_BIG_THREADS_F32 : ROWS_BIG_THREADS_F64;
+  }
   if constexpr (sizeof(T) == 4) {
-    if (g.fast_screen) k_rows = &k_rows_inv<T, true>;
+    if (g.fast_screen) k_rows = rows_big ? &k_rows_inv<T, true, true> : &k_rows_inv<T, true>;
   }
   bool rows_done = false;
   if constexpr (sizeof(T) == 4) {
@@ -1397,7 +1413,7 @@ static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, cons
     }
   }
   if (!rows_done)
-    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, ROWS_MAX_THREADS), fft_smem_bytes<T>(g.nv), s>>>(
+    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap), fft_smem_bytes<T>(g.nv), s>>>(
         g, ft, stack, (double*)pl->accimg.p);
   LAUNCHED();
   CK(cudaGetLastError());
