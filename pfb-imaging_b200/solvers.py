@@ -54,6 +54,11 @@ def pcg(aop, b, x0=None, precond=None, tol=1e-5, maxit=500, minit=100, verbosity
         np.copyto(xprev, x)
         ap = aop(p)
         rho, pap = _dots(reduce, (r, y), (p, ap))
+        if rho == 0.0 and pap == 0.0:
+            # the residual cancelled EXACTLY (small masked systems converge in a couple of iterations and the loop
+            # runs on until ||x - xprev|| drops): the reference forms 0 / 0 here and returns NaNs; the iterate is
+            # already the solution
+            break
         alpha = rho / pap
         x += alpha * p
         r = r + alpha * ap
@@ -156,6 +161,8 @@ def pcg_device(apply_dev, b, x0=None, tol=1e-5, maxit=500, minit=100, verbosity=
     while (eps > tol or k < minit) and k < maxit and stalls < 5:
         apply_dev(ptr(p), ptr(ap), s)
         pap, pp = dot2(p, ap, p, p)
+        if rho == 0.0 and pap == 0.0:  # exact convergence: see pcg
+            break
         alpha = rho / pap
         axpby(x, 1.0, x, alpha, p)
         axpby(r, 1.0, r, alpha, ap)
