@@ -291,6 +291,13 @@ int pfbg_debug_fft1d(int32_t precision, int32_t device, int32_t n, int32_t batch
                      void* out, int32_t mode, int32_t inverse);
 
 /*
+ * Unit-test hook for the fp64 exponential-of-semicircle tap of the DMMA run kernels (csrc/runs_mma.cuh):
+ * out[i] = exp(beta (sqrt(1 - x[i]^2) - 1)) for n host values x in [-1, 1], evaluated by the kernels' own lean
+ * exp / rsqrt (the quantity ducc0 tabulates by piecewise polynomials; tests compare with numpy).
+ */
+int pfbg_debug_es_fast64(int32_t device, int64_t n, const double* x, double beta, double* out);
+
+/*
  * Unit-test hook for the fp32 pair engine (csrc/fft2.cuh) behind the TMA-fed column transforms: `batch` groups of
  * 2 np interleaved transforms of length n, in / out (batch, 2 np, n) complex64 on the host.  aos != 0: the first
  * stage reads the array-of-structures order the TMA unit delivers.

@@ -1278,8 +1278,12 @@ static int run_grid2img(pfbg_plan* pl, cudaStream_t s, const void* beam, const v
 
 // threads per CTA for a row transform: the multiple of 32 (<= cap, >= cap/2) that balances the
 // radix-16 stage best (n/16 butterflies)
-static int row_threads(int n, int cap) {
-  int nb = n / 16, best = cap;
+static int row_threads(int n, int cap, int radix = 16) {
+  if (const char* e = getenv("PFBG_ROW_THREADS")) {  // tuning hook
+    const int t = atoi(e);
+    if (t >= 32 && t <= cap && t % 32 == 0) return t;
+  }
+  int nb = n / radix, best = cap;
   double best_eff = 0.0;
   for (int t = cap; t >= cap / 2; t -= 32) {
     int per = (nb + t - 1) / t;
@@ -1346,7 +1350,7 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
     }
   }
   if (!rows_done)
-    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap), fft_smem_bytes<T>(g.nv), s>>>(
+    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap, sizeof(T) == 8 ? 8 : 16), fft_smem_bytes<T>(g.nv), s>>>(
         g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, stack);
   LAUNCHED();
   CK(cudaGetLastError());
@@ -1413,7 +1417,7 @@ static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, cons
     }
   }
   if (!rows_done)
-    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap), fft_smem_bytes<T>(g.nv), s>>>(
+    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap, sizeof(T) == 8 ? 8 : 16), fft_smem_bytes<T>(g.nv), s>>>(
         g, ft, stack, (double*)pl->accimg.p);
   LAUNCHED();
   CK(cudaGetLastError());
@@ -2198,6 +2202,30 @@ extern "C" int pfbg_debug_fft1d(int32_t precision, int32_t device, int32_t n, in
   CK(cudaSetDevice(device));
   return precision == PFBG_F32 ? debug_fft_t<float>(n, batch, in, out, mode, inverse)
                                : debug_fft_t<double>(n, batch, in, out, mode, inverse);
+}
+
+// unit-test hook: the lean fp64 ES tap of the DMMA run kernels (runs_mma.cuh) at n positions x in [-1, 1]
+__global__ void k_debug_es_fast64(const double* __restrict__ x, double beta, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = es_fast64(x[i], beta);
+}
+extern "C" int pfbg_debug_es_fast64(int32_t device, int64_t n, const double* x, double beta, double* out) {
+  if (!x || !out || n < 1) return fail(PFBG_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(device));
+  double *dx = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&dx, (size_t)n * 8));
+  cudaError_t e = cudaMalloc(&dout, (size_t)n * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_debug_es_fast64<<<(unsigned)((n + 255) / 256), 256>>>(dx, beta, n, dout);
+    LAUNCHED();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "debug_es_fast64: %s", cudaGetErrorString(e));
+  return PFBG_OK;
 }
 
 extern "C" int pfbg_debug_fft2(int32_t device, int32_t n, int32_t np, int32_t batch, const void* in, void* out,

@@ -30,6 +30,9 @@
                           4 rows x 4 consecutive slots of a half-warp operand load on distinct 8-byte banks */
 #define MMA_ROWS (MMA_NB + 8)  /* MMA steps may read (never use) up to 7 rows past the batch */
 #define MMA_SLICE 256
+#ifndef MMA_MINB
+#define MMA_MINB 5  /* resident 96-thread CTAs per SM the register budget is set for */
+#endif
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -128,7 +131,7 @@ __device__ __forceinline__ int run_shift(const RunPos& o, const RunPos& n) {
   return d < 12 ? d : 12;
 }
 
-__global__ void __launch_bounds__(MMA_R* MMA_TEAMS * 32, 5)
+__global__ void __launch_bounds__(MMA_R* MMA_TEAMS * 32, MMA_MINB)
 k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact, const double2* __restrict__ vis,
                 int64_t vis_rs, int64_t vis_cs, const double* __restrict__ wgt, double2* __restrict__ grid,
                 int vis_sorted, int apply_phase, unsigned long long* __restrict__ queue) {
@@ -301,7 +304,7 @@ k_grid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact
 
 // Degridding.  Taps are shared by the team (named barriers); the footprint of a run lives in the B fragments and only
 // the column classes that entered the footprint are fetched when the run origin moves along v.
-__global__ void __launch_bounds__(MMA_R* MMA_TEAMS * 32, 5)
+__global__ void __launch_bounds__(MMA_R* MMA_TEAMS * 32, MMA_MINB)
 k_degrid_runs_mma(GParams p, const VisRec<double>* __restrict__ recs, int64_t nact, const double2* __restrict__ grid,
                   const double* __restrict__ wgt, double2* __restrict__ vis_out, double2* __restrict__ out_sorted,
                   int apply_phase, unsigned long long* __restrict__ queue) {

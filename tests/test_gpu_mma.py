@@ -83,3 +83,22 @@ def test_mma_hessian_long_runs_and_tail_batches(gpu):
     assert rel_l2(h_mma, h_old) <= 1e-13
     assert rel_l2(h_mma, ref) <= 1e-12
     gp.close()
+
+
+@pytest.mark.parametrize("beta", [13.7, 16.4, 23.34, 31.0, 37.0])
+def test_lean_fp64_tap_against_numpy(gpu, beta):
+    """The taps of the DMMA kernels (a * rsqrt(a) + Cody-Waite exp, no special cases) against numpy's exp / sqrt over
+    the whole support, including both ends and the values next to them."""
+    import ctypes as C
+
+    from pfb_imaging_b200 import _lib
+
+    lib = _lib.load()
+    x = np.concatenate([np.linspace(-1.0, 1.0, 200001), [np.nextafter(1.0, 0.0), np.nextafter(-1.0, 0.0), 0.0],
+                        1.0 - np.logspace(-16, -1, 64)])
+    out = np.empty_like(x)
+    _lib.check(lib.pfbg_debug_es_fast64(0, x.size, x.ctypes.data_as(C.c_void_p), float(beta), out.ctypes.data_as(C.c_void_p)))
+    ref = np.exp(beta * (np.sqrt((1.0 - x) * (1.0 + x)) - 1.0))
+    rel = np.abs(out - ref) / ref
+    print(f"beta {beta}: max rel err {rel.max():.2e}")
+    assert rel.max() <= 2e-14  # ~ beta ulps; the requested accuracies end at 1e-10
