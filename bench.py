@@ -13,6 +13,12 @@ round-1 mode instead (every GPU owns a complete job, weak scaling).
 import argparse
 import json
 import os
+
+# The helper side of a plane offload spins on flags in device memory while the same GPU runs its own band on other
+# streams: every stream needs its own hardware queue, or the band's kernels line up behind a waiting helper kernel
+# (the default of 8 connections aliases streams).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import subprocess
 import sys
 import threading

@@ -16,7 +16,14 @@ Host logic only (lists and dicts); the device work is in ``libpfbgrid.so``.
 
 from __future__ import annotations
 
-from .wgridder import GridderPlan, SplitHelper
+import os
+
+# A helper's transform kernels spin on flags in device memory while the same GPU runs its own band on other streams:
+# give every stream its own hardware queue (the default of 8 connections aliases streams, and the band's kernels would
+# line up behind a waiting helper kernel).  Only effective when set before the CUDA context is created.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from .wgridder import GridderPlan, SplitHelper  # noqa: E402
 
 # cost model of one offloaded plane, relative to the owner's measured per-plane transform time: the helper's column
 # passes run against peer memory (NVLink sectors instead of L2 hits), and the first plane of an offload also pays
