@@ -187,13 +187,38 @@ COST_GRID_CELL = {"single": 8.0e-12, "double": 2.0e-11}
 RUNS_MAX_W = 8
 
 
+def fft_cost_factor(n, precision):
+    """Relative cost per cell of the fused shared-memory transforms for an axis of n = 2^a 3^b 5^c 7^d 11^e cells: one
+    pass over the data per radix stage (powers of two go three (fp64, radix 8) or four (fp32, radix 16) at a time),
+    odd radices cost more per pass.  Measured on the C2 geometry in fp64 (12 / 11 / 10 planes, ms per forward + inverse
+    pair): 5760 -> 13.5, 6144 -> 10.3, 6048 -> 15.2, 6720 -> 19.0, 7168 -> 15.6, i.e. 0.73 / 1.02 / 1.13 / 0.90 of the
+    per-cell cost at 5760; this model gives 0.78 / 1.13 / 1.03 / 0.97.  Normalised to the sizes COST_GRID_CELL was
+    measured at (fp32: 6144, fp64: 5760)."""
+    stage = {3: 1.0, 5: 1.4, 7: 2.2, 11: 3.5}
+    k = 3 if precision == "double" else 4
+    m, cost, a = int(n), 0.0, 0
+    while m % 2 == 0:
+        m //= 2
+        a += 1
+    cost += -(-a // k)
+    for pr, c in stage.items():
+        while m % pr == 0:
+            m //= pr
+            cost += c
+    if m != 1:
+        cost += 5.0 * math.log2(m)  # not a size the plan produces
+    return cost / (6.4 if precision == "double" else 4.0)
+
+
 def vis_cost(precision, W, ndim, nvis=0):
     """Run kernels: one warp per run for W <= 8; fp64 9 <= W <= 12: a team of 3 warps on the DMMA path
     (csrc/runs_mma.cuh; measured 5.1e-10 s per sample and direction on the C2 band of 25 M samples, whatever W is in
     that range, and 1.15e-9 on the 1 M samples of C1, which do not fill the GPU);
     scalar teams of 8 warps for W <= 16 (and of 4 for a single-precision W <= 12, which W_LIMIT rules out)."""
     if W <= RUNS_MAX_W:
-        return COST_VIS_RUNS[precision]
+        # W < 8 with w-gridding leaves the constant-stride / cyclic-column flush and fetch of the one-warp kernels for
+        # their general path (C1 in fp64, W = 7 against W = 8: degrid 1.18 against 0.40 ms, grid 0.74 against 0.47 ms)
+        return COST_VIS_RUNS[precision] * (2.0 if (W < RUNS_MAX_W and ndim == 3) else 1.0)
     if W <= 12:
         return COST_VIS_RUNS[precision] * ((1.3 if nvis >= 4_000_000 else 3.0) if precision == "double" else 5.0)
     return COST_VIS_RUNS[precision] * 9.0
@@ -294,6 +319,7 @@ def make_plan(
         cost = (
             2.0 * nvis * vis_cost(precision, W, ndim, nvis)
             + 2.0 * npl * nu * nv * COST_GRID_CELL[precision]
+            * 0.5 * (fft_cost_factor(nu, precision) + fft_cost_factor(nv, precision))
         )
         if best is None or cost < best[0]:
             best = (cost, s, W, beta, err, nu, nv, dw, npl, sig_eff)
