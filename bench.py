@@ -534,17 +534,31 @@ def run_ours(args, cfg):
     else:
         my_bands = list(job_bands) if nbands > 1 else [rank % 8]
 
-    bands = []
-    for b in my_bands:
+    def bind_band(b, **extra):
         d, cell, x = make_inputs(cfg, b)
         gp = W.plan_for(d["uvw"], d["freq"], npix_x=cfg["nx"], npix_y=cfg["nx"], pixsize_x=cell, pixsize_y=cell,
                         epsilon=cfg["epsilon"], flip_v=True, divide_by_n=False, precision=cfg["precision"],
                         mask=d["mask"], sigma_min=1.1, sigma_max=3.0, device=local,
-                        external_stack=bool(cfg.get("share_stack")))
+                        external_stack=bool(cfg.get("share_stack")), **extra)
         gp.bind_weights(d["wgt"])
         x_d = torch.from_numpy(x).to(dev)
-        bands.append(dict(b=b, d=d, cell=cell, x=x, gp=gp, x_d=x_d, out_d=torch.empty_like(x_d), info=gp.info(),
-                          wsum=float(d["wgt"].sum(dtype=np.float64)), nvis=d["uvw"].shape[0] * d["freq"].size))
+        return dict(b=b, d=d, cell=cell, x=x, gp=gp, x_d=x_d, out_d=torch.empty_like(x_d), info=gp.info(),
+                    wsum=float(d["wgt"].sum(dtype=np.float64)), nvis=d["uvw"].shape[0] * d["freq"].size)
+
+    bands = [bind_band(b) for b in my_bands]
+    if cfg.get("share_stack") and bands:
+        # the bands of this GPU take turns on one shared plane stack: a band whose cheapest plan needs a larger stack
+        # than what is left next to the bound data of all of them is planned again under that limit
+        # (make_plan(max_stack_bytes=))
+        torch.cuda.synchronize()
+        free_b, _tot = torch.cuda.mem_get_info(dev)
+        # (what the first Hessian apply still allocates per band: the bucket-ordered model visibilities)
+        limit = int(free_b) - sum(bd["nvis"] for bd in bands) * 2 * p - (6 << 30)
+        for i, bd in enumerate(bands):
+            if int(bd["info"]["grid_bytes"]) > limit:
+                bd["gp"].close()
+                del bd["x_d"], bd["out_d"]
+                bands[i] = bind_band(bd["b"], max_stack_bytes=limit)
     nvis_local = sum(bd["nvis"] for bd in bands)
     stream = torch.cuda.current_stream().cuda_stream
     arena = None

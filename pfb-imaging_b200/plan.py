@@ -236,7 +236,7 @@ def make_plan(
     *, nx, ny, pixsize_x, pixsize_y, center_x=0.0, center_y=0.0, epsilon,
     flip_u=False, flip_v=False, flip_w=False, do_wgridding=True, divide_by_n=True,
     sigma_min=1.1, sigma_max=2.6, precision="double", wmin=0.0, wmax=0.0, nvis=0,
-    force_sigma=None, force_W=None, safety=None, mirror=True,
+    force_sigma=None, force_W=None, safety=None, mirror=True, max_stack_bytes=None,
 ) -> Plan:
     """Choose (sigma, W, beta, nu, nv, planes) for one gridder geometry."""
     nx, ny = int(nx), int(ny)
@@ -321,6 +321,11 @@ def make_plan(
             + 2.0 * npl * nu * nv * COST_GRID_CELL[precision]
             * 0.5 * (fft_cost_factor(nu, precision) + fft_cost_factor(nv, precision))
         )
+        # `max_stack_bytes`: what the caller can spare for the plane stack (e.g. the bands of a GPU that share one
+        # stack next to everything else that is resident): candidates beyond it only win when nothing fits
+        stack = npl * nu * nv * (8 if precision == "single" else 16)
+        if max_stack_bytes is not None and stack > max_stack_bytes:
+            cost += 1e6 * (1.0 + stack / max_stack_bytes)
         if best is None or cost < best[0]:
             best = (cost, s, W, beta, err, nu, nv, dw, npl, sig_eff)
     if best is None:

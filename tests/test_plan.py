@@ -92,3 +92,18 @@ def test_batch_plan_gives_every_snapshot_its_own_plane_block():
         assert np.floor((lo - a) / plan.dw - plan.W / 2) + 1 >= 0
         assert np.floor((hi - a) / plan.dw - plan.W / 2) + 1 + plan.W <= n
     assert plan.nplanes_std == int(npl.sum())
+
+
+def test_max_stack_bytes_limits_the_plane_stack():
+    """make_plan(max_stack_bytes=): the cheapest plan that fits the budget; the smallest stack when nothing fits."""
+    kw = dict(nx=10240, ny=10240, pixsize_x=6e-6, pixsize_y=6e-6, epsilon=1e-5, precision="single", wmin=0.0, wmax=9000.0,
+              nvis=62_500_000, sigma_min=1.1, sigma_max=3.0)
+    free = make_plan(**kw)
+    stack = free.nplanes * free.nu * free.nv * 8
+    tight = make_plan(max_stack_bytes=int(0.9 * stack), **kw)
+    assert tight.nplanes * tight.nu * tight.nv * 8 <= 0.9 * stack
+    assert (tight.nu, tight.W) != (free.nu, free.W) or tight.nplanes < free.nplanes
+    same = make_plan(max_stack_bytes=2 * stack, **kw)
+    assert (same.nu, same.W, same.nplanes) == (free.nu, free.W, free.nplanes)
+    tiny = make_plan(max_stack_bytes=1, **kw)  # nothing fits: the smallest stack the accuracy allows
+    assert tiny.nplanes * tiny.nu * tiny.nv * 8 <= tight.nplanes * tight.nu * tight.nv * 8
