@@ -283,6 +283,22 @@ int pfbg_split_end(pfbg_plan* plan);
 int pfbg_plan_get_window(const pfbg_plan* plan, int32_t* window4);
 
 /*
+ * Visibilities and weights of one correlation behind diagonal Jones terms, as `pfb init` prepares them for the gridder.
+ * Replaces: pfb_imaging.utils.correlations._weight_data_impl / wgt_func / vis_func
+ * (src/pfb_imaging/utils/correlations.py:195-232):
+ *   wgt[r, f] = Re(w0 gp gq conj(gp) conj(gq)),  vis[r, f] = w0 gq v0 conj(gp),
+ *   gp = jones[row_t[r] * js_t + ant1[r] * js_a + f * js_c] (element strides of the complex Jones array), gq with ant2,
+ *   (v0, w0) = correlation 0 of data / weight (nrow, nchan, ncorr).  row_t[r] < 0: the row is in no time bin and
+ *   stays zero.  Products in the reference's order with every operation rounded separately: bit-identical to the
+ *   numba loop.  The per-Stokes variant (utils/weighting.py:274-468) needs radiomesh's generated expressions and is
+ *   not provided.  Host or device pointers (flags); host pointers: synchronous.
+ */
+int pfbg_weight_data_corr(int32_t precision, int32_t device, const void* data, const void* weight, const void* jones,
+                          const int32_t* row_t, const int32_t* ant1, const int32_t* ant2, int64_t nrow, int32_t nchan,
+                          int32_t ncorr, int64_t jones_elems, int64_t js_t, int64_t js_a, int64_t js_c, void* vis,
+                          void* wgt, uint32_t flags, void* stream);
+
+/*
  * Unit-test hook for the in-shared-memory FFT engine behind the fused plane transforms:
  * `batch` transforms of length n (2^a 3^b 5^c 7^d), complex of `precision`, host pointers.
  * mode 0 = decimation in frequency, 1 = decimation in time; inverse != 0 -> e^{+2 pi i nk/n}.

@@ -109,3 +109,24 @@ def l2_reweight(residual_vis, wgt, mask, dof, wgtp=None):
     out = np.array(wgt, copy=True)
     out *= (dof + 2) / (dof + ressq / ovar[:, None, None])  # :527-530
     return out
+
+
+def weight_data_corr(data, weight, jones, tbin_idx, tbin_counts, ant1, ant2):
+    """numpy restatement of utils/correlations.py:195-232 (`_weight_data_impl`, `wgt_func`, `vis_func`): one
+    correlation behind diagonal Jones terms, products in the reference's order."""
+    data, weight, jones = np.asarray(data), np.asarray(weight), np.asarray(jones)
+    nrow, nchan, _ = data.shape
+    start = np.asarray(tbin_idx) - np.min(tbin_idx)
+    row_t = np.full(nrow, -1)
+    for t in range(start.size):
+        row_t[start[t]:start[t] + tbin_counts[t]] = t
+    ok = row_t >= 0
+    vis = np.zeros((nrow, nchan), dtype=data.dtype)
+    wgt = np.zeros((nrow, nchan), dtype=data.real.dtype)
+    gp = jones[row_t[ok], np.asarray(ant1)[ok], :, 0, 0]
+    gq = jones[row_t[ok], np.asarray(ant2)[ok], :, 0, 0]
+    w0 = weight[ok][:, :, 0].astype(data.dtype)  # the real weight enters the products as a complex number
+    v0 = data[ok][:, :, 0]
+    wgt[ok] = (w0 * gp * gq * np.conjugate(gp) * np.conjugate(gq)).real
+    vis[ok] = w0 * gq * v0 * np.conjugate(gp)
+    return vis, wgt

@@ -2163,6 +2163,51 @@ extern "C" int pfbg_l2_reweight(int32_t precision, int32_t device, const void* r
   return PFBG_OK;
 }
 
+extern "C" int pfbg_weight_data_corr(int32_t precision, int32_t device, const void* data, const void* weight,
+                                     const void* jones, const int32_t* row_t, const int32_t* ant1, const int32_t* ant2,
+                                     int64_t nrow, int32_t nchan, int32_t ncorr, int64_t jones_elems, int64_t js_t,
+                                     int64_t js_a, int64_t js_c, void* vis, void* wgt, uint32_t flags, void* stream) {
+  if (!data || !weight || !jones || !row_t || !ant1 || !ant2 || !vis || !wgt) return fail(PFBG_ERR_ARG, "null argument");
+  if (nrow < 0 || nchan <= 0 || ncorr <= 0 || jones_elems <= 0) return fail(PFBG_ERR_ARG, "bad sizes");
+  if (precision != PFBG_F32 && precision != PFBG_F64) return fail(PFBG_ERR_ARG, "bad precision");
+  CK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool dev = flags & PFBG_DEVICE_PTRS;
+  const size_t rb = precision == PFBG_F32 ? 4 : 8;
+  const int64_t nvis = nrow * nchan;
+  TmpBufs t;
+  void *dd, *dw, *dj, *dt, *d1, *d2, *dv, *dg;
+  CKRC(t.get(&dd, data, (size_t)nvis * ncorr * 2 * rb, dev, true, s));
+  CKRC(t.get(&dw, weight, (size_t)nvis * ncorr * rb, dev, true, s));
+  CKRC(t.get(&dj, jones, (size_t)jones_elems * 2 * rb, dev, true, s));
+  CKRC(t.get(&dt, row_t, (size_t)nrow * 4, dev, true, s));
+  CKRC(t.get(&d1, ant1, (size_t)nrow * 4, dev, true, s));
+  CKRC(t.get(&d2, ant2, (size_t)nrow * 4, dev, true, s));
+  CKRC(t.get(&dv, vis, (size_t)nvis * 2 * rb, dev, false, s));
+  CKRC(t.get(&dg, wgt, (size_t)nvis * rb, dev, false, s));
+  CK(cudaMemsetAsync(dv, 0, (size_t)nvis * 2 * rb, s));
+  CK(cudaMemsetAsync(dg, 0, (size_t)nvis * rb, s));
+  if (nvis > 0) {
+    const unsigned grd = (unsigned)((nvis + 255) / 256);
+    if (precision == PFBG_F32)
+      k_weight_data_corr<float><<<grd, 256, 0, s>>>((const float2*)dd, (const float*)dw, (const float2*)dj, (const int32_t*)dt,
+                                                      (const int32_t*)d1, (const int32_t*)d2, nrow, nchan, ncorr, js_t, js_a, js_c,
+                                                      (float2*)dv, (float*)dg);
+    else
+      k_weight_data_corr<double><<<grd, 256, 0, s>>>((const double2*)dd, (const double*)dw, (const double2*)dj, (const int32_t*)dt,
+                                                       (const int32_t*)d1, (const int32_t*)d2, nrow, nchan, ncorr, js_t, js_a, js_c,
+                                                       (double2*)dv, (double*)dg);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (!dev) {
+      CK(cudaMemcpyAsync(vis, dv, (size_t)nvis * 2 * rb, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(wgt, dg, (size_t)nvis * rb, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  if (!dev) CK(cudaStreamSynchronize(s));
+  return PFBG_OK;
+}
+
 // ---------------------------------------------------------------------------
 // unit-test hook for the shared-memory FFT engine (fft.cuh)
 // ---------------------------------------------------------------------------

@@ -146,3 +146,62 @@ __global__ void k_l2_apply(const T* __restrict__ rv, const T* __restrict__ wgtp,
     w[k] = (T)((double)w[k] * (numer / (dof + (double)q / ov)));
   }
 }
+
+
+// ---------------------------------------------------------------------------
+// Visibility / weight preparation of one correlation behind diagonal Jones terms (`pfb init`,
+// utils/correlations.py:195-232): for row r of time bin t with antennas (p, q) and channel f
+//   wgt[r, f] = Re( w0 gp gq conj(gp) conj(gq) )        vis[r, f] = w0 gq v0 conj(gp)
+// with gp = jones[t, p, f, 0, 0], gq = jones[t, q, f, 0, 0], (v0, w0) = correlation 0 of data / weight.
+// The products are formed in the reference's order, every operation rounded on its own (no FMA contraction), so the
+// result is bit-identical to the numba loop.  HBM bound: (2 + ncorr) p + ... in, 3p out per sample.
+// ---------------------------------------------------------------------------
+template <typename T> struct wd_ops;
+template <> struct wd_ops<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+};
+template <> struct wd_ops<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+};
+template <typename T, typename C2>
+__device__ __forceinline__ C2 wd_cmul(C2 a, C2 b) {  // (ac - bd) + i (ad + bc), four products, two sums
+  using O = wd_ops<T>;
+  C2 r;
+  r.x = O::sub(O::mul(a.x, b.x), O::mul(a.y, b.y));
+  r.y = O::add(O::mul(a.x, b.y), O::mul(a.y, b.x));
+  return r;
+}
+
+template <typename T>
+__global__ void k_weight_data_corr(const typename cplx_of<T>::type* __restrict__ data, const T* __restrict__ weight,
+                                   const typename cplx_of<T>::type* __restrict__ jones, const int32_t* __restrict__ row_t,
+                                   const int32_t* __restrict__ ant1, const int32_t* __restrict__ ant2, int64_t nrow,
+                                   int nchan, int ncorr, int64_t js_t, int64_t js_a, int64_t js_c,
+                                   typename cplx_of<T>::type* __restrict__ vis, T* __restrict__ wgt) {
+  using C2 = typename cplx_of<T>::type;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrow * nchan) return;
+  const int64_t row = i / nchan;
+  const int chan = (int)(i - row * nchan);
+  const int t = row_t[row];
+  if (t < 0) return;  // a row outside every time bin keeps the zeros it was initialised with
+  const C2 gp = jones[t * js_t + ant1[row] * js_a + chan * js_c];
+  const C2 gq = jones[t * js_t + ant2[row] * js_a + chan * js_c];
+  const T w0 = weight[i * ncorr];
+  const C2 v0 = data[i * ncorr];
+  C2 w0c; w0c.x = w0; w0c.y = (T)0;  // the reference multiplies by the real weight as a complex number
+  const C2 gpc = {gp.x, -gp.y}, gqc = {gq.x, -gq.y};
+  C2 a = wd_cmul<T, C2>(w0c, gp);
+  a = wd_cmul<T, C2>(a, gq);
+  a = wd_cmul<T, C2>(a, gpc);
+  a = wd_cmul<T, C2>(a, gqc);
+  wgt[i] = a.x;
+  C2 b = wd_cmul<T, C2>(w0c, gq);
+  b = wd_cmul<T, C2>(b, v0);
+  b = wd_cmul<T, C2>(b, gpc);
+  vis[i] = b;
+}

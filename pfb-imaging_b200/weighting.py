@@ -160,3 +160,56 @@ def box_sum_counts(counts, npix_super):
     for c in range(counts.shape[0]):
         out[c] = uniform_filter(counts[c], size=size, mode="constant", cval=0.0) * (size * size)
     return out
+
+
+def weight_data_corr(data, weight, jones, tbin_idx, tbin_counts, ant1, ant2):
+    """Visibilities and weights of one correlation behind diagonal Jones terms: the body of
+    ``pfb_imaging.utils.correlations._weight_data_impl`` (``/root/reference/src/pfb_imaging/utils/correlations.py:
+    195-232``, what `pfb init` hands to the gridder for single-correlation products), same arguments and outputs:
+
+        data (nrow, nchan, ncorr) complex, weight (nrow, nchan, ncorr) real, jones (ntime, nant, nchan, ndir, ncorr_j)
+        complex [direction 0, correlation 0 are used], tbin_idx / tbin_counts (ntime) first row and length of every
+        time bin (any common offset), ant1 / ant2 (nrow)  ->  vis (nrow, nchan) complex, wgt (nrow, nchan) real
+
+        wgt = Re(w0 gp gq conj(gp) conj(gq)),   vis = w0 gq v0 conj(gp)
+
+    Runs on the device (``pfbg_weight_data_corr``), bit-identical to the numba loop.  Unlike the reference this does
+    not modify `tbin_idx` in place.  The per-Stokes ``utils.weighting.weight_data`` (:274-468) takes its expressions
+    from ``radiomesh.generated._stokes_expr``, which is not available here, and is not provided."""
+    data = np.asarray(data)
+    if data.ndim != 3 or data.dtype not in (np.complex64, np.complex128):
+        raise TypeError("data must be a complex64 / complex128 array of shape (nrow, nchan, ncorr)")
+    rdt = np.float32 if data.dtype == np.complex64 else np.float64
+    nrow, nchan, ncorr = data.shape
+    weight = np.asarray(weight)
+    if weight.shape != data.shape:
+        raise ValueError("weight shape does not match data")
+    jones = np.asarray(jones)
+    if jones.ndim != 5:
+        raise NotImplementedError("only diagonal Jones terms (ntime, nant, nchan, ndir, ncorr) are supported")
+    d = np.ascontiguousarray(data)
+    w = np.ascontiguousarray(weight, dtype=rdt)
+    j = np.ascontiguousarray(jones, dtype=data.dtype)
+    tbin_idx = np.asarray(tbin_idx, dtype=np.int64)
+    tbin_counts = np.asarray(tbin_counts, dtype=np.int64)
+    start = tbin_idx - (tbin_idx.min() if tbin_idx.size else 0)
+    row_t = np.full(nrow, -1, dtype=np.int32)
+    for t in range(start.size):  # later bins win where bins overlap, like the sequential loop of the reference
+        row_t[start[t]:start[t] + tbin_counts[t]] = t
+    a1 = np.ascontiguousarray(ant1, dtype=np.int32)
+    a2 = np.ascontiguousarray(ant2, dtype=np.int32)
+    if a1.shape != (nrow,) or a2.shape != (nrow,):
+        raise ValueError("ant1 / ant2 must have one entry per row")
+    nt, nant, nch_j, ndir, ncj = j.shape
+    if nch_j != nchan:
+        raise ValueError("jones and data disagree on the number of channels")
+    if nrow and (max(a1.max(), a2.max()) >= nant or row_t.max() >= nt):
+        raise ValueError("antenna or time index outside the Jones array")
+    vis = np.empty((nrow, nchan), dtype=data.dtype)
+    wgt = np.empty((nrow, nchan), dtype=rdt)
+    lib = _lib.load()
+    es = j.itemsize
+    _lib.check(lib.pfbg_weight_data_corr(_prec(rdt), current_device(), _p(d), _p(w), _p(j), _p(row_t), _p(a1), _p(a2), nrow,
+                                         nchan, ncorr, j.size, j.strides[0] // es, j.strides[1] // es, j.strides[2] // es,
+                                         _p(vis), _p(wgt), _lib.HOST_PTRS, None))
+    return vis, wgt
