@@ -791,9 +791,27 @@ def run_ours(args, cfg):
         torch.cuda.synchronize()
         ms64 = a0.elapsed_time(a1) / 5
         i64 = gp.info()
-        f64 = {"workload": cfg64["name"] + " (band 0)", "value": d["uvw"].shape[0] * d["freq"].size / (ms64 * 1e-3) / 1e6,
+        gp.set_profiling(True)
+        rec64 = []
+        for _ in range(3):
+            gp.hessian_dev(x_d.data_ptr(), None, ws, 0.0, o_d.data_ptr(), stream)
+            torch.cuda.synchronize()
+            rec64.append(gp.timings())
+        gp.set_profiling(False)
+        nv64 = d["uvw"].shape[0] * d["freq"].size
+        ph64 = dict(zip(["stage_in", "pad_screen_fft", "degrid", "zero_grid", "spread", "fft_crop_screen", "stage_out"],
+                        np.median(np.array(rec64), axis=0).tolist()))
+        # the run kernels of this path are DMMA m8n8k4 contractions (csrc/runs_mma.cuh): 13.5 DMMA of 256 FMAs per
+        # sample and direction; their roof is the fp64 rate of the tensor pipe (measured 37 TFLOP/s on B200)
+        dmma_floor_ms = nv64 * 13.5 * 512 / 37.0e12 * 1e3
+        f64 = {"workload": cfg64["name"] + " (band 0)", "value": nv64 / (ms64 * 1e-3) / 1e6,
                "unit": "Mvis/s", "ms_per_band": ms64, "dtype": "f64",
-               "plan": {k: i64[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "pmirror")}}
+               "plan": {k: i64[k] for k in ("W", "sigma", "nu", "nv", "nplanes", "pmirror")},
+               "phases_ms": ph64,
+               "run_kernels": "k_degrid_runs_mma / k_grid_runs_mma (FP64 tensor cores, DMMA m8n8k4)" if 9 <= i64["W"] <= 12
+                              else "scalar fp64 run kernels",
+               "dmma_floor_ms_per_direction": dmma_floor_ms,
+               "frac_of_dmma_roof": {"degrid": dmma_floor_ms / ph64["degrid"], "spread": dmma_floor_ms / ph64["spread"]}}
         gp.close()
         del x_d, o_d
 
