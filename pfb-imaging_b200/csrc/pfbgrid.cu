@@ -1276,6 +1276,15 @@ static int run_grid2img(pfbg_plan* pl, cudaStream_t s, const void* beam, const v
   return PFBG_OK;
 }
 
+// planes of a row pass that go through the pair engine: all of an even count, all but the last of an odd one
+// (PFBG_ROWS_ODD=pair keeps the last plane there too: A/B)
+static int rows_odd_split(int nq) {
+  if (!(nq & 1)) return nq;
+  const char* e = getenv("PFBG_ROWS_ODD");
+  if (e && strcmp(e, "pair") == 0) return nq;
+  return nq - 1;
+}
+
 // threads per CTA for a row transform: the multiple of 32 (<= cap, >= cap/2) that balances the
 // radix-16 stage best (n/16 butterflies)
 static int row_threads(int n, int cap, int radix = 16) {
@@ -1340,19 +1349,27 @@ static int run_fused_fwd(pfbg_plan* pl, cudaStream_t s, const void* x, const voi
   if constexpr (sizeof(T) == 4) {
     if (g.fast_screen) k_rows = rows_big ? &k_rows_fwd<T, true, true> : &k_rows_fwd<T, true>;
   }
-  bool rows_done = false;
+  // The pair engine transforms two planes per CTA; a last odd plane would cost a whole pair slot there, the one-plane
+  // kernel does it for ~0.55 of one (C2: 4 of the 8 bands have an odd plane count)
+  int nq2 = 0;  // planes that go through the pair engine
   if constexpr (sizeof(T) == 4) {
     if (pl->rows2) {
-      cudaError_t e = rows2_fwd_launch(g, ft, nq, g.fast_screen != 0, pl->rows_r8, (const float*)x, (const float*)beam,
-                                       (const float*)pl->corr.p, (float2*)stack, s);
-      if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "k_rows2_fwd launch: %s", cudaGetErrorString(e));
-      rows_done = true;
+      nq2 = rows_odd_split(nq);
+      if (nq2 > 0) {
+        cudaError_t e = rows2_fwd_launch(g, ft, nq2, g.fast_screen != 0, pl->rows_r8, (const float*)x, (const float*)beam,
+                                         (const float*)pl->corr.p, (float2*)stack, s);
+        if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "k_rows2_fwd launch: %s", cudaGetErrorString(e));
+        LAUNCHED();
+      }
     }
   }
-  if (!rows_done)
-    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap, sizeof(T) == 8 ? 8 : 16), fft_smem_bytes<T>(g.nv), s>>>(
-        g, ft, (const T*)x, (const T*)beam, (const T*)pl->corr.p, stack);
-  LAUNCHED();
+  if (nq2 < nq) {
+    FusedTabs ft1 = ft;
+    ft1.q0 = ft.q0 + nq2;
+    k_rows<<<dim3(nq - nq2, g.nx), row_threads(g.nv, rows_cap, sizeof(T) == 8 ? 8 : 16), fft_smem_bytes<T>(g.nv), s>>>(
+        g, ft1, (const T*)x, (const T*)beam, (const T*)pl->corr.p, stack);
+    LAUNCHED();
+  }
   CK(cudaGetLastError());
   const dim3 cgrid(ft.b_len / CC, nq);
   const size_t csm = fft_smem_bytes<T>(g.nu * CC);
@@ -1408,18 +1425,24 @@ static int run_fused_inv_acc(pfbg_plan* pl, cudaStream_t s, int q0, int nq, cons
   if constexpr (sizeof(T) == 4) {
     if (g.fast_screen) k_rows = rows_big ? &k_rows_inv<T, true, true> : &k_rows_inv<T, true>;
   }
-  bool rows_done = false;
+  int nq2 = 0;  // planes that go through the pair engine (see run_fused_fwd)
   if constexpr (sizeof(T) == 4) {
     if (pl->rows2) {
-      cudaError_t e = rows2_inv_launch(g, ft, nq, g.fast_screen != 0, pl->rows_r8, (const float2*)stack, (double*)pl->accimg.p, s);
-      if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "k_rows2_inv launch: %s", cudaGetErrorString(e));
-      rows_done = true;
+      nq2 = rows_odd_split(nq);
+      if (nq2 > 0) {
+        cudaError_t e = rows2_inv_launch(g, ft, nq2, g.fast_screen != 0, pl->rows_r8, (const float2*)stack, (double*)pl->accimg.p, s);
+        if (e != cudaSuccess) return fail(PFBG_ERR_CUDA, "k_rows2_inv launch: %s", cudaGetErrorString(e));
+        LAUNCHED();
+      }
     }
   }
-  if (!rows_done)
-    k_rows<<<dim3(nq, g.nx), row_threads(g.nv, rows_cap, sizeof(T) == 8 ? 8 : 16), fft_smem_bytes<T>(g.nv), s>>>(
-        g, ft, stack, (double*)pl->accimg.p);
-  LAUNCHED();
+  if (nq2 < nq) {
+    FusedTabs ft1 = ft;
+    ft1.q0 = ft.q0 + nq2;
+    k_rows<<<dim3(nq - nq2, g.nx), row_threads(g.nv, rows_cap, sizeof(T) == 8 ? 8 : 16), fft_smem_bytes<T>(g.nv), s>>>(
+        g, ft1, stack, (double*)pl->accimg.p);
+    LAUNCHED();
+  }
   CK(cudaGetLastError());
   return PFBG_OK;
 }
