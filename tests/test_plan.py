@@ -107,3 +107,20 @@ def test_max_stack_bytes_limits_the_plane_stack():
     assert (same.nu, same.W, same.nplanes) == (free.nu, free.W, free.nplanes)
     tiny = make_plan(max_stack_bytes=1, **kw)  # nothing fits: the smallest stack the accuracy allows
     assert tiny.nplanes * tiny.nu * tiny.nv * 8 <= tight.nplanes * tight.nu * tight.nv * 8
+
+
+def test_fft_cost_factor_orders_the_measured_sizes():
+    """The size model of the planner against the measured order of the fp64 transform sizes (per cell
+    6144 < 7168 < 5760 < 6048 < 6720) and its normalisation points."""
+    from pfb_imaging_b200.plan import fft_cost_factor as f
+
+    assert f(5760, "double") == pytest.approx(1.0) and f(6144, "single") == pytest.approx(1.0)
+    assert f(6144, "double") < f(7168, "double") < f(5760, "double") < f(6720, "double")
+    assert f(6144, "double") < 0.85 * f(5760, "double")
+    assert f(16384, "single") < f(15360, "single")  # config 4: the power of two wins per cell
+    # the C2 geometry in fp64 at eps 1e-7 lands on the 6144^2 grid (W = 11), in fp32 at 1e-5 it stays there (W = 8)
+    kw = dict(nx=4096, ny=4096, pixsize_x=1.2e-5, pixsize_y=1.2e-5, wmin=0.0, wmax=2000.0, nvis=25_000_000, sigma_min=1.1,
+              sigma_max=3.0)
+    p64 = make_plan(epsilon=1e-7, precision="double", **kw)
+    p32 = make_plan(epsilon=1e-5, precision="single", **kw)
+    assert (p64.nu, p64.W) == (6144, 11) and (p32.nu, p32.W) == (6144, 8)
